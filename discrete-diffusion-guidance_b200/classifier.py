@@ -1,0 +1,68 @@
+"""Guidance classifier for D-CBG: mirror of `classifier.Classifier`'s inference
+surface (reference classifier.py:132-216, 300-327, 484-490) over the
+`DITClassifier` backbone (models/dit.py:470-556)."""
+from __future__ import annotations
+
+import torch
+
+from . import weights
+from .dit import DIT
+
+
+class Classifier:
+
+  def __init__(self, config, tokenizer, device=None):
+    self.config = config
+    self.tokenizer = tokenizer
+    # classifier.py:151-156
+    self.vocab_size = tokenizer.vocab_size
+    if (not hasattr(tokenizer, 'mask_token') or tokenizer.mask_token is None):
+      self.mask_index = self.vocab_size
+      self.vocab_size += 1
+    else:
+      self.mask_index = tokenizer.mask_token_id
+    if config.classifier_backbone != 'dit':
+      raise NotImplementedError(
+        f'Classifier backbone {config.classifier_backbone} not implemented.')
+    self.classifier_model = DIT(config, vocab_size=self.vocab_size,
+                                device=device, classifier=True)
+    self.time_conditioning = config.time_conditioning
+    self.round_bf16 = True
+    self.chunk_sequences = 16384   # candidate sequences per classifier launch
+
+  def load_state_dict(self, state_dict, strict=True):
+    self.classifier_model.load_state_dict(state_dict,
+                                          prefix='classifier_model.')
+    return self
+
+  @classmethod
+  def load_from_checkpoint(cls, checkpoint_path, tokenizer, config,
+                           device=None, **_):
+    self = cls(config, tokenizer, device=device)
+    sd = weights.load_checkpoint_state(checkpoint_path, use_ema=False,
+                                       prefix='classifier_model.')
+    return self.load_state_dict(sd)
+
+  def eval(self):
+    return self
+
+  def to(self, device):
+    return self
+
+  def _process_sigma(self, sigma):
+    # classifier.py:484-490
+    if sigma.ndim > 1:
+      sigma = sigma.squeeze(-1)
+    if not self.time_conditioning:
+      sigma = torch.zeros_like(sigma)
+    assert sigma.ndim == 1, sigma.shape
+    return sigma
+
+  def get_log_probs(self, x, sigma, x_emb=None):
+    """classifier.py:316-327 for token ids (n, L) -> (n, classes) fp32."""
+    if x_emb is not None or x.ndim != 2:
+      raise NotImplementedError(
+        'one-hot / x_emb classifier inputs (first-order CBG, NOS) are not '
+        'implemented yet')
+    return self.classifier_model.classify(x, self._process_sigma(sigma),
+                                          round_bf16=self.round_bf16)

@@ -1,0 +1,344 @@
+// Bandwidth-bound pieces of the DiT forward (reference models/dit.py):
+// conditioning MLP, adaLN linears, gather + LayerNorm + modulate, weight casts,
+// the classifier head and the exact-CBG candidate generator.
+#include "ddg_common.cuh"
+
+namespace ddg {
+namespace {
+
+__device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
+
+// ---------------------------------------------------------------- cond_embed
+// One CTA per conditioning row (models/dit.py:155-213, 433-446); fp32.
+__global__ void cond_embed_kernel(const float* __restrict__ sigma, int sigma_row_stride,
+                                  const int32_t* __restrict__ step_ptr, int sigma_step_stride,
+                                  const int64_t* __restrict__ label, int cond_dim, int freq_dim,
+                                  const float* __restrict__ w0, const float* __restrict__ b0,
+                                  const float* __restrict__ w2, const float* __restrict__ b2,
+                                  const float* __restrict__ table, float* __restrict__ c_out) {
+  extern __shared__ float sm[];
+  float* emb = sm;              // freq_dim
+  float* h1 = sm + freq_dim;    // cond_dim
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+  if (sigma) {
+    const int step = step_ptr ? *step_ptr : 0;
+    const float t = sigma[(int64_t)r * sigma_row_stride + (int64_t)step * sigma_step_stride];
+    const int half = freq_dim / 2;
+    for (int k = tid; k < half; k += blockDim.x) {
+      // freqs = exp(-log(10000) * k / half)        models/dit.py:182-186
+      const float f = expf(-9.210340371976184f * (float)k / (float)half);
+      const float arg = t * f;
+      emb[k] = cosf(arg);
+      emb[half + k] = sinf(arg);
+    }
+    if ((freq_dim & 1) && tid == 0) emb[freq_dim - 1] = 0.f;
+    __syncthreads();
+    for (int o = warp; o < cond_dim; o += nwarp) {
+      float acc = 0.f;
+      for (int k = lane; k < freq_dim; k += 32) acc += w0[(int64_t)o * freq_dim + k] * emb[k];
+      acc = warp_sum(acc);
+      if (lane == 0) h1[o] = silu(acc + b0[o]);
+    }
+    __syncthreads();
+  }
+  for (int o = warp; o < cond_dim; o += nwarp) {
+    float c = 0.f;
+    if (sigma) {
+      float acc = 0.f;
+      for (int k = lane; k < cond_dim; k += 32) acc += w2[(int64_t)o * cond_dim + k] * h1[k];
+      acc = warp_sum(acc);
+      c = silu(acc + b2[o]);
+    }
+    if (label && lane == 0) c += silu(table[label[r] * cond_dim + o]);
+    if (lane == 0) c_out[(int64_t)r * cond_dim + o] = c;
+  }
+}
+
+// ---------------------------------------------------------------- adaLN
+// out[r, o] = round_T( sum_k round_T(c[r,k]) * round_T(W[o,k]) + round_T(b[o]) )
+// and round_T(1 + that) for the `scale` chunks.  One warp per output column,
+// looping over the (few) conditioning rows.
+template <typename T>
+__global__ void adaln_kernel(const float* __restrict__ c, int n_rows, int cond_dim,
+                             const float* __restrict__ w, const float* __restrict__ b, int n_out,
+                             int chunk, uint32_t one_plus_mask, int n_chunks,
+                             T* __restrict__ out, int64_t ld_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_out) return;
+  const int o = warp;
+  const bool plus1 = (one_plus_mask >> ((o / chunk) % n_chunks)) & 1u;
+  const float bias = Cvt<T>::round(b[o]);
+  for (int r = 0; r < n_rows; ++r) {
+    float acc = 0.f;
+    for (int k = lane; k < cond_dim; k += 32)
+      acc += Cvt<T>::round(c[(int64_t)r * cond_dim + k]) * Cvt<T>::round(w[(int64_t)o * cond_dim + k]);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float v = Cvt<T>::round(acc + bias);
+      if (plus1) v = Cvt<T>::round(1.f + v);
+      out[(int64_t)r * ld_out + o] = Cvt<T>::from_f32(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- LN + modulate
+// One warp per token row; hidden % 128 == 0, hidden <= 128 * MAXV.
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256)
+ln_modulate_kernel(float* __restrict__ x, int64_t rows, int hidden,
+                   const int64_t* __restrict__ ids, int64_t ids_period,
+                   const float* __restrict__ embedding,
+                   const float* __restrict__ ln_w, const T* __restrict__ shift,
+                   const T* __restrict__ ops, int64_t mod_stride, int64_t rows_per_mod,
+                   T* __restrict__ out) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = hidden >> 7;  // float4 per lane
+  float4 v[MAXV];
+  const float* src = ids ? embedding + ids[row % ids_period] * (int64_t)hidden : x + row * (int64_t)hidden;
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      v[i] = *reinterpret_cast<const float4*>(src + (i * 32 + lane) * 4);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  if (ids) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (i < nv) *reinterpret_cast<float4*>(x + row * (int64_t)hidden + (i * 32 + lane) * 4) = v[i];
+  }
+  const float mean = warp_sum(sum) / (float)hidden;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)hidden + 1e-5f);
+  const int64_t mrow = rows_per_mod > 0 ? row / rows_per_mod : 0;
+  const T* sh = shift ? shift + mrow * mod_stride : nullptr;
+  const T* sc = ops ? ops + mrow * mod_stride : nullptr;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 w4 = *reinterpret_cast<const float4*>(ln_w + col);
+      float y[4] = {(v[i].x - mean) * rstd * w4.x, (v[i].y - mean) * rstd * w4.y,
+                    (v[i].z - mean) * rstd * w4.z, (v[i].w - mean) * rstd * w4.w};
+      if (sh) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          y[e] = y[e] * Cvt<T>::to_f32(sc[col + e]) + Cvt<T>::to_f32(sh[col + e]);
+      }
+      T o4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o4[e] = Cvt<T>::from_f32(y[e]);
+      *reinterpret_cast<uint2*>(out + row * (int64_t)hidden + col) = *reinterpret_cast<uint2*>(o4);
+    }
+  }
+}
+
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = i; k < n; k += stride) dst[k] = Cvt<T>::from_f32(src[k]);
+}
+
+// ---------------------------------------------------------------- classifier head
+// mean over L -> Linear(h -> classes) -> log_softmax; one CTA per sequence.
+__global__ void __launch_bounds__(256)
+classifier_head_kernel(const float* __restrict__ x, int seq_len, int hidden,
+                       const float* __restrict__ w, const float* __restrict__ b, int n_classes,
+                       int round_bf16, float* __restrict__ log_probs) {
+  extern __shared__ float sm[];
+  float* mean = sm;               // hidden
+  float* logit = sm + hidden;     // n_classes
+  const int64_t n = blockIdx.x;
+  const float* xs = x + n * (int64_t)seq_len * hidden;
+  for (int col = threadIdx.x; col < hidden; col += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < seq_len; ++l) acc += xs[(int64_t)l * hidden + col];
+    mean[col] = acc / (float)seq_len;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int c = warp; c < n_classes; c += nwarp) {
+    float acc = 0.f;
+    for (int k = lane; k < hidden; k += 32) {
+      float a = mean[k], ww = w[(int64_t)c * hidden + k];
+      if (round_bf16) { a = bf16_round(a); ww = bf16_round(ww); }
+      acc += a * ww;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float bb = b[c];
+      if (round_bf16) bb = bf16_round(bb);
+      float v = acc + bb;
+      if (round_bf16) v = bf16_round(v);
+      logit[c] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = -INFINITY;
+    for (int c = 0; c < n_classes; ++c) m = fmaxf(m, logit[c]);
+    float s = 0.f;
+    for (int c = 0; c < n_classes; ++c) s += expf(logit[c] - m);
+    const float ls = logf(s);
+    for (int c = 0; c < n_classes; ++c) {
+      float v = (logit[c] - m) - ls;
+      if (round_bf16) v = bf16_round(v);
+      log_probs[n * n_classes + c] = v;
+    }
+  }
+}
+
+__global__ void cbg_candidates_kernel(const int64_t* __restrict__ xt, int seq_len, int vocab,
+                                      int64_t c0, int64_t n, int64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * seq_len) return;
+  const int64_t ci = i / seq_len;
+  const int pos = (int)(i % seq_len);
+  const int64_t c = c0 + ci;
+  const int64_t b = c / ((int64_t)seq_len * vocab);
+  const int l = (int)((c / vocab) % seq_len);
+  const int v = (int)(c % vocab);
+  out[i] = (pos == l) ? (int64_t)v : xt[b * seq_len + pos];
+}
+
+}  // namespace
+}  // namespace ddg
+
+using namespace ddg;
+
+extern "C" int ddg_cond_embed(const float* sigma, int32_t sigma_row_stride, const int32_t* step_ptr,
+                              int32_t sigma_step_stride, const int64_t* label, int32_t n,
+                              int32_t cond_dim, int32_t freq_dim, const float* w0, const float* b0,
+                              const float* w2, const float* b2, const float* label_table, float* c_out,
+                              ddg_stream_t stream) {
+  int rc = ddg_device_check();
+  if (rc) return rc;
+  DDG_REQUIRE(n >= 0 && cond_dim > 0 && c_out, DDG_ERR_INVALID, "cond_embed: bad args");
+  DDG_REQUIRE(sigma || label, DDG_ERR_INVALID, "cond_embed: need sigma or label");
+  if (sigma) DDG_REQUIRE(w0 && b0 && w2 && b2 && freq_dim > 0, DDG_ERR_INVALID, "cond_embed: null sigma_map weights");
+  if (label)
+    DDG_REQUIRE(label_table, DDG_ERR_INVALID,
+                "Conditioning variable provided, but Model was not initialized with condition embedding layer.");
+  if (n == 0) return DDG_OK;
+  const size_t smem = sizeof(float) * (size_t)(freq_dim + cond_dim);
+  cond_embed_kernel<<<n, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+    sigma, sigma_row_stride, step_ptr, sigma_step_stride, label, cond_dim, freq_dim, w0, b0, w2, b2,
+    label_table, c_out);
+  return check_cuda(cudaGetLastError(), "cond_embed launch");
+}
+
+extern "C" int ddg_adaln(const float* c, int32_t n_rows, int32_t cond_dim, const float* w, const float* b,
+                         int32_t n_out, int32_t dtype, int32_t chunk, uint32_t one_plus_mask,
+                         int32_t n_chunks, void* out, int64_t ld_out, ddg_stream_t stream) {
+  int rc = ddg_device_check();
+  if (rc) return rc;
+  DDG_REQUIRE(c && w && b && out && n_rows >= 0 && n_out > 0 && cond_dim > 0, DDG_ERR_INVALID, "adaln: bad args");
+  DDG_REQUIRE(chunk > 0 && n_chunks > 0 && n_chunks <= 32, DDG_ERR_INVALID, "adaln: bad chunking");
+  DDG_REQUIRE(ld_out >= n_out, DDG_ERR_INVALID, "adaln: ld_out < n_out");
+  if (n_rows == 0) return DDG_OK;
+  const int warps_per_cta = 8;
+  const unsigned grid = (unsigned)((n_out + warps_per_cta - 1) / warps_per_cta);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == DDG_F16)
+    adaln_kernel<__half><<<grid, 256, 0, s>>>(c, n_rows, cond_dim, w, b, n_out, chunk, one_plus_mask, n_chunks,
+                                              reinterpret_cast<__half*>(out), ld_out);
+  else if (dtype == DDG_BF16)
+    adaln_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(c, n_rows, cond_dim, w, b, n_out, chunk, one_plus_mask,
+                                                     n_chunks, reinterpret_cast<__nv_bfloat16*>(out), ld_out);
+  else {
+    set_error("adaln: dtype must be f16 or bf16");
+    return DDG_ERR_INVALID;
+  }
+  return check_cuda(cudaGetLastError(), "adaln launch");
+}
+
+extern "C" int ddg_ln_modulate(float* x, int64_t rows, int32_t hidden, const int64_t* ids,
+                               int64_t ids_period, const float* embedding, const float* ln_weight, const void* shift,
+                               const void* one_plus_scale, int64_t mod_stride, int64_t rows_per_mod,
+                               int32_t dtype, void* out, ddg_stream_t stream) {
+  int rc = ddg_device_check();
+  if (rc) return rc;
+  DDG_REQUIRE(x && ln_weight && out && rows >= 0, DDG_ERR_INVALID, "ln_modulate: bad args");
+  DDG_REQUIRE(hidden % 128 == 0 && hidden >= 128 && hidden <= 2048, DDG_ERR_UNSUPPORTED,
+              "ln_modulate: hidden=%d must be a multiple of 128 in [128, 2048]", hidden);
+  DDG_REQUIRE((shift == nullptr) == (one_plus_scale == nullptr), DDG_ERR_INVALID,
+              "ln_modulate: shift and one_plus_scale go together");
+  if (ids) DDG_REQUIRE(embedding && ids_period > 0, DDG_ERR_INVALID, "ln_modulate: ids without embedding/period");
+  if (rows == 0) return DDG_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+#define DDG_LN_LAUNCH(T, MAXV)                                                                      \
+  ln_modulate_kernel<T, MAXV><<<grid, 256, 0, s>>>(x, rows, hidden, ids, ids_period, embedding, ln_weight,      \
+                                                   reinterpret_cast<const T*>(shift),               \
+                                                   reinterpret_cast<const T*>(one_plus_scale),      \
+                                                   mod_stride, rows_per_mod, reinterpret_cast<T*>(out))
+  if (dtype == DDG_F16) {
+    if (hidden <= 1024) DDG_LN_LAUNCH(__half, 8); else DDG_LN_LAUNCH(__half, 16);
+  } else if (dtype == DDG_BF16) {
+    if (hidden <= 1024) DDG_LN_LAUNCH(__nv_bfloat16, 8); else DDG_LN_LAUNCH(__nv_bfloat16, 16);
+  } else {
+    set_error("ln_modulate: dtype must be f16 or bf16");
+    return DDG_ERR_INVALID;
+  }
+#undef DDG_LN_LAUNCH
+  return check_cuda(cudaGetLastError(), "ln_modulate launch");
+}
+
+extern "C" int ddg_cast(const float* src, void* dst, int64_t n, int32_t dtype, ddg_stream_t stream) {
+  int rc = ddg_device_check();
+  if (rc) return rc;
+  DDG_REQUIRE(src && dst && n >= 0, DDG_ERR_INVALID, "cast: bad args");
+  if (n == 0) return DDG_OK;
+  int64_t g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == DDG_F16) cast_kernel<__half><<<(unsigned)g, 256, 0, s>>>(src, reinterpret_cast<__half*>(dst), n);
+  else if (dtype == DDG_BF16)
+    cast_kernel<__nv_bfloat16><<<(unsigned)g, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  else {
+    set_error("cast: dtype must be f16 or bf16");
+    return DDG_ERR_INVALID;
+  }
+  return check_cuda(cudaGetLastError(), "cast launch");
+}
+
+extern "C" int ddg_classifier_head(const float* x, int32_t n, int32_t seq_len, int32_t hidden, const float* w,
+                                   const float* b, int32_t n_classes, int32_t round_bf16, float* log_probs,
+                                   ddg_stream_t stream) {
+  int rc = ddg_device_check();
+  if (rc) return rc;
+  DDG_REQUIRE(x && w && b && log_probs && n >= 0 && seq_len > 0 && hidden > 0 && n_classes > 0,
+              DDG_ERR_INVALID, "classifier_head: bad args");
+  if (n == 0) return DDG_OK;
+  const size_t smem = sizeof(float) * (size_t)(hidden + n_classes);
+  classifier_head_kernel<<<n, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+    x, seq_len, hidden, w, b, n_classes, round_bf16, log_probs);
+  return check_cuda(cudaGetLastError(), "classifier_head launch");
+}
+
+extern "C" int ddg_cbg_candidates(const int64_t* xt, int32_t seq_len, int32_t vocab, int64_t c0, int64_t n,
+                                  int64_t* ids_out, ddg_stream_t stream) {
+  int rc = ddg_device_check();
+  if (rc) return rc;
+  DDG_REQUIRE(xt && ids_out && seq_len > 0 && vocab > 0 && c0 >= 0 && n >= 0, DDG_ERR_INVALID,
+              "cbg_candidates: bad args");
+  if (n == 0) return DDG_OK;
+  const int64_t total = n * seq_len;
+  cbg_candidates_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    xt, seq_len, vocab, c0, n, ids_out);
+  return check_cuda(cudaGetLastError(), "cbg_candidates launch");
+}

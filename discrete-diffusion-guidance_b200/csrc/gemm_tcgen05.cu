@@ -1,0 +1,533 @@
+// tcgen05 / TMEM / TMA GEMM for the DiT linears (reference models/dit.py:284,
+// 312, 242-245, 359-366 -- there they are cuBLAS calls behind nn.Linear under
+// autocast).  out = epilogue(A[M,K] @ W[N,K]^T), 16-bit operands, fp32
+// accumulation in tensor memory.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0     TMA producer: A/W k-blocks -> 128B-swizzled smem ring (4 stages)
+//   warp 1     MMA issuer:   one thread issues tcgen05.mma 128x256x16, commits
+//                            stage-release and accumulator-ready mbarriers
+//   warp 2     TMEM allocator (512 columns = 2 accumulators of 128x256 fp32)
+//   warps 4-7  epilogue: tcgen05.ld accumulator -> registers -> fused epilogue
+//              (bias / GELU-tanh / rotary / gate+residual) -> global
+// The two TMEM accumulators let the epilogue of tile i overlap the MMAs of
+// tile i+1.
+#include <cuda.h>
+
+#include "ddg_common.cuh"
+
+namespace ddg {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;           // 64 x 16-bit = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int B_STAGE_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_THREADS = 128;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmParams {
+  void* out;
+  const void* bias;
+  const void* gate;
+  const void* rope_cos;
+  const void* rope_sin;
+  int64_t ld_out, gate_stride, rows_per_mod;
+  int M, N, K;
+  int seq_len, rope_cols;
+};
+
+// ------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+    "{\n\t"
+    ".reg .pred P1;\n\t"
+    "WAIT_LOOP:\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+    "@P1 bra.uni WAIT_DONE;\n\t"
+    "bra.uni WAIT_LOOP;\n\t"
+    "WAIT_DONE:\n\t"
+    "}" ::"r"(addr), "r"(parity)
+    : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+    ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+    : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, 128 x 256 x 16, 16-bit inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+    "{\n\t"
+    ".reg .pred p;\n\t"
+    "setp.ne.b32 p, %4, 0;\n\t"
+    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+    "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+    : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+    : "r"(taddr));
+}
+// The registers are listed as in/out operands so that no use of them can be
+// scheduled ahead of the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (PTX ISA "matrix
+// descriptor"): start>>4 | LBO(ignored for swizzled K-major)=1 | SBO = 8 rows
+// * 128 B = 1024 B | version 1 | layout SWIZZLE_128B (2).
+__device__ __forceinline__ uint64_t make_smem_desc(const void* p) {
+  const uint32_t addr = smem_u32(p);
+  uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A/B format (0 f16,
+// 1 bf16) at bits 7-9 / 10-12, both K-major, N>>3 at 17-22, M>>4 at 24-28.
+template <typename T> __host__ __device__ constexpr uint32_t make_idesc();
+template <> __host__ __device__ constexpr uint32_t make_idesc<__half>() {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+template <> __host__ __device__ constexpr uint32_t make_idesc<__nv_bfloat16>() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ 16-bit helpers
+template <typename T> struct H2;
+template <> struct H2<__half> {
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack(uint32_t w) {
+    return __half22float2(*reinterpret_cast<__half2*>(&w));
+  }
+};
+template <> struct H2<__nv_bfloat16> {
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack(uint32_t w) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+  }
+};
+
+// loads 32 consecutive 16-bit values (64 B, 16B-aligned) as fp32
+template <typename T>
+__device__ __forceinline__ void load32(const T* p, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p) + i);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = H2<T>::unpack(w[k]);
+      v[i * 8 + 2 * k] = f.x;
+      v[i * 8 + 2 * k + 1] = f.y;
+    }
+  }
+}
+
+// stores 32 fp32 values as 16-bit at out[0..32), columns >= n_valid dropped
+template <typename T>
+__device__ __forceinline__ void store32(T* out, const float (&v)[32], int n_valid) {
+  if (n_valid >= 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 r;
+      r.x = H2<T>::pack(v[i * 8 + 0], v[i * 8 + 1]);
+      r.y = H2<T>::pack(v[i * 8 + 2], v[i * 8 + 3]);
+      r.z = H2<T>::pack(v[i * 8 + 4], v[i * 8 + 5]);
+      r.w = H2<T>::pack(v[i * 8 + 6], v[i * 8 + 7]);
+      reinterpret_cast<uint4*>(out)[i] = r;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < n_valid) out[i] = Cvt<T>::from_f32(v[i]);
+  }
+}
+
+__device__ __forceinline__ float gelu_tanh(float v) {
+  // 0.5 v (1 + tanh(u)) == v * sigmoid(2u),  u = sqrt(2/pi) (v + 0.044715 v^3)
+  const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+  return __fdividef(v, 1.f + __expf(-2.f * u));
+}
+
+// ------------------------------------------------------------------ kernel
+template <typename T, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;   // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_THREADS); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * BM;
+        const int n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(&tma_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BK, m0);
+          tma_load_2d(&tma_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<T>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_a + stage * A_STAGE_BYTES);
+          const uint64_t bdesc = make_smem_desc(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle row
+            umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                     (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem stage when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);       // accumulator ready for the epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------ epilogue
+    const int ew = warp - EPI_WARP0;            // TMEM lanes 32*ew .. 32*ew+31
+    const int row_in_tile = ew * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * BM;
+      const int n0 = (tile % num_n) * BN;
+      const int m = m0 + row_in_tile;
+      const bool row_ok = m < p.M;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+
+      float cs[32], sn[32];
+      if (EPI == DDG_EPI_QKV_ROPE) {
+        const int pos = row_ok ? (m % p.seq_len) : 0;
+        load32<T>(reinterpret_cast<const T*>(p.rope_cos) + (int64_t)pos * 32, cs);
+        load32<T>(reinterpret_cast<const T*>(p.rope_sin) + (int64_t)pos * 32, sn);
+      }
+      const T* gate_row = nullptr;
+      if (EPI == DDG_EPI_GATE_RESIDUAL && p.gate) {
+        const int64_t mrow = row_ok ? (int64_t)m / p.rows_per_mod : 0;
+        gate_row = reinterpret_cast<const T*>(p.gate) + mrow * p.gate_stride;
+      }
+
+#pragma unroll 1
+      for (int g = 0; g < BN / 64; ++g) {
+        const int nc = n0 + g * 64;             // first column of this 64-wide group
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr + (uint32_t)(g * 64), r0);
+        tmem_ld32(taddr + (uint32_t)(g * 64 + 32), r1);
+        tmem_ld_wait(r0);
+        tmem_ld_wait(r1);
+        if (nc >= p.N) continue;                 // warp-uniform
+        float v0[32], v1[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v0[i] = __uint_as_float(r0[i]); v1[i] = __uint_as_float(r1[i]); }
+        if (p.bias) {
+          float b0[32], b1[32];
+          load32<T>(reinterpret_cast<const T*>(p.bias) + nc, b0);
+          load32<T>(reinterpret_cast<const T*>(p.bias) + nc + 32, b1);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v0[i] += b0[i]; v1[i] += b1[i]; }
+        }
+        // the GEMM output itself is a 16-bit tensor in the reference
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v0[i] = Cvt<T>::round(v0[i]); v1[i] = Cvt<T>::round(v1[i]); }
+
+        if (EPI == DDG_EPI_QKV_ROPE) {
+          if (nc < p.rope_cols) {
+            // NeoX rotary on one 64-wide head: (x1, x2) = (d < 32, d >= 32)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float x1 = v0[i], x2 = v1[i];
+              v0[i] = x1 * cs[i] - x2 * sn[i];
+              v1[i] = x1 * sn[i] + x2 * cs[i];
+            }
+          }
+        } else if (EPI == DDG_EPI_BIAS_GELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v0[i] = gelu_tanh(v0[i]); v1[i] = gelu_tanh(v1[i]); }
+        }
+
+        if (EPI == DDG_EPI_GATE_RESIDUAL) {
+          if (gate_row) {
+            float g0[32], g1[32];
+            load32<T>(gate_row + nc, g0);
+            load32<T>(gate_row + nc + 32, g1);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              v0[i] = Cvt<T>::round(g0[i] * v0[i]);
+              v1[i] = Cvt<T>::round(g1[i] * v1[i]);
+            }
+          }
+          if (row_ok) {
+            float* xr = reinterpret_cast<float*>(p.out) + (int64_t)m * p.ld_out + nc;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float* vv = h ? v1 : v0;
+              if (nc + h * 32 + 32 <= p.N) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float4 x4 = reinterpret_cast<float4*>(xr + h * 32)[i];
+                  x4.x += vv[4 * i]; x4.y += vv[4 * i + 1]; x4.z += vv[4 * i + 2]; x4.w += vv[4 * i + 3];
+                  reinterpret_cast<float4*>(xr + h * 32)[i] = x4;
+                }
+              } else {
+                for (int i = 0; i < 32; ++i)
+                  if (nc + h * 32 + i < p.N) xr[h * 32 + i] += vv[i];
+              }
+            }
+          }
+        } else {
+          if (row_ok) {
+            T* orow = reinterpret_cast<T*>(p.out) + (int64_t)m * p.ld_out + nc;
+            store32<T>(orow, v0, p.N - nc);
+            store32<T>(orow + 32, v1, p.N - nc - 32);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D K-major tensor map: dims {K, rows}, box {64, box_rows}, 128B swizzle, zero OOB fill.
+int make_tma_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t k, int64_t ld, int box_rows, int dtype) {
+  EncodeTiledFn fn = get_encode_fn();
+  DDG_REQUIRE(fn != nullptr, DDG_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dtype == DDG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DDG_REQUIRE(r == CUDA_SUCCESS, DDG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rows=%lld k=%lld ld=%lld", (int)r,
+              (long long)rows, (long long)k, (long long)ld);
+  return DDG_OK;
+}
+
+template <typename T, int EPI>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    DDG_CUDA(cudaFuncSetAttribute(gemm_kernel<T, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done[dev] = true;
+  }
+  const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  int grid = sm_count();
+  if (grid > num_tiles) grid = num_tiles;
+  gemm_kernel<T, EPI><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, p);
+  return check_cuda(cudaGetLastError(), "gemm launch");
+}
+
+template <typename T>
+int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case DDG_EPI_STORE: return launch_gemm<T, DDG_EPI_STORE>(ta, tb, p, s);
+    case DDG_EPI_QKV_ROPE: return launch_gemm<T, DDG_EPI_QKV_ROPE>(ta, tb, p, s);
+    case DDG_EPI_BIAS_GELU: return launch_gemm<T, DDG_EPI_BIAS_GELU>(ta, tb, p, s);
+    case DDG_EPI_GATE_RESIDUAL: return launch_gemm<T, DDG_EPI_GATE_RESIDUAL>(ta, tb, p, s);
+  }
+  set_error("gemm: bad epilogue %d", epi);
+  return DDG_ERR_INVALID;
+}
+
+}  // namespace
+}  // namespace ddg
+
+extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
+  using namespace ddg;
+  DDG_REQUIRE(args != nullptr, DDG_ERR_INVALID, "gemm: null args");
+  const ddg_gemm_args& a = *args;
+  int rc = ddg_device_check();
+  if (rc) return rc;
+  DDG_REQUIRE(a.M >= 0 && a.N > 0 && a.K > 0, DDG_ERR_INVALID, "gemm: bad sizes M=%d N=%d K=%d", a.M, a.N, a.K);
+  if (a.M == 0) return DDG_OK;
+  DDG_REQUIRE(a.a && a.w && a.out, DDG_ERR_INVALID, "gemm: null a/w/out");
+  DDG_REQUIRE(a.dtype == DDG_F16 || a.dtype == DDG_BF16, DDG_ERR_INVALID, "gemm: dtype must be f16 or bf16");
+  DDG_REQUIRE(a.K % 8 == 0 && a.lda % 8 == 0 && a.ldw % 8 == 0 && a.lda >= a.K && a.ldw >= a.K,
+              DDG_ERR_INVALID, "gemm: K, lda, ldw must be multiples of 8 (TMA 16-byte strides)");
+  DDG_REQUIRE(reinterpret_cast<uintptr_t>(a.a) % 16 == 0 && reinterpret_cast<uintptr_t>(a.w) % 16 == 0 &&
+              reinterpret_cast<uintptr_t>(a.out) % 16 == 0, DDG_ERR_INVALID, "gemm: a/w/out must be 16-byte aligned");
+  DDG_REQUIRE(a.ld_out >= a.N, DDG_ERR_INVALID, "gemm: ld_out < N");
+  if (a.epilogue == DDG_EPI_GATE_RESIDUAL)
+    DDG_REQUIRE(a.ld_out % 4 == 0, DDG_ERR_INVALID, "gemm: fp32 residual ld_out must be a multiple of 4");
+  else
+    DDG_REQUIRE(a.ld_out % 8 == 0, DDG_ERR_INVALID, "gemm: 16-bit ld_out must be a multiple of 8");
+  if (a.bias) DDG_REQUIRE(reinterpret_cast<uintptr_t>(a.bias) % 16 == 0, DDG_ERR_INVALID, "gemm: bias alignment");
+  if (a.epilogue == DDG_EPI_QKV_ROPE) {
+    DDG_REQUIRE(a.rope_cos && a.rope_sin && a.seq_len > 0 && a.head_dim == 64 && a.rope_cols % 64 == 0,
+                DDG_ERR_UNSUPPORTED, "gemm: rotary epilogue needs head_dim 64 and cos/sin tables");
+  }
+  if (a.epilogue == DDG_EPI_GATE_RESIDUAL && a.gate)
+    DDG_REQUIRE(a.rows_per_mod > 0 && a.gate_stride % 8 == 0 &&
+                reinterpret_cast<uintptr_t>(a.gate) % 16 == 0, DDG_ERR_INVALID, "gemm: gate layout");
+
+  CUtensorMap ta, tb;
+  rc = make_tma_2d(&ta, a.a, a.M, a.K, a.lda, BM, a.dtype);
+  if (rc) return rc;
+  rc = make_tma_2d(&tb, a.w, a.N, a.K, a.ldw, BN, a.dtype);
+  if (rc) return rc;
+  GemmParams p;
+  p.out = a.out; p.bias = a.bias; p.gate = a.gate; p.rope_cos = a.rope_cos; p.rope_sin = a.rope_sin;
+  p.ld_out = a.ld_out; p.gate_stride = a.gate_stride; p.rows_per_mod = a.rows_per_mod;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.seq_len = a.seq_len; p.rope_cols = a.rope_cols;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a.dtype == DDG_F16) return dispatch_epi<__half>(a.epilogue, ta, tb, p, s);
+  return dispatch_epi<__nv_bfloat16>(a.epilogue, ta, tb, p, s);
+}

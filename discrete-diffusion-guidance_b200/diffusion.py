@@ -1,0 +1,518 @@
+"""Reverse-diffusion sampler: host-side mirror of the reference `Diffusion`
+sampling surface (`diffusion.py:1040-1083, 1281-1624, 1738-1755`).
+
+Same constructor arguments, config keys, method names, argument meanings and
+error behaviour as the reference for the sampling path:
+`Diffusion(config, tokenizer)`, `.sample(eps)`, `._diffusion_sample(...)`,
+`._ddpm_denoise / ._cfg_denoise / ._cbg_denoise(...) -> (xs, q_xs, cache)`,
+`.forward(x, sigma, cond)`.  Underneath, each step is a handful of launches of
+the sm_100a kernels behind the C ABI: one DiT forward (the CFG cond/uncond pair
+batched into a single 2B-row forward), then ONE fused kernel that turns the
+logits into the next token ids.  `sample()` captures one step in a CUDA graph
+and replays it `sampling.steps` times with all per-step scalars read from
+device tables.
+"""
+from __future__ import annotations
+
+import typing
+
+import torch
+
+from . import _lib, config as config_lib, noise_schedule, weights
+from ._lib import check, lib, ptr, stream_ptr
+from .dit import DIT, ModSpec
+
+
+class Diffusion:
+
+  def __init__(self, config, tokenizer, device=None):
+    _lib.require_device()
+    self.config = config
+    self.tokenizer = tokenizer
+    self.device = torch.device(device if device is not None else 'cuda')
+    # diffusion.py:80-95
+    self.vocab_size = tokenizer.vocab_size
+    if (not hasattr(tokenizer, 'mask_token') or tokenizer.mask_token is None):
+      self.mask_index = self.vocab_size
+      self.vocab_size += 1
+    else:
+      self.mask_index = tokenizer.mask_token_id
+    self.parameterization = config.parameterization
+    self.diffusion = config.diffusion
+    if self.parameterization != 'ar' and self.diffusion not in (
+        'absorbing_state', 'uniform'):
+      raise NotImplementedError(
+        f'Diffusion type {self.diffusion} not implemented.')
+    self.T = config.T
+    self.subs_masking = config.subs_masking
+    self.time_conditioning = config.time_conditioning
+    config_lib.validate(config)
+    if config.backbone != 'dit':
+      raise NotImplementedError(
+        f'Backbone {config.backbone} not implemented.')
+    self.backbone = DIT(config, vocab_size=self.vocab_size, device=self.device)
+    self.noise = noise_schedule.get_noise(config)
+    self.neg_infinity = -1_000_000.0
+    self.classifier_model = None
+    self._classifier_path = None
+    # knobs that are not reference config keys
+    self.round_bf16 = True      # reproduce the reference's bf16 log-softmax/exp
+    self.fast_math = True       # ex2/lg2 intrinsics in the fused sampler
+    self.return_q_xs = False    # materialise q_xs (B, L, V) fp32 per step
+    self.use_cuda_graph = True
+    self.noise_fn = None        # i -> injected U (B, L, V); None -> Philox
+    self.prior_fn = None        # (B, L) -> injected prior ids
+    self.seed = int(config.get('seed', 1))
+    self._call_count = 0
+    self._loop = None
+
+  # ---------------------------------------------------------------- weights
+  def load_state_dict(self, state_dict, strict=True):
+    self.backbone.load_state_dict(state_dict, prefix='backbone.')
+    return self
+
+  @classmethod
+  def load_from_checkpoint(cls, checkpoint_path, tokenizer, config, **kw):
+    """`Diffusion.load_from_checkpoint` (main.py:39-47): EMA shadow params
+    are used unless `eval.disable_ema` (diffusion.py:1054-1055)."""
+    self = cls(config, tokenizer, **kw)
+    sd = weights.load_checkpoint_state(
+      checkpoint_path, use_ema=not config.eval.disable_ema)
+    return self.load_state_dict(sd)
+
+  def set_classifier(self, classifier_model):
+    self.classifier_model = classifier_model
+
+  def to(self, device):
+    return self
+
+  def eval(self):
+    return self
+
+  # ---------------------------------------------------------------- helpers
+  def _process_sigma(self, sigma):
+    # diffusion.py:339-348
+    if sigma is None:
+      assert self.parameterization == 'ar'
+      return sigma
+    if sigma.ndim > 1:
+      sigma = sigma.squeeze(-1)
+    if not self.time_conditioning:
+      sigma = torch.zeros_like(sigma)
+    assert sigma.ndim == 1, sigma.shape
+    return sigma
+
+  @property
+  def _mask_logit(self):
+    return self.parameterization == 'subs' or bool(self.subs_masking)
+
+  def _diffusion_code(self):
+    if self.parameterization == 'ar':
+      return _lib.AR
+    if self.diffusion == 'absorbing_state':
+      return _lib.ABSORBING
+    if self.diffusion == 'uniform':
+      return _lib.UNIFORM
+    raise NotImplementedError(
+      f'Diffusion type {self.diffusion} not implemented.')
+
+  def _select_code(self):
+    ev = self.config.get('eval') or {}
+    if ev.get('low_confidence_sampling', False):
+      raise NotImplementedError(
+        'eval.low_confidence_sampling is not implemented in the fused sampler')
+    return (_lib.SELECT_ARGMAX if ev.get('argmax_sampling', False)
+            else _lib.SELECT_RACE)
+
+  def _logits(self, x, sigma, cond=None):
+    """Backbone call of Diffusion.forward (diffusion.py:350-354): raw bf16
+    logits, shape (B, L, V) (strided view)."""
+    sigma = self._process_sigma(sigma)
+    return self.backbone.forward(x, sigma, cond)
+
+  def forward(self, x, sigma, cond=None, x_emb=None, **kwargs):
+    """Returns log-probs (B, L, V) fp32 like `Diffusion.forward`
+    (diffusion.py:350-365).  The sampling path never calls this: the fused
+    kernel consumes the raw logits."""
+    if x_emb is not None or kwargs:
+      raise NotImplementedError('x_emb / inference_params are not on the DiT sampling path')
+    logits = self._logits(x, sigma, cond)
+    B, L, V = logits.shape
+    ids = x.to(self.device, torch.int64).contiguous()
+    out = torch.empty(B, L, V, dtype=torch.float32, device=self.device)
+    check(lib.ddg_log_probs(
+      logits.data_ptr(), logits.stride(1), _lib.BF16, ptr(ids), B * L, V,
+      1 if self.parameterization == 'subs' else 0, 1 if self._mask_logit else 0,
+      self.mask_index, 1 if self.round_bf16 else 0, ptr(out), V, stream_ptr()))
+    return out
+
+  def _sample_prior(self, *batch_dims):
+    """diffusion.py:1006-1013 (uniform: in-kernel Philox randint)."""
+    if self.prior_fn is not None:
+      return self.prior_fn(*batch_dims).to(self.device, torch.int64).contiguous()
+    xt = torch.empty(*batch_dims, dtype=torch.int64, device=self.device)
+    check(lib.ddg_sample_prior(ptr(xt), xt.numel(), self._diffusion_code(),
+                               self.vocab_size, self.mask_index,
+                               self.seed + 7919 * self._call_count,
+                               stream_ptr()))
+    return xt
+
+  def _step_scalars(self, steps, eps):
+    """(sigma_t, move_chance_t, move_chance_s) per step, formed with the same
+    fp32 torch ops as `_diffusion_sample` (diffusion.py:1293-1323)."""
+    timesteps = torch.linspace(1, eps, steps + 1)
+    dt = (1 - eps) / steps
+    t = timesteps[:-1].clone()
+    if self.T > 0:
+      t = (t * self.T).to(torch.int)
+      t = t / self.T
+      t += (1 / self.T)
+    sigma_t = self.noise.total_noise(t)
+    sigma_s = self.noise.total_noise(t - dt)
+    return sigma_t, 1 - torch.exp(-sigma_t), 1 - torch.exp(-sigma_s)
+
+  def _launch_sampler(self, *, logits_a, ld_a, logits_b=None, ld_b=0, clf=None,
+                      noise=None, xt, xs, mc_t=None, mc_s=None, rows, seq_len,
+                      mc_seq_stride=0, mc_step_stride=0, step_ptr=None, step=0,
+                      guidance=_lib.GUIDE_NONE, gamma=1.0, q_out=None,
+                      select=None, diffusion=None, logits_dtype=_lib.BF16,
+                      seed_ptr=None):
+    V = self.vocab_size
+    a = _lib.SampleStepArgs(
+      logits_a=logits_a, logits_b=logits_b or 0, clf=ptr(clf), noise=ptr(noise),
+      xt=ptr(xt), mc_t=ptr(mc_t), mc_s=ptr(mc_s), step_ptr=ptr(step_ptr),
+      seed_ptr=ptr(seed_ptr), xs=ptr(xs), q_out=ptr(q_out), rows=rows, ld_a=ld_a, ld_b=ld_b,
+      ld_clf=V if clf is not None else 0,
+      ld_noise=(noise.stride(-2) if noise is not None else 0),
+      ld_q=V if q_out is not None else 0, seq_len=seq_len, vocab=V,
+      mc_seq_stride=mc_seq_stride, mc_step_stride=mc_step_stride,
+      logits_dtype=logits_dtype,
+      diffusion=self._diffusion_code() if diffusion is None else diffusion,
+      guidance=guidance, subs=1 if self.parameterization == 'subs' else 0,
+      mask_logit=1 if self._mask_logit else 0, mask_index=self.mask_index,
+      round_bf16=1 if self.round_bf16 else 0,
+      select=self._select_code() if select is None else select,
+      fast_math=1 if (self.fast_math and noise is None) else 0,
+      gamma=float(gamma), seed=self.seed + 7919 * self._call_count,
+      step=int(step), reserved=0)
+    check(lib.ddg_sample_step(a, stream_ptr()))
+
+  def _mc(self, mc):
+    return mc.to(self.device, torch.float32).reshape(-1).contiguous()
+
+  def _step_noise(self, B, L):
+    if self.noise_fn is None:
+      return None
+    U = self.noise_fn(self._step_index).to(self.device, torch.float32)
+    return U.reshape(B * L, self.vocab_size).contiguous()
+
+  _step_index = 0
+
+  # ---------------------------------------------------------------- per step
+  def _ddpm_denoise(self, xt, time_conditioning, move_chance_t, move_chance_s,
+                    cache=None):
+    """diffusion.py:1378-1420 -> (xs, q_xs | None, cache)."""
+    if self.config.sampling.get('use_float64', False):
+      raise NotImplementedError('sampling.use_float64 is not implemented')
+    B, L = xt.shape
+    xt = xt.to(self.device, torch.int64).contiguous()
+    logits = (cache['log_x_theta'] if cache is not None
+              else self._logits(xt, time_conditioning, None))
+    xs = torch.empty_like(xt)
+    q = (torch.empty(B, L, self.vocab_size, dtype=torch.float32, device=self.device)
+         if self.return_q_xs else None)
+    mct, mcs = self._mc(move_chance_t), self._mc(move_chance_s)
+    self._launch_sampler(
+      logits_a=logits.data_ptr(), ld_a=logits.stride(1), xt=xt, xs=xs, mc_t=mct,
+      mc_s=mcs, rows=B * L, seq_len=L, mc_seq_stride=1 if mct.numel() > 1 else 0,
+      noise=self._step_noise(B, L), q_out=q, step=self._step_index)
+    return xs, q, {'log_x_theta': logits}
+
+  def _cfg_denoise(self, cond, gamma, xt, time_conditioning, move_chance_t,
+                   move_chance_s, cache=None):
+    """diffusion.py:1422-1509 -> (xs, q_xs | None, cache).  gamma == 0 / 1 run
+    one forward; otherwise cond and uncond are one batched 2B-row forward."""
+    B, L = xt.shape
+    xt = xt.to(self.device, torch.int64).contiguous()
+    cond = cond.to(self.device, torch.int64)
+    mask_cond = torch.ones_like(cond) * self.config.data.num_classes
+    lc = lu = None
+    if cache is not None:
+      lu, lc = cache['log_x_theta_uncond'], cache['log_x_theta_cond']
+    elif gamma == 0.0:
+      lu = self._logits(xt, time_conditioning, mask_cond)
+    elif gamma == 1.0:
+      lc = self._logits(xt, time_conditioning, cond)
+    else:
+      sigma = self._process_sigma(time_conditioning).to(self.device, torch.float32)
+      mod = ModSpec(n_mod=2 * B, seqs_per_mod=1, sigma=torch.cat([sigma, sigma]),
+                    sigma_row_stride=1, labels=torch.cat([cond, mask_cond]))
+      buf = self.backbone.alloc_logits(2 * B * L)
+      self.backbone.run(xt, 2 * B, L, mod, buf, ids_period=B * L)
+      both = buf.view(2, B, L, self.backbone.vocab_ld)[..., :self.vocab_size]
+      lc, lu = both[0], both[1]
+    xs = torch.empty_like(xt)
+    q = (torch.empty(B, L, self.vocab_size, dtype=torch.float32, device=self.device)
+         if self.return_q_xs else None)
+    mct, mcs = self._mc(move_chance_t), self._mc(move_chance_s)
+    common = dict(xt=xt, xs=xs, mc_t=mct, mc_s=mcs, rows=B * L, seq_len=L,
+                  mc_seq_stride=1 if mct.numel() > 1 else 0,
+                  noise=self._step_noise(B, L), q_out=q, step=self._step_index)
+    if lc is None or lu is None:
+      one = lu if lu is not None else lc
+      self._launch_sampler(logits_a=one.data_ptr(), ld_a=one.stride(1), **common)
+    else:
+      self._launch_sampler(logits_a=lc.data_ptr(), ld_a=lc.stride(1),
+                           logits_b=lu.data_ptr(), ld_b=lu.stride(1),
+                           guidance=_lib.GUIDE_CFG, gamma=gamma, **common)
+    return xs, q, {'log_x_theta_uncond': lu, 'log_x_theta_cond': lc}
+
+  def _classifier_term(self, classifier_model, xt, time_conditioning,
+                       conditioning_class, use_approx):
+    """(B, L, V) fp32 classifier log-prob term of D-CBG."""
+    if use_approx:
+      raise NotImplementedError(
+        'guidance.use_approx (first-order D-CBG) needs the classifier '
+        'backward; not implemented yet')
+    # exact: every single-token edit of xt (diffusion.py:1549-1585), generated
+    # chunk by chunk on the device and never materialised as a whole.
+    B, L = xt.shape
+    V = self.vocab_size
+    total = B * L * V
+    term = torch.empty(total, dtype=torch.float32, device=self.device)
+    sigma = self._process_sigma(time_conditioning).to(self.device, torch.float32)
+    chunk = max(L * V, (classifier_model.chunk_sequences // (L * V)) * (L * V))
+    for c0 in range(0, total, chunk):
+      n = min(chunk, total - c0)
+      ids = torch.empty(n, L, dtype=torch.int64, device=self.device)
+      check(lib.ddg_cbg_candidates(ptr(xt), L, V, c0, n, ptr(ids), stream_ptr()))
+      b0, b1 = c0 // (L * V), (c0 + n) // (L * V)
+      sig = sigma[b0:b1].repeat_interleave(L * V)
+      lp = classifier_model.get_log_probs(ids, sig)
+      term[c0:c0 + n] = lp[:, conditioning_class]
+    return term.view(B, L, V)
+
+  def _cbg_denoise(self, conditioning_class, gamma, classifier_model, xt,
+                   time_conditioning, move_chance_t, move_chance_s,
+                   use_approx=False, cache=None):
+    """diffusion.py:1511-1624 -> (xs, guided_probs | None, cache)."""
+    B, L = xt.shape
+    xt = xt.to(self.device, torch.int64).contiguous()
+    if cache is not None:
+      logits, term = cache['log_x_theta'], cache['classifier_log_prob']
+    else:
+      logits = self._logits(xt, time_conditioning, None)
+      term = self._classifier_term(classifier_model, xt, time_conditioning,
+                                   conditioning_class, use_approx)
+    xs = torch.empty_like(xt)
+    q = (torch.empty(B, L, self.vocab_size, dtype=torch.float32, device=self.device)
+         if self.return_q_xs else None)
+    mct, mcs = self._mc(move_chance_t), self._mc(move_chance_s)
+    self._launch_sampler(
+      logits_a=logits.data_ptr(), ld_a=logits.stride(1), clf=term.contiguous(),
+      xt=xt, xs=xs, mc_t=mct, mc_s=mcs, rows=B * L, seq_len=L,
+      mc_seq_stride=1 if mct.numel() > 1 else 0, noise=self._step_noise(B, L),
+      q_out=q, guidance=_lib.GUIDE_CBG, gamma=gamma, step=self._step_index)
+    return xs, q, {'log_x_theta': logits, 'classifier_log_prob': term}
+
+  # ---------------------------------------------------------------- loops
+  @torch.no_grad()
+  def _diffusion_sample(self, classifier_model=None, cond=None, eps=1e-5):
+    """diffusion.py:1281-1376.  Philox noise + no diagnostics -> one captured
+    step replayed `steps` times; injected noise -> eager per-step calls."""
+    B = self.config.sampling.batch_size
+    L = self.config.model.length
+    steps = self.config.sampling.steps
+    guidance = self.config.get('guidance')
+    method = None if guidance is None else guidance.method
+    if method not in (None, 'cfg', 'cbg'):
+      raise NotImplementedError(f'Guidance method {method} not implemented.')
+    xt = self._sample_prior(B, L)
+    sigma_t, mc_t, mc_s = self._step_scalars(steps, eps)
+    if self.noise_fn is not None or self.return_q_xs or method == 'cbg' \
+        or not self.use_cuda_graph:
+      return self._eager_loop(xt, sigma_t, mc_t, mc_s, method, guidance,
+                              classifier_model, cond)
+    loop = self._get_loop(B, L, method, guidance)
+    return loop.run(xt, sigma_t, mc_t, mc_s, cond)
+
+  def _eager_loop(self, xt, sigma_t, mc_t, mc_s, method, guidance,
+                  classifier_model, cond):
+    B = xt.shape[0]
+    dev = self.device
+    for i in range(sigma_t.numel()):
+      self._step_index = i
+      sig = sigma_t[i].to(dev).expand(B)
+      mct = mc_t[i].to(dev).expand(B)[:, None, None]
+      mcs = mc_s[i].to(dev).expand(B)[:, None, None]
+      if method is None:
+        xt, _, _ = self._ddpm_denoise(xt, sig, mct, mcs)
+      elif method == 'cfg':
+        xt, _, _ = self._cfg_denoise(cond, guidance.gamma, xt, sig, mct, mcs)
+      else:
+        xt, _, _ = self._cbg_denoise(
+          guidance.condition, guidance.gamma, classifier_model, xt, sig, mct,
+          mcs, use_approx=guidance.get('use_approx', False))
+    self._step_index = 0
+    return xt
+
+  def _get_loop(self, B, L, method, guidance):
+    gamma = None if guidance is None else float(guidance.gamma)
+    key = (B, L, method, gamma, self.round_bf16, self.fast_math)
+    if self._loop is None or self._loop.key != key:
+      self._loop = _GraphLoop(self, B, L, method, gamma, key)
+    return self._loop
+
+  def sample(self, eps=1e-5):
+    """`Diffusion.sample` (diffusion.py:1040-1083) -> (batch, length) int64."""
+    guidance = self.config.get('guidance')
+    classifier_model, cond = None, None
+    if guidance is not None:
+      if guidance.method == 'cfg':
+        cond = (torch.ones(self.config.sampling.batch_size, device=self.device)
+                * guidance.condition).to(torch.long)
+      if guidance.method in ('cbg', 'nos', 'fudge', 'pplm'):
+        classifier_model = self._get_classifier(guidance)
+    self._call_count += 1
+    if self.parameterization == 'ar':
+      return self._ar_sample(classifier_model=classifier_model, cond=cond)
+    return self._diffusion_sample(classifier_model=classifier_model, cond=cond,
+                                  eps=eps)
+
+  def _get_classifier(self, guidance):
+    if self.classifier_model is not None:
+      return self.classifier_model
+    from .classifier import Classifier   # loaded once, not per sample() call
+    path = guidance.classifier_checkpoint_path
+    self.classifier_model = Classifier.load_from_checkpoint(
+      path, tokenizer=self.tokenizer, config=self.config, device=self.device)
+    return self.classifier_model
+
+  @torch.no_grad()
+  def _ar_sample(self, classifier_model=None, cond=None):
+    """diffusion.py:1085-1186 (+ _ar_cfg_denoise :1188-1236) for the DiT
+    backbone.  The reference re-encodes the growing prefix; with causal
+    attention a fixed full-length forward gives the same row i, so every step
+    has one shape."""
+    guidance = self.config.get('guidance')
+    method = None if guidance is None else guidance.method
+    if method not in (None, 'cfg'):
+      raise NotImplementedError(f'Guidance method {method} not implemented.')
+    B = self.config.sampling.batch_size
+    L = self.config.model.length
+    V, ld = self.vocab_size, self.backbone.vocab_ld
+    x = torch.zeros(B, L, dtype=torch.int64, device=self.device)
+    x[:, 0] = self.tokenizer.bos_token_id
+    two = method == 'cfg' and guidance.gamma not in (0.0, 1.0)
+    n_fwd = 2 if two else 1
+    buf = self.backbone.alloc_logits(n_fwd * B * L)
+    y = torch.empty(B, dtype=torch.int64, device=self.device)
+    labels = None
+    if method == 'cfg':
+      mask_cond = torch.ones_like(cond) * self.config.data.num_classes
+      labels = (torch.cat([cond, mask_cond]) if two
+                else (mask_cond if guidance.gamma == 0.0 else cond))
+    mod = ModSpec(n_mod=n_fwd * B, seqs_per_mod=1, labels=labels)
+    for i in range(L - 1):
+      self.backbone.run(x, n_fwd * B, L, mod, buf, ids_period=B * L)
+      noise = None
+      if self.noise_fn is not None:
+        noise = self.noise_fn(i).to(self.device, torch.float32).contiguous()
+      self._launch_sampler(
+        logits_a=buf.data_ptr() + i * ld * 2, ld_a=L * ld,
+        logits_b=(buf.data_ptr() + (B * L + i) * ld * 2) if two else None,
+        ld_b=L * ld if two else 0, noise=noise, xt=y, xs=y, rows=B, seq_len=1,
+        guidance=_lib.GUIDE_CFG if two else _lib.GUIDE_NONE,
+        gamma=guidance.gamma if two else 1.0, diffusion=_lib.AR,
+        select=_lib.SELECT_GUMBEL, step=i)
+      x[:, i + 1] = y
+    return x
+
+
+class _GraphLoop:
+  """One reverse step captured in a CUDA graph.  Per-step scalars live in
+  device tables indexed by a device-side step counter that the last node of
+  the graph increments, so the same graph is replayed for every step."""
+
+  def __init__(self, model: Diffusion, B, L, method, gamma, key):
+    self.key = key
+    self.model = model
+    self.B, self.L = B, L
+    self.method = method
+    self.gamma = gamma
+    self.two = method == 'cfg' and gamma not in (0.0, 1.0)
+    self.n_fwd = 2 if self.two else 1
+    dev = model.device
+    self.xt = torch.empty(B, L, dtype=torch.int64, device=dev)
+    self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+    self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)  # Philox key
+    self.logits = model.backbone.alloc_logits(self.n_fwd * B * L)
+    self.labels = (torch.zeros(self.n_fwd, dtype=torch.int64, device=dev)
+                   if method == 'cfg' else None)
+    self.tables = None
+    self.graph = None
+    self.steps = 0
+
+  def _body(self):
+    m, B, L = self.model, self.B, self.L
+    sig, mct, mcs = self.tables
+    mod = ModSpec(n_mod=self.n_fwd, seqs_per_mod=B, sigma=sig,
+                  sigma_row_stride=0, sigma_step_stride=1, step_ptr=self.step,
+                  labels=self.labels)
+    m.backbone.run(self.xt, self.n_fwd * B, L, mod, self.logits,
+                   ids_period=B * L)
+    ld = m.backbone.vocab_ld
+    m._launch_sampler(
+      logits_a=self.logits.data_ptr(), ld_a=ld,
+      logits_b=(self.logits.data_ptr() + B * L * ld * 2) if self.two else None,
+      ld_b=ld if self.two else 0, xt=self.xt, xs=self.xt, mc_t=mct, mc_s=mcs,
+      rows=B * L, seq_len=L, mc_seq_stride=0, mc_step_stride=1,
+      step_ptr=self.step, seed_ptr=self.seed_dev,
+      guidance=_lib.GUIDE_CFG if self.two else _lib.GUIDE_NONE,
+      gamma=self.gamma if self.two else 1.0)
+    check(lib.ddg_step_advance(ptr(self.step), stream_ptr()))
+
+  def prepare(self, xt, sigma_t, mc_t, mc_s, cond):
+    m = self.model
+    steps = sigma_t.numel()
+    dev = m.device
+    sig = sigma_t if m.time_conditioning else torch.zeros_like(sigma_t)
+    if self.tables is None or self.steps != steps:
+      self.tables = tuple(torch.empty(steps, dtype=torch.float32, device=dev)
+                          for _ in range(3))
+      self.steps = steps
+      self.graph = None
+    for dst, src in zip(self.tables, (sig, mc_t, mc_s)):
+      dst.copy_(src.to(torch.float32))
+    if self.method == 'cfg':
+      num_classes = m.config.data.num_classes
+      c = int(cond[0].item()) if cond is not None else 0
+      if self.two:
+        lab = [c, num_classes]
+      else:
+        lab = [num_classes if self.gamma == 0.0 else c]
+      self.labels.copy_(torch.tensor(lab, dtype=torch.int64))
+    self.xt.copy_(xt)
+    self.step.zero_()
+    self.seed_dev.fill_(m.seed + 7919 * m._call_count)
+    if self.graph is None:
+      # one eager step first (lazy attribute / module setup), then capture
+      self._body()
+      torch.cuda.synchronize()
+      self.xt.copy_(xt)
+      self.step.zero_()
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):
+        self._body()
+      self.graph = g
+      self.xt.copy_(xt)
+      self.step.zero_()
+
+  def replay(self, n):
+    for _ in range(n):
+      self.graph.replay()
+
+  def run(self, xt, sigma_t, mc_t, mc_s, cond):
+    self.prepare(xt, sigma_t, mc_t, mc_s, cond)
+    self.replay(self.steps)
+    return self.xt.clone()

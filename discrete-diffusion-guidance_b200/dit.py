@@ -1,0 +1,333 @@
+"""Host side of the DiT denoiser / classifier forward.
+
+Mirrors the interface of the reference backbone (`models/dit.py`: `DIT`
+:369-468, `DITClassifier` :470-556) -- `DIT(config, vocab_size)`,
+`load_state_dict`, `forward(indices, sigma, cond=None)` -> logits (B, L, V) --
+but every per-token operation is a launch of the sm_100a kernels behind the C
+ABI (gather+LayerNorm+modulate, tcgen05 GEMMs with fused epilogues, attention).
+PyTorch only owns the device buffers.
+
+Precision follows the reference on a GPU (SURVEY.md 8a'): fp32 residual
+stream / LayerNorm / conditioning, fp16 blocks for the denoiser
+(`models/dit.py:454`), bf16 blocks for the classifier (:531), bf16 final layer
+and logits (:463).
+"""
+from __future__ import annotations
+
+import dataclasses
+import typing
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+_BIG = 1 << 40
+_FREQ_DIM = 256  # TimestepEmbedder.frequency_embedding_size, models/dit.py:160
+
+
+def _pad_to(n, m):
+  return (n + m - 1) // m * m
+
+
+@dataclasses.dataclass
+class ModSpec:
+  """Where the conditioning rows of one forward come from (one `c` row per
+  `seqs_per_mod` consecutive sequences)."""
+  n_mod: int
+  seqs_per_mod: int
+  sigma: typing.Optional[torch.Tensor] = None   # f32, device
+  sigma_row_stride: int = 0
+  sigma_step_stride: int = 0
+  step_ptr: typing.Optional[torch.Tensor] = None  # int32[1], device
+  labels: typing.Optional[torch.Tensor] = None  # int64 (n_mod,), device
+
+
+class DIT:
+  """B200-native counterpart of `models.dit.DIT` (and, with
+  `classifier=True`, of `models.dit.DITClassifier`)."""
+
+  def __init__(self, config, vocab_size: int, device=None,
+               classifier: bool = False):
+    self.config = config
+    self.vocab_size = vocab_size
+    self.classifier = classifier
+    m = config.classifier_model if classifier else config.model
+    self.hidden = m.hidden_size
+    self.cond_dim = m.cond_dim
+    self.n_blocks = m.n_blocks
+    self.n_heads = m.n_heads
+    self.head_dim = self.hidden // self.n_heads
+    self.causal = config.parameterization == 'ar'
+    self.device = torch.device(device if device is not None else 'cuda')
+    self.block_dtype = torch.bfloat16 if classifier else torch.float16
+    self.head_dtype = torch.bfloat16
+    self.vocab_ld = _pad_to(vocab_size, 64)   # padded logits leading dim
+    self.seg_seqs = None                      # micro-batch (sequences) or None
+    if classifier:
+      pooling = m.get('pooling', 'mean')
+      if pooling != 'mean':
+        raise NotImplementedError(f'`{pooling}` method not implemented.')
+      self.num_classes = m.num_classes
+    if self.head_dim != 64 or self.hidden % 128 != 0:
+      raise NotImplementedError(
+        'ddg_b200 kernels need head_dim == 64 and hidden % 128 == 0 '
+        f'(got hidden={self.hidden}, n_heads={self.n_heads})')
+    self._loaded = False
+    self._ws = None
+    self._ws_rows = 0
+    self._ws_mods = 0
+    self._rope = {}
+
+  # ------------------------------------------------------------------ weights
+  def _cast(self, t: torch.Tensor, dtype, pad_to: int = 0):
+    """fp32 master tensor -> 16-bit device copy via the library's cast."""
+    src = t.to(self.device, torch.float32).contiguous()
+    n = src.numel()
+    out = torch.zeros(max(n, pad_to), dtype=dtype, device=self.device)
+    check(lib.ddg_cast(ptr(src), ptr(out), n, _lib.DTYPE_CODE[dtype],
+                       stream_ptr()))
+    torch.cuda.current_stream().synchronize()
+    return out
+
+  def load_state_dict(self, sd, prefix: typing.Optional[str] = None):
+    _lib.require_device()
+    if prefix is None:
+      prefix = 'classifier_model.' if self.classifier else 'backbone.'
+
+    def get(k):
+      return sd[prefix + k]
+
+    def f32(k):
+      return get(k).to(self.device, torch.float32).contiguous()
+
+    h, V = self.hidden, self.vocab_size
+    if tuple(get('vocab_embed.embedding').shape) != (V, h):
+      raise ValueError('vocab_embed.embedding shape mismatch')
+    self.embedding = f32('vocab_embed.embedding')
+    self.has_sigma = (prefix + 'sigma_map.mlp.0.weight') in sd
+    if self.has_sigma:
+      self.sm_w0, self.sm_b0 = f32('sigma_map.mlp.0.weight'), f32('sigma_map.mlp.0.bias')
+      self.sm_w2, self.sm_b2 = f32('sigma_map.mlp.2.weight'), f32('sigma_map.mlp.2.bias')
+    self.label_table = None
+    if (prefix + 'cond_map.embedding_table.weight') in sd:
+      self.label_table = f32('cond_map.embedding_table.weight')
+    self.use_adaln = (prefix + 'blocks.0.adaLN_modulation.weight') in sd
+    bd = self.block_dtype
+    self.ln1, self.ln2 = [], []
+    self.w_qkv, self.w_out, self.w_fc1, self.w_fc2 = [], [], [], []
+    self.b_fc1, self.b_fc2 = [], []
+    ada_w, ada_b = [], []
+    for i in range(self.n_blocks):
+      p = f'blocks.{i}.'
+      self.ln1.append(f32(p + 'norm1.weight'))
+      self.ln2.append(f32(p + 'norm2.weight'))
+      self.w_qkv.append(self._cast(get(p + 'attn_qkv.weight'), bd))
+      self.w_out.append(self._cast(get(p + 'attn_out.weight'), bd))
+      self.w_fc1.append(self._cast(get(p + 'mlp.0.weight'), bd))
+      self.w_fc2.append(self._cast(get(p + 'mlp.2.weight'), bd))
+      self.b_fc1.append(self._cast(get(p + 'mlp.0.bias'), bd, _pad_to(4 * h, 256)))
+      self.b_fc2.append(self._cast(get(p + 'mlp.2.bias'), bd, _pad_to(h, 256)))
+      if self.use_adaln:
+        ada_w.append(get(p + 'adaLN_modulation.weight'))
+        ada_b.append(get(p + 'adaLN_modulation.bias'))
+    if self.use_adaln:
+      self.ada_w = torch.cat(ada_w, 0).to(self.device, torch.float32).contiguous()
+      self.ada_b = torch.cat(ada_b, 0).to(self.device, torch.float32).contiguous()
+    if self.classifier:
+      self.cls_w, self.cls_b = f32('output_layer.weight'), f32('output_layer.bias')
+    else:
+      self.ln_f = f32('output_layer.norm_final.weight')
+      self.w_vocab = self._cast(get('output_layer.linear.weight'), self.head_dtype)
+      self.b_vocab = self._cast(get('output_layer.linear.bias'), self.head_dtype,
+                                _pad_to(V, 256))
+      self.final_adaln = (prefix + 'output_layer.adaLN_modulation.weight') in sd
+      if self.final_adaln:
+        self.ada_f_w = f32('output_layer.adaLN_modulation.weight')
+        self.ada_f_b = f32('output_layer.adaLN_modulation.bias')
+    self._loaded = True
+    return self
+
+  # ------------------------------------------------------------------ buffers
+  def _rope_tables(self, L: int):
+    if L not in self._rope:
+      # models/dit.py:82-108: fp32 cos/sin, rounded to the qkv dtype (:290-293)
+      inv_freq = 1.0 / (10000 ** (torch.arange(0, self.head_dim, 2).float()
+                                  / self.head_dim))
+      freqs = torch.einsum('i,j->ij', torch.arange(L).float(), inv_freq)
+      self._rope[L] = (freqs.cos().to(self.block_dtype).to(self.device).contiguous(),
+                       freqs.sin().to(self.block_dtype).to(self.device).contiguous())
+    return self._rope[L]
+
+  def _workspace(self, rows: int, n_mod: int):
+    if self._ws is None or rows > self._ws_rows or n_mod > self._ws_mods:
+      rows = max(rows, self._ws_rows)
+      n_mod = max(n_mod, self._ws_mods)
+      h, dev = self.hidden, self.device
+      seg = rows if self.seg_seqs is None else rows   # sized for the full batch
+      ws = {
+        'x': torch.empty(rows, h, dtype=torch.float32, device=dev),
+        'a16': torch.empty(seg, h, dtype=torch.int16, device=dev),
+        'qkv': torch.empty(seg, 3 * h, dtype=torch.int16, device=dev),
+        'h4': torch.empty(seg, 4 * h, dtype=torch.int16, device=dev),
+        'c': torch.empty(n_mod, self.cond_dim, dtype=torch.float32, device=dev),
+        'mod_blk': torch.empty(n_mod, self.n_blocks * 6 * h, dtype=torch.int16, device=dev),
+        'mod_fin': torch.empty(n_mod, 2 * h, dtype=torch.int16, device=dev),
+      }
+      self._ws, self._ws_rows, self._ws_mods = ws, rows, n_mod
+    return self._ws
+
+  def alloc_logits(self, rows: int) -> torch.Tensor:
+    """(rows, vocab_ld) bf16 logits buffer; columns >= vocab are padding."""
+    return torch.empty(rows, self.vocab_ld, dtype=self.head_dtype,
+                       device=self.device)
+
+  # ------------------------------------------------------------------ forward
+  def run(self, ids: torch.Tensor, n_seqs: int, L: int, mod: ModSpec,
+          logits_out: typing.Optional[torch.Tensor] = None,
+          ids_period: typing.Optional[int] = None):
+    """Launches one forward over `n_seqs` sequences of length L.  `ids` holds
+    `ids_period` (default n_seqs*L) int64 token ids, reused cyclically.
+    Denoiser: writes logits (rows, vocab_ld) bf16 into `logits_out`.
+    Classifier: returns the fp32 residual stream (rows, hidden)."""
+    assert self._loaded, 'load_state_dict first'
+    M = n_seqs * L
+    h, nb = self.hidden, self.n_blocks
+    period = M if ids_period is None else ids_period
+    ws = self._workspace(M, mod.n_mod)
+    s = stream_ptr()
+    bcode = _lib.DTYPE_CODE[self.block_dtype]
+    hcode = _lib.DTYPE_CODE[self.head_dtype]
+    rpm = mod.seqs_per_mod * L
+    mod_stride = nb * 6 * h
+    if self.use_adaln:
+      if mod.labels is not None and self.label_table is None:
+        raise ValueError('Conditioning variable provided, but Model was not '
+                         'initialized with condition embedding layer.')
+      use_sigma = self.has_sigma
+      check(lib.ddg_cond_embed(
+        ptr(mod.sigma) if use_sigma else 0, mod.sigma_row_stride,
+        ptr(mod.step_ptr), mod.sigma_step_stride, ptr(mod.labels), mod.n_mod,
+        self.cond_dim, _FREQ_DIM,
+        ptr(self.sm_w0) if use_sigma else 0, ptr(self.sm_b0) if use_sigma else 0,
+        ptr(self.sm_w2) if use_sigma else 0, ptr(self.sm_b2) if use_sigma else 0,
+        ptr(self.label_table), ptr(ws['c']), s))
+      check(lib.ddg_adaln(ptr(ws['c']), mod.n_mod, self.cond_dim, ptr(self.ada_w),
+                          ptr(self.ada_b), nb * 6 * h, bcode, h, 0b010010, 6,
+                          ptr(ws['mod_blk']), mod_stride, s))
+      if not self.classifier and self.final_adaln:
+        check(lib.ddg_adaln(ptr(ws['c']), mod.n_mod, self.cond_dim,
+                            ptr(self.ada_f_w), ptr(self.ada_f_b), 2 * h, hcode, h,
+                            0b10, 2, ptr(ws['mod_fin']), 2 * h, s))
+    elif mod.labels is not None:
+      raise ValueError('Conditioning variable provided, but Model was not '
+                       'initialized with condition embedding layer.')
+    cos, sin = self._rope_tables(L)
+    seg_rows = M if self.seg_seqs is None else max(1, self.seg_seqs) * L
+    for r0 in range(0, M, seg_rows):
+      n = min(seg_rows, M - r0)
+      if r0 % rpm == 0:
+        mod0, rpm_arg = r0 // rpm, rpm
+      elif r0 // rpm == (r0 + n - 1) // rpm:
+        mod0, rpm_arg = r0 // rpm, _BIG
+      else:
+        raise ValueError('micro-batch straddles a conditioning group')
+      if (r0 % period) + n > period and not (r0 == 0 and n == M):
+        raise ValueError('micro-batch straddles the id period')
+      self._run_segment(ws, ids, r0, n, L, period, mod0, rpm_arg, mod_stride,
+                        cos, sin, logits_out, bcode, hcode, s)
+    if self.classifier:
+      return ws['x'][:M]
+    return logits_out
+
+  def _run_segment(self, ws, ids, r0, n, L, period, mod0, rpm, mod_stride, cos,
+                   sin, logits_out, bcode, hcode, s):
+    h, nb = self.hidden, self.n_blocks
+    x = ptr(ws['x']) + r0 * h * 4
+    a16, qkv, h4 = ptr(ws['a16']), ptr(ws['qkv']), ptr(ws['h4'])
+    modb = ptr(ws['mod_blk']) + mod0 * mod_stride * 2
+    ids_p = ptr(ids) + (r0 % period) * 8
+    ada = self.use_adaln
+
+    def gemm(a, lda, w, ldw, out, ld_out, N, K, epi, dtype, bias=0, gate=0,
+             gate_stride=0):
+      g = _lib.GemmArgs(
+        a=a, w=w, out=out, bias=bias, gate=gate, rope_cos=ptr(cos),
+        rope_sin=ptr(sin), lda=lda, ldw=ldw, ld_out=ld_out,
+        gate_stride=gate_stride, rows_per_mod=rpm, M=n, N=N, K=K, dtype=dtype,
+        epilogue=epi, seq_len=L, head_dim=self.head_dim, rope_cols=2 * h)
+      check(lib.ddg_gemm(g, s))
+
+    for i in range(nb):
+      mb = modb + i * 6 * h * 2
+      check(lib.ddg_ln_modulate(
+        x, n, h, ids_p if i == 0 else 0, period, ptr(self.embedding),
+        ptr(self.ln1[i]), mb if ada else 0, mb + h * 2 if ada else 0,
+        mod_stride, rpm, bcode, a16, s))
+      gemm(a16, h, ptr(self.w_qkv[i]), h, qkv, 3 * h, 3 * h, h,
+           _lib.EPI_QKV_ROPE, bcode)
+      check(lib.ddg_attention(qkv, a16, n // L, L, self.n_heads, self.head_dim,
+                              1 if self.causal else 0, bcode, s))
+      gemm(a16, h, ptr(self.w_out[i]), h, x, h, h, h, _lib.EPI_GATE_RESIDUAL,
+           bcode, gate=mb + 2 * h * 2 if ada else 0, gate_stride=mod_stride)
+      check(lib.ddg_ln_modulate(
+        x, n, h, 0, period, 0, ptr(self.ln2[i]), mb + 3 * h * 2 if ada else 0,
+        mb + 4 * h * 2 if ada else 0, mod_stride, rpm, bcode, a16, s))
+      gemm(a16, h, ptr(self.w_fc1[i]), h, h4, 4 * h, 4 * h, h,
+           _lib.EPI_BIAS_GELU, bcode, bias=ptr(self.b_fc1[i]))
+      gemm(h4, 4 * h, ptr(self.w_fc2[i]), 4 * h, x, h, h, 4 * h,
+           _lib.EPI_GATE_RESIDUAL, bcode, bias=ptr(self.b_fc2[i]),
+           gate=mb + 5 * h * 2 if ada else 0, gate_stride=mod_stride)
+    if self.classifier:
+      return
+    fin = self.use_adaln and self.final_adaln
+    mf = ptr(ws['mod_fin']) + mod0 * 2 * h * 2
+    check(lib.ddg_ln_modulate(
+      x, n, h, 0, period, 0, ptr(self.ln_f), mf if fin else 0,
+      mf + h * 2 if fin else 0, 2 * h, rpm, hcode, a16, s))
+    gemm(a16, h, ptr(self.w_vocab), h, ptr(logits_out) + r0 * self.vocab_ld * 2,
+         self.vocab_ld, self.vocab_size, h, _lib.EPI_STORE, hcode,
+         bias=ptr(self.b_vocab))
+
+  # ------------------------------------------------------------------ API
+  def forward(self, indices, sigma, cond=None, x_emb=None,
+              return_hidden_states=False):
+    """`DIT.forward(indices, sigma, cond)` (models/dit.py:426-468): logits
+    (B, L, V) bf16 (a view of the padded buffer)."""
+    if x_emb is not None or return_hidden_states:
+      raise NotImplementedError('x_emb / return_hidden_states (NOS/PPLM paths) '
+                                'are outside the sampling hot path')
+    B, L = indices.shape
+    ids = indices.to(self.device, torch.int64).contiguous()
+    mod = ModSpec(n_mod=B, seqs_per_mod=1)
+    if not self.causal:
+      mod.sigma = sigma.to(self.device, torch.float32).reshape(-1).contiguous()
+      mod.sigma_row_stride = 1
+    if cond is not None:
+      mod.labels = cond.to(self.device, torch.int64).contiguous()
+    logits = self.alloc_logits(B * L)
+    self.run(ids, B, L, mod, logits)
+    return logits.view(B, L, self.vocab_ld)[:, :, :self.vocab_size]
+
+  __call__ = forward
+
+  def classify(self, indices, sigma, round_bf16=True):
+    """`Classifier.get_log_probs` for token ids (classifier.py:316-327 over
+    models/dit.py:516-556): (n, L) ids -> (n, num_classes) fp32 log-probs."""
+    assert self.classifier
+    n, L = indices.shape
+    ids = indices.to(self.device, torch.int64).contiguous()
+    mod = ModSpec(n_mod=n, seqs_per_mod=1)
+    if not self.causal:
+      mod.sigma = sigma.to(self.device, torch.float32).reshape(-1).contiguous()
+      mod.sigma_row_stride = 1 if mod.sigma.numel() > 1 else 0
+      if mod.sigma.numel() == 1:
+        mod.n_mod, mod.seqs_per_mod = 1, n
+    x = self.run(ids, n, L, mod)
+    out = torch.empty(n, self.num_classes, dtype=torch.float32,
+                      device=self.device)
+    check(lib.ddg_classifier_head(ptr(x), n, L, self.hidden, ptr(self.cls_w),
+                                  ptr(self.cls_b), self.num_classes,
+                                  1 if round_bf16 else 0, ptr(out),
+                                  stream_ptr()))
+    return out

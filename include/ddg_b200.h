@@ -1,0 +1,243 @@
+/* ddg_b200 -- C ABI of the B200-native reverse-diffusion sampling hot path.
+ *
+ * Drop-in boundary for the per-step update of denaxen/discrete-diffusion-guidance
+ * (`Diffusion._ddpm_denoise / _cfg_denoise / _cbg_denoise`, `_sample_categorical`
+ * and the `models/dit.py` forward they call).  The reference is pure Python and
+ * has no FFI of its own; each entry point below names the reference code it
+ * replaces (paths relative to the reference root).  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the
+ *     name ends in `_host`; tensors are row-major with explicit leading dims.
+ *   - every call returns 0 on success or a negative DDG_ERR_* code and never
+ *     throws; ddg_last_error() returns a thread-local message.
+ *   - every launch is asynchronous on the caller's stream and graph-capturable:
+ *     no allocation, no synchronisation, no host reads of device memory.
+ *   - there is no CPU fallback: on a device that is not sm_100 every compute
+ *     entry point returns DDG_ERR_UNSUPPORTED.
+ */
+#ifndef DDG_B200_H_
+#define DDG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDG_ABI_VERSION 1
+#define DDG_API __attribute__((visibility("default")))
+
+typedef void* ddg_stream_t; /* cudaStream_t */
+
+enum ddg_status {
+  DDG_OK = 0,
+  DDG_ERR_INVALID = -1,     /* bad argument (shape, alignment, enum)   */
+  DDG_ERR_CUDA = -2,        /* CUDA runtime / driver error             */
+  DDG_ERR_UNSUPPORTED = -3  /* not an sm_100 device / unsupported size */
+};
+
+enum ddg_dtype { DDG_F32 = 0, DDG_F16 = 1, DDG_BF16 = 2 };
+
+/* config.diffusion (reference configs/config.yaml:14) */
+enum ddg_diffusion {
+  DDG_ABSORBING = 0,
+  DDG_UNIFORM = 1,
+  DDG_AR = 2 /* parameterization=ar: select straight from the log-probs */
+};
+/* config.guidance.method (reference configs/guidance/{cfg,cbg}.yaml) */
+enum ddg_guidance { DDG_GUIDE_NONE = 0, DDG_GUIDE_CFG = 1, DDG_GUIDE_CBG = 2 };
+/* categorical selection (reference diffusion.py:1748-1755, 1024-1038) */
+enum ddg_select {
+  DDG_SELECT_RACE = 0,   /* argmax_j p_j / E_j, E = 1e-10 - log(U + 1e-10) */
+  DDG_SELECT_ARGMAX = 1, /* config.eval.argmax_sampling                    */
+  DDG_SELECT_GUMBEL = 2  /* AR: argmax_j logp_j + G_j with G injected      */
+};
+
+DDG_API int ddg_abi_version(void);
+DDG_API const char* ddg_last_error(void);
+/* 0 if the current device is sm_100 (B200); DDG_ERR_UNSUPPORTED otherwise. */
+DDG_API int ddg_device_check(void);
+DDG_API int ddg_sm_count(void);
+
+/* ------------------------------------------------------------------------
+ * Fused per-token sampler.
+ * Replaces, for one reverse step, everything after the backbone forward in
+ *   Diffusion.forward            diffusion.py:356-365 (+ _subs_parameterization :321-337)
+ *   Diffusion._compute_posterior diffusion.py:367-394
+ *   Diffusion._ddpm_denoise      diffusion.py:1393-1420
+ *   Diffusion._cfg_denoise       diffusion.py:1456-1509
+ *   Diffusion._cbg_denoise       diffusion.py:1587-1621
+ *   Diffusion._sample_categorical diffusion.py:1748-1755
+ * One launch reads each logits row once from HBM and writes the next ids.
+ * ---------------------------------------------------------------------- */
+typedef struct ddg_sample_step_args {
+  /* inputs */
+  const void* logits_a;   /* (rows, ld_a) raw backbone logits: the conditional
+                             (or only) forward                               */
+  const void* logits_b;   /* (rows, ld_b) unconditional forward; CFG only     */
+  const float* clf;       /* (rows, ld_clf) classifier log-prob term; CBG only */
+  const float* noise;     /* (rows, ld_noise) injected U in [0,1) (RACE) or
+                             Gumbel G (GUMBEL); NULL -> in-kernel Philox      */
+  const int64_t* xt;      /* (rows,) current ids z_t                          */
+  const float* mc_t;      /* move_chance_t, see mc_* strides                  */
+  const float* mc_s;      /* move_chance_s                                    */
+  const int32_t* step_ptr; /* optional device step counter (graph replay)     */
+  const uint64_t* seed_ptr; /* optional device Philox key (overrides `seed`)   */
+  /* outputs */
+  int64_t* xs;            /* (rows,) next ids z_s                             */
+  float* q_out;           /* optional (rows, ld_q): normalised guided
+                             posterior q_xs (the reference's 2nd return)      */
+  /* sizes */
+  int64_t rows;           /* B * L                                            */
+  int64_t ld_a, ld_b, ld_clf, ld_noise, ld_q;
+  int32_t seq_len;        /* L: row -> sequence = row / L                     */
+  int32_t vocab;          /* V                                                */
+  int32_t mc_seq_stride;  /* element stride per sequence (0: one scalar)      */
+  int32_t mc_step_stride; /* element stride per step (0: no step table);
+                             step = *step_ptr if step_ptr else `step`         */
+  /* modes */
+  int32_t logits_dtype;   /* DDG_F32 | DDG_BF16                               */
+  int32_t diffusion;      /* ddg_diffusion                                    */
+  int32_t guidance;       /* ddg_guidance                                     */
+  int32_t subs;           /* 1: parameterization=subs (zero-mask + carry-over) */
+  int32_t mask_logit;     /* 1: logits[mask_index] += -1e6 (subs or
+                             config.subs_masking)                             */
+  int32_t mask_index;
+  int32_t round_bf16;     /* 1: round log-softmax and exp to bf16 the way the
+                             reference does on a GPU (SURVEY 8a' item 4)      */
+  int32_t select;         /* ddg_select                                       */
+  int32_t fast_math;      /* 1: ex2/lg2.approx intrinsics (production);
+                             0: expf/logf, unfused mul/add (parity)           */
+  float gamma;            /* guidance.gamma                                   */
+  uint64_t seed;          /* Philox key                                       */
+  int32_t step;           /* Philox counter word 3 when step_ptr == NULL      */
+  int32_t reserved;
+} ddg_sample_step_args;
+
+DDG_API int ddg_sample_step(const ddg_sample_step_args* args, ddg_stream_t stream);
+
+/* Log-probs the way Diffusion.forward returns them (diffusion.py:356-365,
+ * 321-337): optional mask-logit, subs carry-over rows, log_softmax; fp32 out.
+ * Not on the sampling path (ddg_sample_step fuses it); provided for the
+ * `forward()` API and for logits-parity tests. */
+DDG_API int ddg_log_probs(const void* logits, int64_t ld, int32_t logits_dtype,
+                  const int64_t* xt, int64_t rows, int32_t vocab,
+                  int32_t subs, int32_t mask_logit, int32_t mask_index,
+                  int32_t round_bf16, float* out, int64_t ld_out,
+                  ddg_stream_t stream);
+
+/* Prior sample (diffusion.py:1006-1013): absorbing -> mask_index everywhere,
+ * uniform -> Philox randint(0, V).  Counter word 3 = 0xFFFFFFFF. */
+DDG_API int ddg_sample_prior(int64_t* xt, int64_t n, int32_t diffusion, int32_t vocab,
+                     int32_t mask_index, uint64_t seed, ddg_stream_t stream);
+
+/* *step_ptr += 1 (single thread); closes one captured step of the loop. */
+DDG_API int ddg_step_advance(int32_t* step_ptr, ddg_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * DiT denoiser forward (models/dit.py:426-468) building blocks.
+ * ---------------------------------------------------------------------- */
+
+/* Conditioning vector c = silu(sigma_map(sigma)) [+ silu(cond_map[label])],
+ * fp32 (models/dit.py:433-446, 155-213).  n rows; label may be NULL (no
+ * cond_map term); sigma may be NULL (AR: c = silu(cond_map[label])).
+ * Row r reads sigma[r * sigma_row_stride + step * sigma_step_stride] with
+ * step = *step_ptr (0 when step_ptr is NULL). */
+DDG_API int ddg_cond_embed(const float* sigma, int32_t sigma_row_stride,
+                   const int32_t* step_ptr, int32_t sigma_step_stride,
+                   const int64_t* label, int32_t n,
+                   int32_t cond_dim, int32_t freq_dim,
+                   const float* w0, const float* b0,  /* (cond_dim,freq_dim) */
+                   const float* w2, const float* b2,  /* (cond_dim,cond_dim) */
+                   const float* label_table,          /* (classes+1,cond_dim) */
+                   float* c_out, ddg_stream_t stream);
+
+/* adaLN_modulation linears (models/dit.py:269-271, 361-362) evaluated the way
+ * autocast(dtype) does: operands rounded to `dtype`, fp32 accumulate, one
+ * output rounding.  out[r, :] = round(c[r,:] @ W^T + b), W (n_out, cond_dim)
+ * fp32 master weights.  Outputs whose bit (col / chunk) % n_chunks of
+ * `one_plus_mask` is set store round(1 + value) instead
+ * (the `1 + scale` of modulate, formed in `dtype`, models/dit.py:47-50). */
+DDG_API int ddg_adaln(const float* c, int32_t n_rows, int32_t cond_dim,
+              const float* w, const float* b, int32_t n_out,
+              int32_t dtype, int32_t chunk, uint32_t one_plus_mask,
+              int32_t n_chunks, void* out, int64_t ld_out,
+              ddg_stream_t stream);
+
+/* LayerNorm (fp32 stats, no bias) * weight, then x*(1+scale)+shift, rounded
+ * once to the GEMM operand dtype (models/dit.py:131-139, 47-50, 280, 321,
+ * 363).  `ids` != NULL additionally gathers x = embedding[ids[row %
+ * ids_period]] and writes it to `x` first (models/dit.py:337, 449; the period
+ * lets the cond/uncond halves of a batched CFG forward share one id buffer).  shift / one_plus_scale are rows of
+ * the adaLN table: row = token_row / rows_per_mod.  shift == NULL: no adaLN. */
+DDG_API int ddg_ln_modulate(float* x, int64_t rows, int32_t hidden,
+                    const int64_t* ids, int64_t ids_period,
+                    const float* embedding,
+                    const float* ln_weight,
+                    const void* shift, const void* one_plus_scale,
+                    int64_t mod_stride, int64_t rows_per_mod,
+                    int32_t dtype, void* out, ddg_stream_t stream);
+
+/* GEMM epilogues (models/dit.py:284-293, 312-316, 242-245/324-325, 359-366) */
+enum ddg_epilogue {
+  DDG_EPI_STORE = 0,        /* out = round(acc [+ bias])            16-bit   */
+  DDG_EPI_QKV_ROPE = 1,     /* round, then NeoX rotary on q,k heads 16-bit   */
+  DDG_EPI_BIAS_GELU = 2,    /* round(gelu_tanh(round(acc + bias)))  16-bit   */
+  DDG_EPI_GATE_RESIDUAL = 3 /* x += round(gate * round(acc [+ bias])) fp32   */
+};
+
+typedef struct ddg_gemm_args {
+  const void* a;        /* (M, K) activations, 16-bit `dtype`, row-major     */
+  const void* w;        /* (N, K) nn.Linear weight, 16-bit `dtype`           */
+  void* out;            /* (M, ld_out) 16-bit, or the fp32 residual stream   */
+  const void* bias;     /* (N,) `dtype` or NULL                              */
+  const void* gate;     /* GATE_RESIDUAL: adaLN gate rows (`dtype`) or NULL  */
+  const void* rope_cos; /* QKV_ROPE: (L, head_dim/2) `dtype`                 */
+  const void* rope_sin;
+  int64_t lda, ldw, ld_out;
+  int64_t gate_stride;  /* elements between gate rows                        */
+  int64_t rows_per_mod; /* gate row = m / rows_per_mod                       */
+  int32_t M, N, K;
+  int32_t dtype;        /* DDG_F16 | DDG_BF16                                */
+  int32_t epilogue;     /* ddg_epilogue                                      */
+  int32_t seq_len;      /* QKV_ROPE: position = m % seq_len                  */
+  int32_t head_dim;     /* QKV_ROPE: 64                                      */
+  int32_t rope_cols;    /* QKV_ROPE: columns [0, rope_cols) are q,k heads    */
+} ddg_gemm_args;
+
+/* tcgen05 / TMEM / TMA GEMM: out = epilogue(a @ w^T). */
+DDG_API int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream);
+
+/* Softmax attention over whole sequences (models/dit.py:303-307):
+ * qkv (B*L, 3*H*D) 16-bit with column order (three, head, dim)
+ * (models/dit.py:285-289) -> out (B*L, H*D).  D must be 64, L <= 256 and a
+ * multiple of 16. */
+DDG_API int ddg_attention(const void* qkv, void* out, int32_t batch, int32_t seq_len,
+                  int32_t n_heads, int32_t head_dim, int32_t causal,
+                  int32_t dtype, ddg_stream_t stream);
+
+/* fp32 -> 16-bit cast of a weight tensor (what autocast does per call;
+ * done once at load time here). */
+DDG_API int ddg_cast(const float* src, void* dst, int64_t n, int32_t dtype,
+             ddg_stream_t stream);
+
+/* Mean over the sequence + Linear(h -> classes) + log_softmax
+ * (models/dit.py:538-555, classifier.py:316-327). x (n*L, hidden) fp32. */
+DDG_API int ddg_classifier_head(const float* x, int32_t n, int32_t seq_len,
+                        int32_t hidden, const float* w, const float* b,
+                        int32_t n_classes, int32_t round_bf16,
+                        float* log_probs, ddg_stream_t stream);
+
+/* Exact D-CBG candidate batch (diffusion.py:1551-1585): for candidate c of
+ * chunk [c0, c0+n): seq b = c / (L*V), l = (c / V) % L, v = c % V;
+ * ids_out[c - c0, :] = xt[b, :] with position l replaced by v. */
+DDG_API int ddg_cbg_candidates(const int64_t* xt, int32_t seq_len, int32_t vocab,
+                       int64_t c0, int64_t n, int64_t* ids_out,
+                       ddg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDG_B200_H_ */

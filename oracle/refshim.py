@@ -1,0 +1,216 @@
+"""TEST INFRASTRUCTURE ONLY -- loader for the *unmodified* reference sampler.
+
+Imports /root/reference (read-only, exists only in the build container) with
+import-time stubs for the packages this image lacks (lightning, hydra,
+omegaconf, torchmetrics, mamba_ssm, causal_conv1d, timm) and a pure-torch
+stand-in for flash_attn's Triton-only rotary (reference models/dit.py:116-121).
+Nothing of the reference is copied: the modules are imported where they lie.
+
+Used by tests/golden/make_golden.py (golden-vector generator) and by
+tests/test_oracle_pins.py (skipped when /root/reference is absent, e.g. on the
+GPU box).  Never imported by the product package, bench.py's timed path or
+smoke().
+"""
+from __future__ import annotations
+
+import importlib.machinery
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get('DDG_REFERENCE_ROOT', '/root/reference')
+
+
+def reference_available() -> bool:
+  return os.path.isfile(os.path.join(REFERENCE_ROOT, 'diffusion.py'))
+
+
+class AttrDict(dict):
+  """Attribute-style dict standing in for omegaconf.DictConfig."""
+
+  def __getattr__(self, k):
+    try:
+      v = self[k]
+    except KeyError as e:
+      raise AttributeError(k) from e
+    return v
+
+  def __setattr__(self, k, v):
+    self[k] = v
+
+
+def to_attrdict(d):
+  if isinstance(d, dict):
+    return AttrDict({k: to_attrdict(v) for k, v in d.items()})
+  if isinstance(d, (list, tuple)):
+    return type(d)(to_attrdict(v) for v in d)
+  return d
+
+
+def _mod(name, **attrs):
+  m = types.ModuleType(name)
+  m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+  m.__path__ = []
+  for k, v in attrs.items():
+    setattr(m, k, v)
+  sys.modules[name] = m
+  return m
+
+
+def _install_stubs():
+  import torch
+  import torch.nn as nn
+
+  if 'lightning' not in sys.modules:
+    class LightningModule(nn.Module):
+      def __init__(self, *a, **k):
+        super().__init__()
+
+      def save_hyperparameters(self, *a, **k):
+        pass
+
+      def log(self, *a, **k):
+        pass
+
+      def log_dict(self, *a, **k):
+        pass
+
+      @property
+      def dtype(self):
+        return torch.float32
+
+      @property
+      def device(self):
+        for p in self.parameters():
+          return p.device
+        return torch.device('cpu')
+
+      @classmethod
+      def load_from_checkpoint(cls, *a, **k):
+        raise RuntimeError('stub: patch load_from_checkpoint')
+
+    rz = _mod('lightning.pytorch.utilities',
+              rank_zero_only=lambda f: f)
+    lp = _mod('lightning.pytorch', utilities=rz)
+    _mod('lightning', LightningModule=LightningModule, pytorch=lp,
+         seed_everything=lambda s: torch.manual_seed(s))
+  if 'hydra' not in sys.modules:
+    hu = _mod('hydra.utils', instantiate=lambda *a, **k: None)
+    _mod('hydra', utils=hu)
+  if 'omegaconf' not in sys.modules:
+    class OmegaConf:
+      @staticmethod
+      def create(d):
+        return to_attrdict(d)
+
+      @staticmethod
+      def register_new_resolver(*a, **k):
+        pass
+    _mod('omegaconf', OmegaConf=OmegaConf, DictConfig=AttrDict)
+  if 'torchmetrics' not in sys.modules:
+    class Metric(nn.Module):
+      def __init__(self, *a, **k):
+        super().__init__()
+
+      def add_state(self, name, default, dist_reduce_fx=None):
+        setattr(self, name, default)
+
+    class MeanMetric(Metric):
+      pass
+
+    class MetricCollection(nn.Module):
+      def __init__(self, *a, **k):
+        super().__init__()
+
+      def set_dtype(self, *_):
+        pass
+
+      def clone(self, prefix=''):
+        return MetricCollection()
+
+      def add_metrics(self, *_):
+        pass
+
+      def reset(self):
+        pass
+    agg = _mod('torchmetrics.aggregation', MeanMetric=MeanMetric)
+    _mod('torchmetrics', Metric=Metric, MetricCollection=MetricCollection,
+         aggregation=agg)
+  if 'mamba_ssm' not in sys.modules:
+    class InferenceParams:
+      def __init__(self, *a, **k):
+        pass
+    _mod('mamba_ssm')
+    _mod('mamba_ssm.ops')
+    _mod('mamba_ssm.ops.selective_scan_interface',
+         mamba_inner_fn=None, selective_scan_fn=None)
+    _mod('mamba_ssm.ops.triton')
+    _mod('mamba_ssm.ops.triton.layernorm', RMSNorm=None,
+         layer_norm_fn=None, rms_norm_fn=None)
+    _mod('mamba_ssm.ops.triton.selective_state_update',
+         selective_state_update=None)
+    _mod('mamba_ssm.utils')
+    _mod('mamba_ssm.utils.generation', InferenceParams=InferenceParams)
+  if 'causal_conv1d' not in sys.modules:
+    _mod('causal_conv1d', causal_conv1d_fn=None, causal_conv1d_update=None)
+  if 'timm' not in sys.modules:
+    sch = _mod('timm.scheduler', CosineLRScheduler=object)
+    _mod('timm', scheduler=sch)
+
+
+_REF = None
+
+
+def load_reference():
+  """Returns a namespace with the reference's `diffusion`, `classifier`,
+  `dataloader`, `noise_schedule`, `models` modules (imported unmodified)."""
+  global _REF
+  if _REF is not None:
+    return _REF
+  if not reference_available():
+    raise RuntimeError(f'reference not found at {REFERENCE_ROOT}')
+  import torch  # noqa: F401
+  import transformers  # noqa: F401
+  import datasets  # noqa: F401
+  _install_stubs()
+  if REFERENCE_ROOT not in sys.path:
+    sys.path.insert(0, REFERENCE_ROOT)
+  import flash_attn.layers.rotary as far
+
+  if not getattr(far, '_ddg_cpu_shim', False):
+    _orig = far.apply_rotary_emb_qkv_
+
+    def _rotary_qkv_(qkv, cos, sin, *a, **k):
+      # reference models/dit.py:116-121 calls the Triton kernel; on CPU use
+      # the same package's pure-torch form on q and k (v untouched).
+      if qkv.is_cuda:
+        return _orig(qkv, cos, sin, *a, **k)
+      qkv[:, :, 0] = far.apply_rotary_emb_torch(qkv[:, :, 0], cos, sin)
+      qkv[:, :, 1] = far.apply_rotary_emb_torch(qkv[:, :, 1], cos, sin)
+      return qkv
+    far.apply_rotary_emb_qkv_ = _rotary_qkv_
+    far._ddg_cpu_shim = True
+  import classifier
+  import dataloader
+  import diffusion
+  import models
+  import noise_schedule
+  _REF = types.SimpleNamespace(
+    diffusion=diffusion, classifier=classifier, dataloader=dataloader,
+    noise_schedule=noise_schedule, models=models)
+  return _REF
+
+
+class SurrogateTokenizer:
+  """Offline stand-in for the HF tokenizers the reference downloads
+  (bert-base-uncased: vocab 30522, [MASK]=103; reference diffusion.py:80-95
+  only reads these attributes on the sampling path)."""
+
+  def __init__(self, vocab_size, mask_token_id, bos_token_id=101,
+               eos_token_id=102, pad_token_id=0):
+    self.vocab_size = vocab_size
+    self.mask_token = '[MASK]'
+    self.mask_token_id = mask_token_id
+    self.bos_token_id = bos_token_id
+    self.eos_token_id = eos_token_id
+    self.pad_token_id = pad_token_id
