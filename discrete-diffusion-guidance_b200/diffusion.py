@@ -451,6 +451,7 @@ class _GraphLoop:
                    if method == 'cfg' else None)
     self.tables = None
     self.graph = None
+    self.ws_generation = -1
     self.steps = 0
 
   def _body(self):
@@ -495,6 +496,8 @@ class _GraphLoop:
     self.xt.copy_(xt)
     self.step.zero_()
     self.seed_dev.fill_(m.seed + 7919 * m._call_count)
+    if self.graph is not None and self.ws_generation != m.backbone.ws_generation:
+      self.graph = None    # workspace buffers were reallocated since capture
     if self.graph is None:
       # one eager step first (lazy attribute / module setup), then capture
       self._body()
@@ -505,6 +508,7 @@ class _GraphLoop:
       with torch.cuda.graph(g):
         self._body()
       self.graph = g
+      self.ws_generation = m.backbone.ws_generation
       self.xt.copy_(xt)
       self.step.zero_()
 

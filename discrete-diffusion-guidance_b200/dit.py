@@ -77,6 +77,7 @@ class DIT:
     self._ws = None
     self._ws_rows = 0
     self._ws_mods = 0
+    self.ws_generation = 0    # bumped when buffers move (captured graphs go stale)
     self._rope = {}
 
   # ------------------------------------------------------------------ weights
@@ -175,6 +176,7 @@ class DIT:
         'mod_fin': torch.empty(n_mod, 2 * h, dtype=torch.int16, device=dev),
       }
       self._ws, self._ws_rows, self._ws_mods = ws, rows, n_mod
+      self.ws_generation += 1
     return self._ws
 
   def alloc_logits(self, rows: int) -> torch.Tensor:

@@ -154,7 +154,10 @@ def _install_stubs():
   if 'causal_conv1d' not in sys.modules:
     _mod('causal_conv1d', causal_conv1d_fn=None, causal_conv1d_update=None)
   if 'timm' not in sys.modules:
-    sch = _mod('timm.scheduler', CosineLRScheduler=object)
+    class CosineLRScheduler:
+      def __init__(self, *a, **k):
+        pass
+    sch = _mod('timm.scheduler', CosineLRScheduler=CosineLRScheduler)
     _mod('timm', scheduler=sch)
 
 

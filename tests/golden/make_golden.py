@@ -1,0 +1,166 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference sampler
+(/root/reference, imported through oracle/refshim.py) on CPU with injected
+prior and noise.  Run in the build container only:
+
+    python tests/golden/make_golden.py [case ...]
+
+The reference is on CPU, where every autocast in it is disabled, so these
+vectors pin the fp32 math of the path (SURVEY.md 8a' item 7).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import ddg_b200  # noqa: E402
+from golden import cases  # noqa: E402
+from oracle import refshim  # noqa: E402
+
+TOPK = 8
+
+
+def build_reference_model(ref, case):
+  cfg = refshim.to_attrdict(cases.config_dict(case))
+  tok = cases.Tok(case.vocab)
+  model = ref.diffusion.Diffusion(cfg, tok)
+  sd = ddg_b200.weights.random_state_dict(
+    ddg_b200.config.to_config(cases.config_dict(case)), tok.vocab_size,
+    seed=case.seed)
+  missing, unexpected = model.load_state_dict(sd, strict=False)
+  assert not unexpected, unexpected
+  assert set(missing) <= {'limiting_distribution'}, missing
+  model.eval()
+  clf = None
+  if case.guidance == 'cbg':
+    clf = ref.classifier.Classifier(cfg, tok)
+    csd = ddg_b200.weights.random_state_dict(
+      ddg_b200.config.to_config(cases.config_dict(case)), tok.vocab_size,
+      seed=case.seed + 1, classifier=True)
+    missing, unexpected = clf.load_state_dict(csd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    clf.eval()
+  return model, clf, cfg
+
+
+def summarise(name, t, out, big):
+  t = t.detach().float()
+  if not big:
+    out[name] = t.numpy()
+    return
+  top = t.topk(TOPK, dim=-1)
+  out[name + '_topv'] = top.values.numpy()
+  out[name + '_topi'] = top.indices.numpy().astype(np.int32)
+  out[name + '_sum'] = t.double().sum(-1).numpy()
+  # a fixed strided slice of columns pins the bulk of the distribution too
+  out[name + '_cols'] = t[..., ::997].numpy()
+
+
+def run_case(ref, case):
+  torch.manual_seed(0)
+  model, clf, cfg = build_reference_model(ref, case)
+  big = case.vocab == 'bert'
+  out = {}
+  xt0 = cases.prior_ids(case)
+  model._sample_prior = lambda *dims: xt0.clone()
+
+  if case.parameterization == 'ar':
+    G = cases.ar_gumbel(case)
+
+    class FakeGumbel:
+      def __init__(self, *a, **k):
+        pass
+
+      def sample(self, shape):
+        assert tuple(shape) == tuple(G.shape), (shape, G.shape)
+        return G.clone()
+    real = torch.distributions.Gumbel
+    torch.distributions.Gumbel = FakeGumbel
+    try:
+      with torch.no_grad():
+        x = model.sample()
+    finally:
+      torch.distributions.Gumbel = real
+    out['samples'] = x.numpy().astype(np.int32)
+    # log-probs of the final sequence pin the causal forward
+    with torch.no_grad():
+      lp = model.forward(x, None)
+    summarise('log_probs_final', lp, out, big)
+    return out
+
+  if clf is not None:
+    ref.classifier.Classifier.load_from_checkpoint = classmethod(
+      lambda cls, *a, **k: clf)
+
+  trace = []
+  step_counter = {'i': 0}
+  real_rand_like = torch.rand_like
+
+  def fake_rand_like(t, *a, **k):
+    U = cases.step_noise(case, step_counter['i'])
+    assert U.shape == t.shape, (U.shape, t.shape)
+    return U.to(t.dtype)
+
+  def wrap(fn_name):
+    orig = getattr(model, fn_name)
+
+    def wrapped(*a, **k):
+      xt = k['xt']
+      xs, q, cache = orig(*a, **k)
+      rec = {'xt': xt.clone(), 'xs': xs.clone(), 'q_xs': q.clone(),
+             'mc_t': k['move_chance_t'].reshape(-1)[0].clone(),
+             'mc_s': k['move_chance_s'].reshape(-1)[0].clone(),
+             'sigma_t': k['time_conditioning'].reshape(-1)[0].clone()}
+      for ck, cv in cache.items():
+        if cv is not None:
+          rec[ck] = cv.clone()
+      trace.append(rec)
+      step_counter['i'] += 1
+      return xs, q, cache
+    setattr(model, fn_name, wrapped)
+
+  for fn in ('_ddpm_denoise', '_cfg_denoise', '_cbg_denoise'):
+    wrap(fn)
+  torch.rand_like = fake_rand_like
+  try:
+    with torch.no_grad():
+      samples = model.sample()
+  finally:
+    torch.rand_like = real_rand_like
+  assert len(trace) == case.steps, (len(trace), case.steps)
+  out['samples'] = samples.numpy().astype(np.int32)
+  out['xt0'] = xt0.numpy().astype(np.int32)
+  for i, rec in enumerate(trace):
+    out[f's{i}_xt'] = rec['xt'].numpy().astype(np.int32)
+    out[f's{i}_xs'] = rec['xs'].numpy().astype(np.int32)
+    out[f's{i}_scalars'] = np.array(
+      [rec['sigma_t'].item(), rec['mc_t'].item(), rec['mc_s'].item()],
+      dtype=np.float32)
+    summarise(f's{i}_q_xs', rec['q_xs'], out, big)
+    for k in ('log_x_theta', 'log_x_theta_cond', 'log_x_theta_uncond',
+              'classifier_log_prob'):
+      if k in rec:
+        summarise(f's{i}_{k}', rec[k], out, big)
+  return out
+
+
+def main(argv):
+  ref = refshim.load_reference()
+  names = argv or [c.name for c in cases.CASES]
+  for name in names:
+    case = cases.CASE_BY_NAME[name]
+    out = run_case(ref, case)
+    path = os.path.join(HERE, f'{name}.npz')
+    np.savez_compressed(path, **out)
+    print(f'{name}: {len(out)} arrays, {os.path.getsize(path) / 1024:.1f} KiB')
+
+
+if __name__ == '__main__':
+  main(sys.argv[1:])

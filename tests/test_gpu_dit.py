@@ -1,0 +1,303 @@
+"""GPU parity of the DiT forward kernels against the CPU oracle / plain torch
+fp32 restatements of the same op.
+
+Tolerances: a 16-bit output may differ from the fp32-accumulated reference by
+one rounding of the result (fp16 2^-11, bf16 2^-8 relative) plus accumulation
+order noise; each test states its bound.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import ddg_b200
+import helpers
+from ddg_b200 import _lib
+from golden import cases
+from oracle import ref_dit
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _gemm(a, w, *, epi, out=None, bias=None, gate=None, rows_per_mod=1 << 40,
+          cos=None, sin=None, seq_len=1, ld_out=None):
+  M, K = a.shape
+  N = w.shape[0]
+  dtype = a.dtype
+  if epi == _lib.EPI_GATE_RESIDUAL:
+    assert out is not None
+  else:
+    ld_out = ld_out or (N + 7) // 8 * 8
+    out = torch.zeros(M, ld_out, dtype=dtype, device=DEV)
+  if bias is not None:   # the kernel reads whole 64-column groups
+    pad = torch.zeros((N + 255) // 256 * 256, dtype=dtype, device=DEV)
+    pad[:N] = bias
+    bias = pad
+  g = _lib.GemmArgs(
+    a=a.data_ptr(), w=w.data_ptr(), out=out.data_ptr(), bias=_lib.ptr(bias),
+    gate=_lib.ptr(gate), rope_cos=_lib.ptr(cos), rope_sin=_lib.ptr(sin),
+    lda=a.stride(0), ldw=w.stride(0), ld_out=out.stride(0),
+    gate_stride=gate.stride(0) if gate is not None else 0,
+    rows_per_mod=rows_per_mod, M=M, N=N, K=K, dtype=_lib.DTYPE_CODE[dtype],
+    epilogue=epi, seq_len=seq_len, head_dim=64, rope_cols=(N // 3) * 2)
+  _lib.check(_lib.lib.ddg_gemm(g, _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  return out
+
+
+def _tol(dtype):
+  return (4e-3, 2e-3) if dtype == torch.float16 else (2e-2, 1.5e-2)  # rtol, atol
+
+
+SHAPES = [(128, 256, 64), (300, 384, 128), (1000, 768, 768), (4096, 2304, 768),
+          (777, 768, 3072), (2048, 3072, 768)]
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES)
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+def test_gemm_store(M, N, K, dtype):
+  g = torch.Generator().manual_seed(M + N + K)
+  a = (torch.randn(M, K, generator=g) * 0.5).to(dtype).to(DEV)
+  w = (torch.randn(N, K, generator=g) * 0.05).to(dtype).to(DEV)
+  b = (torch.randn(N, generator=g) * 0.5).to(dtype).to(DEV)
+  out = _gemm(a, w, epi=_lib.EPI_STORE, bias=b)
+  ref = (a.float() @ w.float().t() + b.float()).to(dtype).float()
+  rtol, atol = _tol(dtype)
+  torch.testing.assert_close(out[:, :N].float(), ref, rtol=rtol, atol=atol)
+
+
+def test_gemm_vocab_head_ragged_n():
+  """bf16 vocab projection, N = 30522 (not a tile multiple), padded ld."""
+  M, N, K = 512, 30522, 768
+  g = torch.Generator().manual_seed(5)
+  a = torch.randn(M, K, generator=g).to(torch.bfloat16).to(DEV)
+  w = (torch.randn(N, K, generator=g) * 0.08).to(torch.bfloat16).to(DEV)
+  b = (torch.randn(N, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+  out = torch.full((M, 30528), 77.0, dtype=torch.bfloat16, device=DEV)
+  bias = torch.zeros(30720, dtype=torch.bfloat16, device=DEV)
+  bias[:N] = b
+  garg = _lib.GemmArgs(a=a.data_ptr(), w=w.data_ptr(), out=out.data_ptr(),
+                       bias=bias.data_ptr(), lda=K, ldw=K, ld_out=30528, M=M,
+                       N=N, K=K, dtype=_lib.BF16, epilogue=_lib.EPI_STORE,
+                       rows_per_mod=1, seq_len=1, head_dim=64)
+  _lib.check(_lib.lib.ddg_gemm(garg, _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  ref = (a.float() @ w.float().t() + b.float()).to(torch.bfloat16).float()
+  torch.testing.assert_close(out[:, :N].float(), ref, rtol=2e-2, atol=3e-2)
+  assert bool((out[:, N:] == 77.0).all()), 'padding columns must stay untouched'
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+def test_gemm_bias_gelu(dtype):
+  M, N, K = 512, 3072, 768
+  g = torch.Generator().manual_seed(6)
+  a = torch.randn(M, K, generator=g).to(dtype).to(DEV)
+  w = (torch.randn(N, K, generator=g) * 0.05).to(dtype).to(DEV)
+  b = (torch.randn(N, generator=g) * 0.2).to(dtype).to(DEV)
+  out = _gemm(a, w, epi=_lib.EPI_BIAS_GELU, bias=b)
+  pre = (a.float() @ w.float().t() + b.float()).to(dtype).float()
+  ref = torch.nn.functional.gelu(pre, approximate='tanh').to(dtype).float()
+  rtol, atol = _tol(dtype)
+  torch.testing.assert_close(out[:, :N].float(), ref, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('with_gate', [True, False])
+def test_gemm_gate_residual(dtype, with_gate):
+  """x += round(gate * round(acc + bias)); gate row chosen per sequence."""
+  L, nseq, N, K = 32, 6, 768, 768
+  M = L * nseq
+  g = torch.Generator().manual_seed(7)
+  a = torch.randn(M, K, generator=g).to(dtype).to(DEV)
+  w = (torch.randn(N, K, generator=g) * 0.05).to(dtype).to(DEV)
+  b = (torch.randn(N, generator=g) * 0.2).to(dtype).to(DEV)
+  gate = torch.randn(nseq, 2 * N, generator=g).to(dtype).to(DEV)  # strided rows
+  x0 = torch.randn(M, N, generator=g).to(DEV)
+  x = x0.clone()
+  _gemm(a, w, epi=_lib.EPI_GATE_RESIDUAL, out=x, bias=b,
+        gate=gate[:, N:] if with_gate else None, rows_per_mod=L)
+  y = (a.float() @ w.float().t() + b.float()).to(dtype).float()
+  if with_gate:
+    gsel = gate[:, N:].float().repeat_interleave(L, dim=0)
+    y = (gsel * y).to(dtype).float()
+  rtol, atol = _tol(dtype)
+  torch.testing.assert_close(x, x0 + y, rtol=rtol, atol=4 * atol)
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+def test_gemm_qkv_rope(dtype):
+  """QKV projection with the NeoX rotary fused on q,k heads
+  (models/dit.py:284-293), checked against the oracle's rotary."""
+  B, L, H = 3, 64, 4
+  h = H * 64
+  M = B * L
+  g = torch.Generator().manual_seed(8)
+  a = torch.randn(M, h, generator=g).to(dtype).to(DEV)
+  w = (torch.randn(3 * h, h, generator=g) * 0.06).to(dtype).to(DEV)
+  cos, sin = ref_dit.rotary_tables(L, 64)
+  out = _gemm(a, w, epi=_lib.EPI_QKV_ROPE, cos=cos.to(dtype).to(DEV).contiguous(),
+              sin=sin.to(dtype).to(DEV).contiguous(), seq_len=L)
+  qkv = (a.float() @ w.float().t()).to(dtype).float().cpu().view(B, L, 3, H, 64)
+  q = ref_dit._rope(qkv[:, :, 0], cos, sin, dtype)
+  k = ref_dit._rope(qkv[:, :, 1], cos, sin, dtype)
+  ref = torch.stack([q, k, qkv[:, :, 2]], dim=2).reshape(M, 3 * h)
+  rtol, atol = _tol(dtype)
+  torch.testing.assert_close(out[:, :3 * h].float().cpu(), ref, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('L', [16, 32, 64, 128, 256])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('causal', [False, True])
+def test_attention(L, dtype, causal):
+  B, H = 3, 4
+  g = torch.Generator().manual_seed(L)
+  qkv = (torch.randn(B * L, 3 * H * 64, generator=g) * 1.5).to(dtype)
+  out = torch.empty(B * L, H * 64, dtype=dtype, device=DEV)
+  qd = qkv.to(DEV)
+  _lib.check(_lib.lib.ddg_attention(qd.data_ptr(), out.data_ptr(), B, L, H, 64,
+                                    int(causal), _lib.DTYPE_CODE[dtype],
+                                    _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  v = qkv.float().view(B, L, 3, H, 64)
+  ref = ref_dit._attention(v[:, :, 0], v[:, :, 1], v[:, :, 2], causal, dtype)
+  rtol, atol = _tol(dtype)
+  torch.testing.assert_close(out.float().cpu().view(B, L, H, 64), ref,
+                             rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('hidden', [128, 512, 768, 1024])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+def test_ln_modulate(hidden, dtype):
+  L, nseq, V = 16, 5, 50
+  rows = L * nseq
+  g = torch.Generator().manual_seed(hidden)
+  emb = torch.randn(V, hidden, generator=g).to(DEV)
+  ids = torch.randint(0, V, (rows,), generator=g).to(DEV)
+  lnw = (1 + 0.1 * torch.randn(hidden, generator=g)).to(DEV)
+  mod = torch.randn(nseq, 3 * hidden, generator=g).to(dtype).to(DEV)
+  shift, ops = mod[:, :hidden], mod[:, hidden:2 * hidden]
+  x = torch.empty(rows, hidden, device=DEV)
+  out = torch.empty(rows, hidden, dtype=dtype, device=DEV)
+  _lib.check(_lib.lib.ddg_ln_modulate(
+    x.data_ptr(), rows, hidden, ids.data_ptr(), rows, emb.data_ptr(),
+    lnw.data_ptr(), shift.data_ptr(), ops.data_ptr(), mod.stride(0), L,
+    _lib.DTYPE_CODE[dtype], out.data_ptr(), _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  xe = emb[ids]
+  assert torch.equal(x, xe)
+  y = torch.nn.functional.layer_norm(xe, [hidden]) * lnw
+  y = y * ops.float().repeat_interleave(L, 0) + shift.float().repeat_interleave(L, 0)
+  rtol, atol = _tol(dtype)
+  torch.testing.assert_close(out.float(), y.to(dtype).float(), rtol=rtol, atol=atol)
+  # no-adaLN form, input taken from x
+  _lib.check(_lib.lib.ddg_ln_modulate(
+    x.data_ptr(), rows, hidden, 0, rows, 0, lnw.data_ptr(), 0, 0, 0, L,
+    _lib.DTYPE_CODE[dtype], out.data_ptr(), _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  y = torch.nn.functional.layer_norm(xe, [hidden]) * lnw
+  torch.testing.assert_close(out.float(), y.to(dtype).float(), rtol=rtol, atol=atol)
+
+
+def _model(case, classifier=False):
+  cfg, tok, sd, csd = helpers.case_state(case)
+  m = ddg_b200.DIT(cfg, tok.vocab_size, device=DEV, classifier=classifier)
+  m.load_state_dict(csd if classifier else sd)
+  return m, cfg, tok, sd, csd
+
+
+@pytest.mark.parametrize('name', ['udlm_cfg_g2', 'mdlm_null', 'bert_udlm_cfg_g2',
+                                  'ar_null'])
+def test_dit_forward_matches_oracle(name):
+  """Whole denoiser forward vs the CPU oracle with the reference's GPU
+  roundings (fp16 blocks, bf16 head).  bf16 logits: 1 ulp = 2^-8 relative;
+  bound: |d| <= 0.06 + 0.03 |ref| and mean |d| <= 0.01."""
+  case = cases.CASE_BY_NAME[name]
+  m, cfg, tok, sd, _ = _model(case)
+  B, L = case.batch, case.length
+  g = torch.Generator().manual_seed(3)
+  ids = torch.randint(0, tok.vocab_size, (B, L), generator=g)
+  sigma = torch.tensor([0.3, 1.7])[:B]
+  cond = torch.tensor([1, 2])[:B] if case.guidance == 'cfg' else None
+  causal = case.parameterization == 'ar'
+  if not case.time_conditioning:
+    sigma = torch.zeros_like(sigma)
+  logits = m.forward(ids.to(DEV), None if causal else sigma.to(DEV),
+                     cond.to(DEV) if cond is not None else None)
+  torch.cuda.synchronize()
+  ref = ref_dit.dit_forward(sd, ids, None if causal else sigma, cond,
+                            n_heads=case.n_heads, causal=causal,
+                            rounding=ref_dit.Rounding.gpu_denoiser())
+  d = (logits.float().cpu() - ref).abs()
+  assert bool((d <= 0.06 + 0.03 * ref.abs()).all()), d.max().item()
+  assert d.mean().item() <= 0.01, d.mean().item()
+  # and against the pure-fp32 reference math: the 16-bit pipeline stays close
+  ref32 = ref_dit.dit_forward(sd, ids, None if causal else sigma, cond,
+                              n_heads=case.n_heads, causal=causal)
+  assert (logits.float().cpu() - ref32).abs().mean().item() <= 0.03
+
+
+def test_conditioning_and_adaln_tables():
+  case = cases.CASE_BY_NAME['udlm_cfg_g2']
+  m, cfg, tok, sd, _ = _model(case)
+  n = 4
+  sigma = torch.tensor([0.0, 0.5, 2.0, 6.9])
+  labels = torch.tensor([0, 1, 2, 1])
+  c_ref = ref_dit.conditioning(sd, 'backbone.', sigma, labels)
+  ws = m._workspace(n * case.length, n)
+  mod = ddg_b200.ModSpec(n_mod=n, seqs_per_mod=1, sigma=sigma.to(DEV),
+                         sigma_row_stride=1, labels=labels.to(DEV))
+  ids = torch.zeros(n, case.length, dtype=torch.long, device=DEV)
+  m.run(ids, n, case.length, mod, m.alloc_logits(n * case.length))
+  torch.cuda.synchronize()
+  torch.testing.assert_close(ws['c'][:n].cpu(), c_ref, rtol=2e-5, atol=2e-6)
+  h = case.hidden
+  ada = ref_dit._linear(c_ref, sd['backbone.blocks.1.adaLN_modulation.weight'],
+                        sd['backbone.blocks.1.adaLN_modulation.bias'], torch.float16)
+  got = ws['mod_blk'][:n].view(torch.float16).float().cpu()[:, 6 * h:12 * h]
+  exp = ada.clone()
+  for ch in (1, 4):   # scale chunks hold 1 + scale, formed in fp16
+    exp[:, ch * h:(ch + 1) * h] = (1.0 + ada[:, ch * h:(ch + 1) * h]).half().float()
+  torch.testing.assert_close(got, exp, rtol=2e-3, atol=1e-3)
+
+
+def test_classifier_matches_oracle():
+  case = cases.CASE_BY_NAME['udlm_cbg']
+  m, cfg, tok, sd, csd = _model(case, classifier=True)
+  g = torch.Generator().manual_seed(9)
+  n = 37
+  ids = torch.randint(0, tok.vocab_size, (n, case.length), generator=g)
+  sigma = torch.rand(n, generator=g) * 3
+  got = m.classify(ids.to(DEV), sigma.to(DEV), round_bf16=True)
+  torch.cuda.synchronize()
+  ref = ref_dit.classifier_log_probs(
+    csd, ids, sigma, n_heads=case.n_heads, time_conditioning=True,
+    rounding=ref_dit.Rounding.gpu_classifier())
+  torch.testing.assert_close(got.cpu(), ref, rtol=3e-2, atol=3e-2)
+  assert torch.allclose(got.exp().sum(-1).cpu(), torch.ones(n), atol=2e-2)
+
+
+def test_cbg_candidates():
+  L, V, B = 5, 7, 3
+  xt = torch.randint(0, V, (B, L))
+  n = B * L * V
+  out = torch.empty(n, L, dtype=torch.long, device=DEV)
+  _lib.check(_lib.lib.ddg_cbg_candidates(xt.to(DEV).data_ptr(), L, V, 0, n,
+                                         out.data_ptr(), _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  exp = xt[:, None, :].repeat(1, L * V, 1).view(-1, L)
+  idx = torch.arange(L * V).repeat(B)
+  exp[torch.arange(n), idx // V] = idx % V     # diffusion.py:1556-1580
+  assert torch.equal(out.cpu(), exp)
+
+
+def test_gemm_rejects_bad_arguments():
+  a = torch.zeros(8, 12, dtype=torch.float16, device=DEV)   # K % 8 != 0
+  w = torch.zeros(8, 12, dtype=torch.float16, device=DEV)
+  o = torch.zeros(8, 8, dtype=torch.float16, device=DEV)
+  g = _lib.GemmArgs(a=a.data_ptr(), w=w.data_ptr(), out=o.data_ptr(), lda=12,
+                    ldw=12, ld_out=8, M=8, N=8, K=12, dtype=_lib.F16,
+                    epilogue=_lib.EPI_STORE, rows_per_mod=1, seq_len=1, head_dim=64)
+  with pytest.raises(ValueError):
+    _lib.check(_lib.lib.ddg_gemm(g, 0))

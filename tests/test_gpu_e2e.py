@@ -1,0 +1,158 @@
+"""End-to-end checks of the public sampling API on the GPU: the per-step
+functions (the drop-in boundary), the CUDA-graph loop, and every
+guidance x parameterization combination of the reference's config surface."""
+import pytest
+import torch
+
+import ddg_b200
+import helpers
+from golden import cases
+from oracle import ref_sampler
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _diffusion(case, **over):
+  cfg, tok, sd, csd = helpers.case_state(case)
+  for k, v in over.items():
+    node = cfg
+    parts = k.split('.')
+    for p in parts[:-1]:
+      node = node[p]
+    node[parts[-1]] = v
+  model = ddg_b200.Diffusion(cfg, tok, device=DEV).load_state_dict(sd)
+  if csd is not None:
+    clf = ddg_b200.Classifier(cfg, tok, device=DEV).load_state_dict(csd)
+    model.set_classifier(clf)
+  return model, cfg, tok
+
+
+@pytest.mark.parametrize('name', [c.name for c in cases.CASES
+                                  if c.parameterization != 'ar'])
+def test_step_api_ids_follow_own_logits(name):
+  """Per-step API with injected noise: the ids must be what the oracle's
+  update (with the reference's GPU roundings) selects from the logits the
+  CUDA forward produced -- id parity downstream of identical logits."""
+  case = cases.CASE_BY_NAME[name]
+  model, cfg, tok = _diffusion(case)
+  model.return_q_xs = True
+  B, L, V = case.batch, case.length, tok.vocab_size
+  sig, mct, mcs = ref_sampler.step_scalars(case.steps, 1e-5, case.T)
+  s2, m2, m3 = model._step_scalars(case.steps, 1e-5)
+  torch.testing.assert_close(s2, sig, rtol=1e-6, atol=1e-7)
+  torch.testing.assert_close(m2, mct, rtol=1e-6, atol=1e-7)
+  torch.testing.assert_close(m3, mcs, rtol=1e-6, atol=1e-7)
+  xt = cases.prior_ids(case)
+  kw = dict(diffusion=case.diffusion, mask_index=tok.mask_token_id,
+            lp_dtype=torch.bfloat16, argmax_sampling=case.argmax_sampling)
+  param = case.parameterization
+  for i in range(case.steps):
+    U = cases.step_noise(case, i)
+    model.noise_fn = lambda _i, U=U: U
+    sigma_t = sig[i].expand(B).to(DEV)
+    mc_t = mct[i].expand(B)[:, None, None]
+    mc_s = mcs[i].expand(B)[:, None, None]
+
+    def lps(logits):
+      return ref_sampler.log_probs_from_logits(
+        logits.float().cpu(), xt, parameterization=param,
+        mask_index=tok.mask_token_id, subs_masking=case.subs_masking,
+        lp_dtype=torch.bfloat16)
+    if case.guidance is None:
+      xs, q, cache = model._ddpm_denoise(xt.to(DEV), sigma_t, mc_t.to(DEV), mc_s.to(DEV))
+      xs_ref, q_ref = ref_sampler.ddpm_update(lps(cache['log_x_theta']), xt, mc_t, mc_s, U, **kw)
+    elif case.guidance == 'cfg':
+      cond = torch.full((B,), case.condition, dtype=torch.long, device=DEV)
+      xs, q, cache = model._cfg_denoise(cond, case.gamma, xt.to(DEV), sigma_t,
+                                        mc_t.to(DEV), mc_s.to(DEV))
+      lc, lu = cache['log_x_theta_cond'], cache['log_x_theta_uncond']
+      xs_ref, q_ref = ref_sampler.cfg_update(
+        lps(lc) if lc is not None else None, lps(lu) if lu is not None else None,
+        case.gamma, xt, mc_t, mc_s, U, **kw)
+    else:
+      xs, q, cache = model._cbg_denoise(
+        case.condition, case.gamma, model.classifier_model, xt.to(DEV), sigma_t,
+        mc_t.to(DEV), mc_s.to(DEV), use_approx=False)
+      xs_ref, q_ref = ref_sampler.cbg_update(
+        lps(cache['log_x_theta']), cache['classifier_log_prob'].cpu(), case.gamma,
+        xt, mc_t, mc_s, U, **kw)
+    torch.cuda.synchronize()
+    assert xs.dtype == torch.int64 and tuple(xs.shape) == (B, L)
+    helpers.assert_close_frac(q, q_ref, rtol=3e-4, atol=1e-6, loose_frac=2e-3,
+                              loose_rtol=2e-2)
+    helpers.assert_ids_match(xs, xs_ref, q_ref,
+                             None if case.argmax_sampling else U,
+                             f'{name} step {i}', tol=2e-2)
+    xt = xs_ref
+
+
+@pytest.mark.parametrize('name', ['udlm_null', 'mdlm_null', 'udlm_cfg_g2',
+                                  'mdlm_cfg_g2', 'udlm_cfg_g0', 'udlm_cfg_g1',
+                                  'udlm_T1000', 'bert_udlm_cfg_g2'])
+def test_graph_loop_equals_eager_loop(name):
+  """sample() through the captured CUDA graph == the same steps launched
+  eagerly through the per-step API (same Philox key), and repeated sample()
+  calls draw fresh noise."""
+  case = cases.CASE_BY_NAME[name]
+  model, cfg, tok = _diffusion(case, **{'sampling.steps': 12})
+  model.prior_fn = lambda *dims: cases.prior_ids(case)
+  a = model.sample()
+  model._call_count -= 1
+  model.use_cuda_graph = False
+  b = model.sample()
+  torch.cuda.synchronize()
+  assert a.dtype == torch.int64 and tuple(a.shape) == (case.batch, case.length)
+  assert torch.equal(a, b)
+  model.use_cuda_graph = True
+  c = model.sample()
+  assert not torch.equal(a, c)
+  if case.diffusion == 'absorbing_state':
+    # log-linear schedule ends at move chance ~1e-5: every mask is resolved
+    # with overwhelming probability; unmasked ids never the mask id
+    assert (a == tok.mask_token_id).float().mean().item() < 0.05
+  assert int(a.min()) >= 0 and int(a.max()) < tok.vocab_size
+
+
+def test_cbg_sample_runs_and_guides():
+  case = cases.CASE_BY_NAME['udlm_cbg']
+  model, cfg, tok = _diffusion(case, **{'sampling.steps': 3})
+  out = model.sample()
+  torch.cuda.synchronize()
+  assert tuple(out.shape) == (case.batch, case.length)
+
+
+def test_ar_sample_matches_oracle_selection():
+  """AR: full-length causal forward + Gumbel-max with injected noise; ids must
+  follow the CUDA forward's own logits (checked position by position)."""
+  case = cases.CASE_BY_NAME['ar_null']
+  model, cfg, tok = _diffusion(case)
+  G = cases.ar_gumbel(case)
+  model.noise_fn = lambda i: G[:, i]
+  x = model.sample()
+  torch.cuda.synchronize()
+  assert x[:, 0].eq(tok.bos_token_id).all()
+  lp = model.forward(x, None).cpu()
+  ok = 0
+  for i in range(case.length - 1):
+    ref = ref_sampler.ar_select(lp[:, i], G[:, i])
+    ok += int((ref == x[:, i + 1].cpu()).sum())
+  assert ok >= case.batch * (case.length - 1) - 1
+
+
+def test_error_semantics_match_reference():
+  case = cases.CASE_BY_NAME['udlm_null']
+  cfg, tok, sd, _ = helpers.case_state(case)
+  cfg.guidance = ddg_b200.config.to_config({'method': 'nos', 'condition': 0, 'gamma': 1.0})
+  model = ddg_b200.Diffusion(cfg, tok, device=DEV).load_state_dict(sd)
+  with pytest.raises(NotImplementedError):
+    model._diffusion_sample()
+  cfg2, _, sd2, _ = helpers.case_state(case)
+  model2 = ddg_b200.Diffusion(cfg2, tok, device=DEV).load_state_dict(sd2)
+  with pytest.raises(ValueError):   # cond without cond_map (models/dit.py:437-441)
+    model2._logits(torch.zeros(2, 32, dtype=torch.long, device=DEV),
+                   torch.zeros(2, device=DEV), torch.zeros(2, dtype=torch.long, device=DEV))
+  cfg3, _, _, _ = helpers.case_state(case)
+  cfg3.diffusion = 'uniform_data_marginals'
+  with pytest.raises(NotImplementedError):
+    ddg_b200.Diffusion(cfg3, tok, device=DEV)

@@ -1,0 +1,280 @@
+"""GPU parity of the fused sampler kernel (ddg_sample_step, C ABI).
+
+Tolerances (stated once, used below):
+  * ids: bit-exact against the reference / oracle on identical logits and
+    injected noise, except near-ties (selection scores within 2e-5 relative);
+  * q_xs: |dq| <= 1e-6 + 2e-4 |q|  (fp32 exp/log implementation differences).
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from golden import cases
+from oracle import ref_dit, ref_sampler
+
+pytestmark = pytest.mark.gpu
+
+DIFFUSION_CASES = [c.name for c in cases.CASES if c.parameterization != 'ar']
+
+
+def _oracle_logits(case, oracle, xt, sigma_t, cond):
+  """Raw fp32 backbone logits from the CPU oracle for one step."""
+  sigma = sigma_t if case.time_conditioning else torch.zeros_like(sigma_t)
+  return ref_dit.dit_forward(oracle.sd, xt, sigma, cond, n_heads=case.n_heads)
+
+
+@pytest.mark.parametrize('name', DIFFUSION_CASES)
+def test_kernel_replays_reference_goldens(name):
+  """Feeds the kernel the same fp32 logits and uniforms the reference saw and
+  requires the reference's own ids and posterior (tests/golden/*.npz)."""
+  case = cases.CASE_BY_NAME[name]
+  gold = helpers.load_golden(name)
+  big = case.vocab == 'bert'
+  oracle = helpers.make_oracle(case)
+  tok = cases.Tok(case.vocab)
+  V, B, L = tok.vocab_size, case.batch, case.length
+  dev = torch.device('cuda')
+  near = 0
+  for i in range(case.steps):
+    xt = torch.from_numpy(gold[f's{i}_xt']).long()
+    sc = gold[f's{i}_scalars']
+    sigma_t = torch.full((B,), float(sc[0]))
+    U = cases.step_noise(case, i)
+    kw = dict(xt=xt, mc_t=float(sc[1]), mc_s=float(sc[2]), vocab=V, seq_len=L,
+              diffusion=case.diffusion, noise=U,
+              subs=case.parameterization == 'subs',
+              mask_logit=case.parameterization == 'subs' or case.subs_masking,
+              mask_index=tok.mask_token_id, round_bf16=False, fast_math=False,
+              select='argmax' if case.argmax_sampling else 'race', want_q=True)
+    if case.guidance == 'cfg':
+      cond = torch.full((B,), case.condition, dtype=torch.long)
+      la = lb = None
+      if case.gamma != 0.0:
+        la = _oracle_logits(case, oracle, xt, sigma_t, cond)
+      if case.gamma != 1.0:
+        lb = _oracle_logits(case, oracle, xt, sigma_t,
+                            torch.full_like(cond, case.num_classes))
+      if la is None or lb is None:
+        one = la if la is not None else lb
+        xs, q = helpers.sampler_kernel(
+          logits_a=one.reshape(B * L, V).to(dev).contiguous(), **kw)
+      else:
+        xs, q = helpers.sampler_kernel(
+          logits_a=la.reshape(B * L, V).to(dev).contiguous(),
+          logits_b=lb.reshape(B * L, V).to(dev).contiguous(),
+          guidance='cfg', gamma=case.gamma, **kw)
+    elif case.guidance == 'cbg':
+      la = _oracle_logits(case, oracle, xt, sigma_t, None)
+      term = ref_sampler.cbg_classifier_term_exact(
+        oracle.clf_log_probs, xt, sigma_t, V, case.condition)
+      xs, q = helpers.sampler_kernel(
+        logits_a=la.reshape(B * L, V).to(dev).contiguous(), clf=term,
+        guidance='cbg', gamma=case.gamma, **kw)
+    else:
+      la = _oracle_logits(case, oracle, xt, sigma_t, None)
+      xs, q = helpers.sampler_kernel(
+        logits_a=la.reshape(B * L, V).to(dev).contiguous(), **kw)
+    q = q.view(B, L, V)
+    helpers.check_summary(f's{i}_q_xs', q, gold, big, rtol=2e-4, atol=1e-6)
+    gold_xs = torch.from_numpy(gold[f's{i}_xs']).long()
+    # the 30522-vocab fixtures store q_xs as a summary only: score near-ties
+    # with the (just verified) kernel posterior there
+    q_ref = q.cpu() if big else torch.from_numpy(gold[f's{i}_q_xs'])
+    near += helpers.assert_ids_match(
+      xs.view(B, L), gold_xs, q_ref, None if case.argmax_sampling else U,
+      f'{name} step {i}')
+  print(f'{name}: near-ties {near}')
+
+
+def _rand_logits(rows, V, ld, dtype, seed, scale=3.0):
+  g = torch.Generator().manual_seed(seed)
+  full = torch.zeros(rows, ld, dtype=torch.float32)
+  full[:, :V] = torch.randn(rows, V, generator=g) * scale
+  return full.to(dtype)
+
+
+MODES = [
+  ('uniform', 'none'), ('uniform', 'cfg'), ('uniform', 'cbg'),
+  ('absorbing_state', 'none'), ('absorbing_state', 'cfg'),
+  ('absorbing_state', 'cbg'),
+]
+
+
+@pytest.mark.parametrize('diffusion,guidance', MODES)
+@pytest.mark.parametrize('V,ld', [(30522, 30528), (30522, 30522), (35, 64), (1000, 1000)])
+@pytest.mark.parametrize('round_bf16', [True, False])
+def test_kernel_vs_oracle_bf16_logits(diffusion, guidance, V, ld, round_bf16):
+  """bf16 logits (what the DiT head emits), every mode, aligned / unaligned
+  leading dims, with and without the reference's GPU roundings."""
+  B, L = 2, 6
+  rows = B * L
+  dev = torch.device('cuda')
+  mask = 4 if V < 100 else 103
+  subs = diffusion == 'absorbing_state'
+  la = _rand_logits(rows, V, ld, torch.bfloat16, 1)
+  lb = _rand_logits(rows, V, ld, torch.bfloat16, 2)
+  g = torch.Generator().manual_seed(3)
+  U = torch.rand(B, L, V, generator=g)
+  clf = torch.randn(B, L, V, generator=g) * 0.5 - 1.0
+  if subs:
+    xt = torch.full((B, L), mask, dtype=torch.long)
+    xt[0, :2] = torch.tensor([7, 9])      # two carried-over tokens
+  else:
+    xt = torch.randint(0, V, (B, L), generator=g)
+  mc_t = torch.tensor([0.61, 0.37])
+  mc_s = torch.tensor([0.59, 0.33])
+  lp_dtype = torch.bfloat16 if round_bf16 else None
+  param = 'subs' if subs else 'd3pm'
+
+  def lps(l):
+    return ref_sampler.log_probs_from_logits(
+      l[:, :V].float().view(B, L, V), xt, parameterization=param,
+      mask_index=mask, lp_dtype=lp_dtype)
+  kw = dict(diffusion=diffusion, mask_index=mask, lp_dtype=lp_dtype)
+  mct3, mcs3 = mc_t[:, None, None], mc_s[:, None, None]
+  if guidance == 'none':
+    xs_ref, q_ref = ref_sampler.ddpm_update(lps(la), xt, mct3, mcs3, U, **kw)
+  elif guidance == 'cfg':
+    xs_ref, q_ref = ref_sampler.cfg_update(lps(la), lps(lb), 2.0, xt, mct3, mcs3, U, **kw)
+  else:
+    xs_ref, q_ref = ref_sampler.cbg_update(lps(la), clf, 1.5, xt, mct3, mcs3, U, **kw)
+  xs, q = helpers.sampler_kernel(
+    logits_a=la.to(dev), logits_b=lb.to(dev) if guidance == 'cfg' else None,
+    clf=clf if guidance == 'cbg' else None, noise=U, xt=xt, mc_t=mc_t,
+    mc_s=mc_s, vocab=V, seq_len=L, diffusion=diffusion, guidance=guidance,
+    gamma=2.0 if guidance == 'cfg' else 1.5, subs=subs, mask_logit=subs,
+    mask_index=mask, round_bf16=round_bf16, fast_math=False, want_q=True)
+  q = q.view(B, L, V).cpu()
+  # with the bf16 roundings on, an fp32 last-ulp difference can flip a bf16
+  # rounding (0.4 % of that element): allow <= 0.1 % of entries to move 1 bf16 ulp
+  helpers.assert_close_frac(q, q_ref, rtol=3e-4, atol=1e-6,
+                            loose_frac=1e-3 if round_bf16 else 0.0,
+                            loose_rtol=2e-2)
+  helpers.assert_ids_match(xs.view(B, L), xs_ref, q_ref, U,
+                           f'{diffusion}/{guidance}/V{V}',
+                           tol=2e-2 if round_bf16 else 2e-5)
+  if subs:   # carry-over (diffusion.py:1414-1418)
+    assert xs.view(B, L)[0, 0].item() == 7 and xs.view(B, L)[0, 1].item() == 9
+
+
+@pytest.mark.parametrize('diffusion,guidance', MODES)
+def test_philox_stream_matches_cpu_regeneration(diffusion, guidance):
+  """In-kernel Philox mode == injected-noise mode fed the same stream
+  regenerated on the CPU (pins the production RNG path bit for bit)."""
+  B, L, V, ld = 2, 5, 30522, 30528
+  rows = B * L
+  dev = torch.device('cuda')
+  subs = diffusion == 'absorbing_state'
+  la = _rand_logits(rows, V, ld, torch.bfloat16, 5).to(dev)
+  lb = _rand_logits(rows, V, ld, torch.bfloat16, 6).to(dev)
+  g = torch.Generator().manual_seed(7)
+  clf = torch.randn(B, L, V, generator=g) * 0.5
+  xt = (torch.full((B, L), 103, dtype=torch.long) if subs
+        else torch.randint(0, V, (B, L), generator=g))
+  seed, step = 0x1234567890ABCDEF, 17
+  U = torch.from_numpy(helpers.philox_uniform(seed, step, rows, V))
+  common = dict(logits_a=la, logits_b=lb if guidance == 'cfg' else None,
+                clf=clf if guidance == 'cbg' else None, xt=xt, mc_t=0.5,
+                mc_s=0.45, vocab=V, seq_len=L, diffusion=diffusion,
+                guidance=guidance, gamma=2.0, subs=subs, mask_logit=subs,
+                mask_index=103, round_bf16=True, fast_math=False)
+  xs_inj, _ = helpers.sampler_kernel(noise=U, **common)
+  xs_phx, _ = helpers.sampler_kernel(noise=None, seed=seed, step=step, **common)
+  assert torch.equal(xs_inj, xs_phx)
+  xs_other, _ = helpers.sampler_kernel(noise=None, seed=seed, step=step + 1, **common)
+  assert not torch.equal(xs_other, xs_phx)
+
+
+def test_fast_math_agrees_with_careful_math():
+  """Production (ex2/lg2 intrinsics) vs parity math: same ids except a few
+  near-ties, on a full-size LM1B UDLM D-CFG tile."""
+  B, L, V, ld = 8, 128, 30522, 30528
+  rows = B * L
+  dev = torch.device('cuda')
+  g = torch.Generator(device=dev).manual_seed(1)
+  la = (torch.randn(rows, ld, device=dev, generator=g) * 3).to(torch.bfloat16)
+  lb = (torch.randn(rows, ld, device=dev, generator=g) * 3).to(torch.bfloat16)
+  xt = torch.randint(0, V, (rows,), device=dev, generator=g)
+  common = dict(logits_a=la, logits_b=lb, xt=xt, mc_t=0.5, mc_s=0.499,
+                vocab=V, seq_len=L, diffusion='uniform', guidance='cfg',
+                gamma=2.0, round_bf16=True, seed=9, step=3)
+  a, _ = helpers.sampler_kernel(fast_math=False, **common)
+  b, _ = helpers.sampler_kernel(fast_math=True, **common)
+  frac = (a != b).float().mean().item()
+  assert frac < 5e-3, frac
+
+
+def test_full_size_properties():
+  """BASELINE.json config 3 shape per GPU (64 x 128 x 30522): properties that
+  do not need the CPU oracle."""
+  B, L, V, ld = 64, 128, 30522, 30528
+  rows = B * L
+  dev = torch.device('cuda')
+  g = torch.Generator(device=dev).manual_seed(2)
+  la = (torch.randn(rows, ld, device=dev, generator=g) * 3).to(torch.bfloat16)
+  lb = (torch.randn(rows, ld, device=dev, generator=g) * 3).to(torch.bfloat16)
+  xt = torch.randint(0, V, (rows,), device=dev, generator=g)
+  kw = dict(xt=xt, mc_t=0.7, mc_s=0.699, vocab=V, seq_len=L, round_bf16=True,
+            fast_math=True, seed=11, step=0)
+  # determinism
+  a, _ = helpers.sampler_kernel(logits_a=la, logits_b=lb, diffusion='uniform',
+                                guidance='cfg', gamma=2.0, **kw)
+  b, _ = helpers.sampler_kernel(logits_a=la, logits_b=lb, diffusion='uniform',
+                                guidance='cfg', gamma=2.0, **kw)
+  assert torch.equal(a, b)
+  assert int(a.min()) >= 0 and int(a.max()) < V
+  # gamma == 1 mixes to the conditional posterior alone
+  c, _ = helpers.sampler_kernel(logits_a=la, logits_b=lb, diffusion='uniform',
+                                guidance='cfg', gamma=1.0, **kw)
+  d, _ = helpers.sampler_kernel(logits_a=la, diffusion='uniform', guidance='none', **kw)
+  assert (c != d).float().mean().item() < 2e-3
+  # with mc_s ~ mc_t (tiny step) UDLM keeps almost every token
+  e, _ = helpers.sampler_kernel(logits_a=la, diffusion='uniform', guidance='none',
+                                **dict(kw, mc_t=0.5, mc_s=0.5 - 1e-6))
+  assert (e == xt).float().mean().item() > 0.99
+  # argmax selection == argmax of the analytic posterior (torch on the GPU)
+  f, _ = helpers.sampler_kernel(logits_a=la, diffusion='uniform', guidance='none',
+                                select='argmax', **dict(kw, round_bf16=False, fast_math=False))
+  x = torch.softmax(la[:, :V].float(), dim=-1)
+  a_s, a_t = 1 - 0.699, 1 - 0.7
+  q = (a_s - a_t) * x + (1 - a_t / a_s) * (1 - a_s) / V
+  q.scatter_add_(1, xt[:, None], (a_t * V * x.gather(1, xt[:, None]) + a_t / a_s - a_t))
+  assert (f == q.argmax(-1)).float().mean().item() > 0.999
+  # absorbing: unmasked tokens are carried over, masked ones never stay out of range
+  xt_m = xt.clone()
+  xt_m[::2] = 103
+  h, _ = helpers.sampler_kernel(logits_a=la, diffusion='absorbing_state', guidance='none',
+                                subs=True, mask_logit=True, mask_index=103,
+                                **dict(kw, xt=xt_m))
+  assert torch.equal(h[1::2], xt_m[1::2])
+
+
+def test_ar_gumbel_selection():
+  B, V = 16, 35
+  dev = torch.device('cuda')
+  g = torch.Generator().manual_seed(4)
+  logits = torch.randn(B, 64, generator=g) * 2
+  G = -torch.log(-torch.log(torch.rand(B, V, generator=g).clamp(1e-9, 1 - 1e-7)))
+  lp = torch.log_softmax(logits[:, :V], -1)
+  ref = ref_sampler.ar_select(lp, G)
+  xs, _ = helpers.sampler_kernel(
+    logits_a=logits.to(dev), xt=torch.zeros(B, dtype=torch.long), mc_t=0.0,
+    mc_s=0.0, vocab=V, seq_len=1, diffusion='ar', noise=G, select='gumbel')
+  assert torch.equal(xs.cpu(), ref)
+
+
+def test_error_semantics():
+  """Reference raises NotImplementedError for unknown diffusion / guidance
+  (diffusion.py:1364-1366, 1408-1410)."""
+  from ddg_b200 import _lib
+  dev = torch.device('cuda')
+  la = torch.zeros(4, 64, device=dev)
+  xt = torch.zeros(4, dtype=torch.long, device=dev)
+  a = _lib.SampleStepArgs(logits_a=la.data_ptr(), xt=xt.data_ptr(), xs=xt.data_ptr(),
+                          rows=4, ld_a=64, seq_len=4, vocab=35, diffusion=7)
+  with pytest.raises(NotImplementedError):
+    _lib.check(_lib.lib.ddg_sample_step(a, 0))
+  a.diffusion, a.guidance = 1, 9
+  with pytest.raises(NotImplementedError):
+    _lib.check(_lib.lib.ddg_sample_step(a, 0))
