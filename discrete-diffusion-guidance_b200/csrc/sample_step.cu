@@ -29,6 +29,9 @@ __host__ __device__ constexpr bool mode_two(int m) { return m == ABS_CFG || m ==
 __host__ __device__ constexpr bool mode_clf(int m) { return m == ABS_CBG || m == UNI_CBG; }
 __host__ __device__ constexpr bool mode_abs(int m) { return m <= ABS_CBG; }
 __host__ __device__ constexpr bool mode_uni(int m) { return m >= UNI_NONE && m <= UNI_CBG; }
+// modes whose q_xs the reference passes through a final softmax
+// (diffusion.py:1495, 1617); the others return the posterior as formed.
+__host__ __device__ constexpr bool mode_softmax(int m) { return m == UNI_CFG || m == ABS_CBG || m == UNI_CBG; }
 
 template <bool FAST> struct Mth {
   static __device__ __forceinline__ float exp(float x) { return FAST ? __expf(x) : expf(x); }
@@ -373,7 +376,7 @@ sample_step_kernel(const ddg_sample_step_args a) {
         }
         vm = fmaxf(vm, g[e]);
       }
-      if (a.q_out) {
+      if (a.q_out && mode_softmax(MODE)) {
         gacc.push_max(vm);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) gacc.add(g[e]);
@@ -382,11 +385,14 @@ sample_step_kernel(const ddg_sample_step_args a) {
     Grp<GROUP>::argmax(best, bidx, sm);
     if (bidx == 0x7fffffff) bidx = 0;   // every score was -inf / NaN
     if (lane_in_group == 0) a.xs[row] = (int64_t)bidx;
-    // ---------------- pass 3 (debug / API): normalised q_xs
+    // ---------------- pass 3 (debug / API): q_xs as the reference returns it
     if (a.q_out) {
-      float M, lnS;
-      lse_finish<GROUP, FAST>(gacc.m, gacc.s, sm, M, lnS);
-      const float lse = M + lnS;
+      float lse = 0.f;
+      if (mode_softmax(MODE)) {
+        float M, lnS;
+        lse_finish<GROUP, FAST>(gacc.m, gacc.s, sm, M, lnS);
+        lse = M + lnS;
+      }
       float* q = a.q_out + row * a.ld_q;
       for (int j0 = lane_in_group * VEC; j0 < V; j0 += GROUP * VEC) {
         float va[VEC], vb[VEC];

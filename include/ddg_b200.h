@@ -87,8 +87,9 @@ typedef struct ddg_sample_step_args {
   const uint64_t* seed_ptr; /* optional device Philox key (overrides `seed`)   */
   /* outputs */
   int64_t* xs;            /* (rows,) next ids z_s                             */
-  float* q_out;           /* optional (rows, ld_q): normalised guided
-                             posterior q_xs (the reference's 2nd return)      */
+  float* q_out;           /* optional (rows, ld_q): q_xs, the reference's 2nd
+                             return (softmax-normalised for D-CFG on uniform
+                             and for D-CBG, the posterior as formed otherwise) */
   /* sizes */
   int64_t rows;           /* B * L                                            */
   int64_t ld_a, ld_b, ld_clf, ld_noise, ld_q;

@@ -176,7 +176,7 @@ def test_philox_stream_matches_cpu_regeneration(diffusion, guidance):
   U = torch.from_numpy(helpers.philox_uniform(seed, step, rows, V))
   common = dict(logits_a=la, logits_b=lb if guidance == 'cfg' else None,
                 clf=clf if guidance == 'cbg' else None, xt=xt, mc_t=0.5,
-                mc_s=0.45, vocab=V, seq_len=L, diffusion=diffusion,
+                mc_s=0.05, vocab=V, seq_len=L, diffusion=diffusion,
                 guidance=guidance, gamma=2.0, subs=subs, mask_logit=subs,
                 mask_index=103, round_bf16=True, fast_math=False)
   xs_inj, _ = helpers.sampler_kernel(noise=U, **common)
