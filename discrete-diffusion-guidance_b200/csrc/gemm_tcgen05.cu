@@ -3,13 +3,14 @@
 // autocast).  out = epilogue(A[M,K] @ W[N,K]^T), 16-bit operands, fp32
 // accumulation in tensor memory.
 //
-// Structure (one persistent CTA per SM, 256 threads):
+// Structure (one persistent CTA per SM, 384 threads):
 //   warp 0     TMA producer: A/W k-blocks -> 128B-swizzled smem ring (4 stages)
 //   warp 1     MMA issuer:   one thread issues tcgen05.mma 128x256x16, commits
 //                            stage-release and accumulator-ready mbarriers
 //   warp 2     TMEM allocator (512 columns = 2 accumulators of 128x256 fp32)
-//   warps 4-7  epilogue: tcgen05.ld accumulator -> registers -> fused epilogue
-//              (bias / GELU-tanh / rotary / gate+residual) -> global
+//   warps 4-11 epilogue: tcgen05.ld accumulator -> registers -> fused epilogue
+//              (bias / GELU-tanh / rotary / gate+residual) -> padded smem slab
+//              -> coalesced global stores
 // The two TMEM accumulators let the epilogue of tile i overlap the MMAs of
 // tile i+1.
 #include <cuda.h>
@@ -27,11 +28,13 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int B_STAGE_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_THREADS = 256;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_ROW_BYTES = 80;                  // 64 B payload + 16 B pad: conflict-free 128-bit stores
+constexpr int EPI_SLAB_BYTES = 32 * EPI_ROW_BYTES;  // one warp's 32 accumulator rows
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * EPI_SLAB_BYTES;
 
 struct GemmParams {
   void* out;
@@ -85,6 +88,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
     "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
     ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
     : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)
+               : "memory");
+  return v;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -214,10 +226,25 @@ __device__ __forceinline__ void store32(T* out, const float (&v)[32], int n_vali
   }
 }
 
+// rounds 32 fp32 values to T and back with packed conversions (F2FP + unpack)
+template <typename T>
+__device__ __forceinline__ void round32(float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 f = H2<T>::unpack(H2<T>::pack(v[2 * i], v[2 * i + 1]));
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+
 __device__ __forceinline__ float gelu_tanh(float v) {
   // 0.5 v (1 + tanh(u)) == v * sigmoid(2u),  u = sqrt(2/pi) (v + 0.044715 v^3)
-  const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
-  return __fdividef(v, 1.f + __expf(-2.f * u));
+  // exp(-2u) = ex2(v * (c1 + c2 v^2)), c1 = -2 sqrt(2/pi) log2(e), c2 = 0.044715 c1
+  const float z = v * fmaf(v * v, -0.10294324f, -2.3022082f);
+  float ez, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ez) : "f"(z));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + ez));
+  return v * r;
 }
 
 // ------------------------------------------------------------------ kernel
@@ -235,6 +262,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* tmem_full = bars + 2 * STAGES;   // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* smem_epi = smem + STAGES * STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -309,104 +337,182 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     __syncwarp();
   } else if (warp >= EPI_WARP0) {
-    // ------------------------------------------------ epilogue
-    const int ew = warp - EPI_WARP0;            // TMEM lanes 32*ew .. 32*ew+31
-    const int row_in_tile = ew * 32 + lane;
+    // ------------------------------------------------ epilogue (8 warps)
+    // Warp e owns accumulator rows 32*(e%4).. (its TMEM lane quarter) and
+    // columns 128*(e/4)..: two warps per scheduler keep the FMA/MUFU work of
+    // the fused epilogues latency-hidden.  Register phase: thread = row (what
+    // tcgen05.ld 32x32b gives).  Finished values pass through a warp-private
+    // padded shared-memory slab (32 rows x 80 B) and come back with lanes
+    // running along the row, so each global access covers 8 rows x 64
+    // contiguous bytes instead of 32 rows x 16 bytes.
+    const int e = warp - EPI_WARP0;
+    const int quarter = e & 3;                  // == warp % 4: TMEM lanes 32*quarter..
+    const int chalf = e >> 2;                   // column half of the tile
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t stg = smem_u32(smem_epi + e * EPI_SLAB_BYTES);
+    const uint32_t stg_wr = stg + (uint32_t)lane * EPI_ROW_BYTES;
+    const int crow = lane >> 2;                 // coalesced phase: row in an 8-row slab
+    const int cchunk = lane & 3;                // 16-byte chunk of the 64-byte row
+    const uint32_t stg_rd = stg + (uint32_t)crow * EPI_ROW_BYTES + (uint32_t)cchunk * 16;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * BM;
-      const int n0 = (tile % num_n) * BN;
+      const int n0 = (tile % num_n) * BN + chalf * (BN / 2);
       const int m = m0 + row_in_tile;
       const bool row_ok = m < p.M;
+      const int mw = m0 + quarter * 32;         // first row of this warp's slab
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr =
+        tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chalf * (BN / 2));
 
-      float cs[32], sn[32];
-      if (EPI == DDG_EPI_QKV_ROPE) {
-        const int pos = row_ok ? (m % p.seq_len) : 0;
-        load32<T>(reinterpret_cast<const T*>(p.rope_cos) + (int64_t)pos * 32, cs);
-        load32<T>(reinterpret_cast<const T*>(p.rope_sin) + (int64_t)pos * 32, sn);
-      }
-      const T* gate_row = nullptr;
-      if (EPI == DDG_EPI_GATE_RESIDUAL && p.gate) {
-        const int64_t mrow = row_ok ? (int64_t)m / p.rows_per_mod : 0;
-        gate_row = reinterpret_cast<const T*>(p.gate) + mrow * p.gate_stride;
-      }
-
+      if (EPI == DDG_EPI_GATE_RESIDUAL) {
+        // -------- x += round(gate * round(acc + bias)), fp32 residual stream
+        const T* gate_row = nullptr;
+        if (p.gate) {
+          const int64_t mrow = row_ok ? (int64_t)m / p.rows_per_mod : 0;
+          gate_row = reinterpret_cast<const T*>(p.gate) + mrow * p.gate_stride;
+        }
+        float* xslab = reinterpret_cast<float*>(p.out) + (int64_t)mw * p.ld_out + cchunk * 4;
+        float4 xn[2][4];                         // x of the next 32 columns
+        auto prefetch_x = [&](int nc) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = 8 * i + crow;
+              const bool ok = (mw + row < p.M) && (nc + h * 16 + cchunk * 4 < p.N);
+              xn[h][i] = ok ? *reinterpret_cast<const float4*>(xslab + (int64_t)row * p.ld_out + nc + h * 16)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        prefetch_x(n0);
 #pragma unroll 1
-      for (int g = 0; g < BN / 64; ++g) {
-        const int nc = n0 + g * 64;             // first column of this 64-wide group
-        uint32_t r0[32], r1[32];
-        tmem_ld32(taddr + (uint32_t)(g * 64), r0);
-        tmem_ld32(taddr + (uint32_t)(g * 64 + 32), r1);
-        tmem_ld_wait(r0);
-        tmem_ld_wait(r1);
-        if (nc >= p.N) continue;                 // warp-uniform
-        float v0[32], v1[32];
+        for (int g = 0; g < BN / 64; ++g) {
+          const int nc = n0 + g * 32;
+          uint32_t r0[32];
+          tmem_ld32(taddr + (uint32_t)(g * 32), r0);
+          tmem_ld_wait(r0);
+          if (nc >= p.N) continue;               // warp-uniform
+          float4 xc[2][4];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { v0[i] = __uint_as_float(r0[i]); v1[i] = __uint_as_float(r1[i]); }
-        if (p.bias) {
-          float b0[32], b1[32];
-          load32<T>(reinterpret_cast<const T*>(p.bias) + nc, b0);
-          load32<T>(reinterpret_cast<const T*>(p.bias) + nc + 32, b1);
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { v0[i] += b0[i]; v1[i] += b1[i]; }
-        }
-        // the GEMM output itself is a 16-bit tensor in the reference
+            for (int i = 0; i < 4; ++i) xc[h][i] = xn[h][i];
+          if (g + 1 < BN / 64 && nc + 32 < p.N) prefetch_x(nc + 32);
+          float v0[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { v0[i] = Cvt<T>::round(v0[i]); v1[i] = Cvt<T>::round(v1[i]); }
-
-        if (EPI == DDG_EPI_QKV_ROPE) {
-          if (nc < p.rope_cols) {
-            // NeoX rotary on one 64-wide head: (x1, x2) = (d < 32, d >= 32)
+          for (int i = 0; i < 32; ++i) v0[i] = __uint_as_float(r0[i]);
+          if (p.bias) {
+            float b0[32];
+            load32<T>(reinterpret_cast<const T*>(p.bias) + nc, b0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x1 = v0[i], x2 = v1[i];
-              v0[i] = x1 * cs[i] - x2 * sn[i];
-              v1[i] = x1 * sn[i] + x2 * cs[i];
-            }
+            for (int i = 0; i < 32; ++i) v0[i] += b0[i];
           }
-        } else if (EPI == DDG_EPI_BIAS_GELU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { v0[i] = gelu_tanh(v0[i]); v1[i] = gelu_tanh(v1[i]); }
-        }
-
-        if (EPI == DDG_EPI_GATE_RESIDUAL) {
+          round32<T>(v0);
           if (gate_row) {
-            float g0[32], g1[32];
+            float g0[32];
             load32<T>(gate_row + nc, g0);
-            load32<T>(gate_row + nc + 32, g1);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              v0[i] = Cvt<T>::round(g0[i] * v0[i]);
-              v1[i] = Cvt<T>::round(g1[i] * v1[i]);
-            }
+            for (int i = 0; i < 32; ++i) v0[i] *= g0[i];
+            round32<T>(v0);
           }
-          if (row_ok) {
-            float* xr = reinterpret_cast<float*>(p.out) + (int64_t)m * p.ld_out + nc;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float* vv = h ? v1 : v0;
-              if (nc + h * 32 + 32 <= p.N) {
+          for (int h = 0; h < 2; ++h) {
+            __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float4 x4 = reinterpret_cast<float4*>(xr + h * 32)[i];
-                  x4.x += vv[4 * i]; x4.y += vv[4 * i + 1]; x4.z += vv[4 * i + 2]; x4.w += vv[4 * i + 3];
-                  reinterpret_cast<float4*>(xr + h * 32)[i] = x4;
-                }
-              } else {
-                for (int i = 0; i < 32; ++i)
-                  if (nc + h * 32 + i < p.N) xr[h * 32 + i] += vv[i];
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(stg_wr + q * 16, __float_as_uint(v0[16 * h + 4 * q]),
+                           __float_as_uint(v0[16 * h + 4 * q + 1]), __float_as_uint(v0[16 * h + 4 * q + 2]),
+                           __float_as_uint(v0[16 * h + 4 * q + 3]));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = 8 * i + crow;
+              const uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
+              if ((mw + row < p.M) && (nc + h * 16 + cchunk * 4 < p.N)) {
+                float4 o = xc[h][i];
+                o.x += __uint_as_float(y.x); o.y += __uint_as_float(y.y);
+                o.z += __uint_as_float(y.z); o.w += __uint_as_float(y.w);
+                *reinterpret_cast<float4*>(xslab + (int64_t)row * p.ld_out + nc + h * 16) = o;
               }
             }
           }
-        } else {
-          if (row_ok) {
-            T* orow = reinterpret_cast<T*>(p.out) + (int64_t)m * p.ld_out + nc;
-            store32<T>(orow, v0, p.N - nc);
-            store32<T>(orow + 32, v1, p.N - nc - 32);
+        }
+      } else {
+        // -------- 16-bit outputs: store / rotary / bias+GELU
+        float cs[32], sn[32];
+        if (EPI == DDG_EPI_QKV_ROPE) {
+          const int pos = row_ok ? (m % p.seq_len) : 0;
+          load32<T>(reinterpret_cast<const T*>(p.rope_cos) + (int64_t)pos * 32, cs);
+          load32<T>(reinterpret_cast<const T*>(p.rope_sin) + (int64_t)pos * 32, sn);
+        }
+        T* oslab = reinterpret_cast<T*>(p.out) + (int64_t)mw * p.ld_out + cchunk * 8;
+#pragma unroll 1
+        for (int g = 0; g < BN / 128; ++g) {
+          const int nc = n0 + g * 64;             // first column of this 64-wide group
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + (uint32_t)(g * 64), r0);
+          tmem_ld32(taddr + (uint32_t)(g * 64 + 32), r1);
+          tmem_ld_wait(r0);
+          tmem_ld_wait(r1);
+          if (nc >= p.N) continue;                 // warp-uniform
+          float v0[32], v1[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v0[i] = __uint_as_float(r0[i]); v1[i] = __uint_as_float(r1[i]); }
+          if (p.bias) {
+            float b0[32], b1[32];
+            load32<T>(reinterpret_cast<const T*>(p.bias) + nc, b0);
+            load32<T>(reinterpret_cast<const T*>(p.bias) + nc + 32, b1);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v0[i] += b0[i]; v1[i] += b1[i]; }
+          }
+          if (EPI == DDG_EPI_QKV_ROPE) {
+            if (nc < p.rope_cols) {
+              // the GEMM output is a 16-bit tensor in the reference; the rotary
+              // then runs in fp32 on those values (NeoX: x1 = d < 32, x2 = d >= 32)
+              round32<T>(v0);
+              round32<T>(v1);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x1 = v0[i], x2 = v1[i];
+                v0[i] = x1 * cs[i] - x2 * sn[i];
+                v1[i] = x1 * sn[i] + x2 * cs[i];
+              }
+            }
+          } else if (EPI == DDG_EPI_BIAS_GELU) {
+            round32<T>(v0);
+            round32<T>(v1);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v0[i] = gelu_tanh(v0[i]); v1[i] = gelu_tanh(v1[i]); }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float* vv = h ? v1 : v0;
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(stg_wr + q * 16, H2<T>::pack(vv[8 * q], vv[8 * q + 1]),
+                           H2<T>::pack(vv[8 * q + 2], vv[8 * q + 3]), H2<T>::pack(vv[8 * q + 4], vv[8 * q + 5]),
+                           H2<T>::pack(vv[8 * q + 6], vv[8 * q + 7]));
+            __syncwarp();
+            const int col = nc + h * 32 + cchunk * 8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = 8 * i + crow;
+              const uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
+              if (mw + row < p.M) {
+                T* dst = oslab + (int64_t)row * p.ld_out + nc + h * 32;
+                if (col + 8 <= p.N) {
+                  *reinterpret_cast<uint4*>(dst) = y;
+                } else {
+                  const T* ye = reinterpret_cast<const T*>(&y);
+                  for (int k = 0; k < 8; ++k)
+                    if (col + k < p.N) dst[k] = ye[k];
+                }
+              }
+            }
           }
         }
       }
@@ -506,7 +612,8 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
               reinterpret_cast<uintptr_t>(a.out) % 16 == 0, DDG_ERR_INVALID, "gemm: a/w/out must be 16-byte aligned");
   DDG_REQUIRE(a.ld_out >= a.N, DDG_ERR_INVALID, "gemm: ld_out < N");
   if (a.epilogue == DDG_EPI_GATE_RESIDUAL)
-    DDG_REQUIRE(a.ld_out % 4 == 0, DDG_ERR_INVALID, "gemm: fp32 residual ld_out must be a multiple of 4");
+    DDG_REQUIRE(a.ld_out % 4 == 0 && a.N % 4 == 0, DDG_ERR_INVALID,
+                "gemm: fp32 residual N and ld_out must be multiples of 4");
   else
     DDG_REQUIRE(a.ld_out % 8 == 0, DDG_ERR_INVALID, "gemm: 16-bit ld_out must be a multiple of 8");
   if (a.bias) DDG_REQUIRE(reinterpret_cast<uintptr_t>(a.bias) % 16 == 0, DDG_ERR_INVALID, "gemm: bias alignment");
