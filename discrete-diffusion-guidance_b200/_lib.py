@@ -42,7 +42,8 @@ class SampleStepArgs(C.Structure):
     ('guidance', C.c_int32), ('subs', C.c_int32), ('mask_logit', C.c_int32),
     ('mask_index', C.c_int32), ('round_bf16', C.c_int32),
     ('select', C.c_int32), ('fast_math', C.c_int32), ('gamma', C.c_float),
-    ('seed', C.c_uint64), ('step', C.c_int32), ('reserved', C.c_int32)]
+    ('seed', C.c_uint64), ('step', C.c_int32), ('stats_chunks', C.c_int32),
+    ('stats_a', C.c_void_p), ('stats_b', C.c_void_p), ('stats_ld', C.c_int64)]
 
 
 class GemmArgs(C.Structure):
@@ -53,7 +54,9 @@ class GemmArgs(C.Structure):
     ('ld_out', C.c_int64), ('gate_stride', C.c_int64),
     ('rows_per_mod', C.c_int64), ('M', C.c_int32), ('N', C.c_int32),
     ('K', C.c_int32), ('dtype', C.c_int32), ('epilogue', C.c_int32),
-    ('seq_len', C.c_int32), ('head_dim', C.c_int32), ('rope_cols', C.c_int32)]
+    ('seq_len', C.c_int32), ('head_dim', C.c_int32), ('rope_cols', C.c_int32),
+    ('stats', C.c_void_p), ('stats_ld', C.c_int64),
+    ('stats_mask_col', C.c_int32), ('reserved', C.c_int32)]
 
 
 def _load():

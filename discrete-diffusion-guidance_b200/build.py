@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libddg_b200.so')
 STAMP = os.path.join(HERE, 'csrc', '.build_stamp')
-SOURCES = ['capi.cu', 'sample_step.cu', 'dit_ops.cu', 'gemm_tcgen05.cu',
-           'attention.cu']
+SOURCES = ['capi.cu', 'sample_step.cu', 'sample_fused.cu', 'dit_ops.cu',
+           'gemm_tcgen05.cu', 'attention.cu']
 NVCC_FLAGS = [
   '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
   '-std=c++17', '--threads', '8', '-Xcompiler', '-fPIC', '-Xcompiler',

@@ -45,6 +45,9 @@ struct GemmParams {
   int64_t ld_out, gate_stride, rows_per_mod;
   int M, N, K;
   int seq_len, rope_cols;
+  float2* stats;        // optional per-(128-column chunk, row) softmax partials
+  int64_t stats_ld;
+  int mask_col;         // column excluded from the partials (-1: none)
 };
 
 // ------------------------------------------------------------------ PTX
@@ -235,6 +238,13 @@ __device__ __forceinline__ void round32(float (&v)[32]) {
     v[2 * i] = f.x;
     v[2 * i + 1] = f.y;
   }
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ float gelu_tanh(float v) {
@@ -449,6 +459,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           load32<T>(reinterpret_cast<const T*>(p.rope_sin) + (int64_t)pos * 32, sn);
         }
         T* oslab = reinterpret_cast<T*>(p.out) + (int64_t)mw * p.ld_out + cchunk * 8;
+        float st_m = -INFINITY, st_s = 0.f;      // running (max, sum 2^((v-max) log2e)) of this row chunk
 #pragma unroll 1
         for (int g = 0; g < BN / 128; ++g) {
           const int nc = n0 + g * 64;             // first column of this 64-wide group
@@ -486,6 +497,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             round32<T>(v1);
 #pragma unroll
             for (int i = 0; i < 32; ++i) { v0[i] = gelu_tanh(v0[i]); v1[i] = gelu_tanh(v1[i]); }
+          } else if (EPI == DDG_EPI_STORE && p.stats != nullptr) {
+            // log-softmax partials of the stored (rounded) logits, so that the
+            // fused sampler never needs its own normaliser pass over the row
+            round32<T>(v0);
+            round32<T>(v1);
+            const bool plain = (nc + 64 <= p.N) && !(p.mask_col >= nc && p.mask_col < nc + 64);
+            float gm = -INFINITY;
+            if (plain) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) gm = fmaxf(gm, fmaxf(v0[i], v1[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (nc + i < p.N && nc + i != p.mask_col) gm = fmaxf(gm, v0[i]);
+                if (nc + 32 + i < p.N && nc + 32 + i != p.mask_col) gm = fmaxf(gm, v1[i]);
+              }
+            }
+            const float nm = fmaxf(st_m, gm);
+            if (nm > -INFINITY) {
+              const float nml = nm * kLog2e;
+              st_s *= ex2f_approx(st_m * kLog2e - nml);
+              float add = 0.f;
+              if (plain) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  add += ex2f_approx(fmaf(v0[i], kLog2e, -nml)) + ex2f_approx(fmaf(v1[i], kLog2e, -nml));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  if (nc + i < p.N && nc + i != p.mask_col) add += ex2f_approx(fmaf(v0[i], kLog2e, -nml));
+                  if (nc + 32 + i < p.N && nc + 32 + i != p.mask_col)
+                    add += ex2f_approx(fmaf(v1[i], kLog2e, -nml));
+                }
+              }
+              st_s += add;
+              st_m = nm;
+            }
           }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -515,6 +563,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
           }
         }
+        if (EPI == DDG_EPI_STORE && p.stats != nullptr && row_ok && n0 < p.N)
+          p.stats[(int64_t)(n0 / (BN / 2)) * p.stats_ld + m] = make_float2(st_m, st_s);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -634,6 +684,12 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
   p.out = a.out; p.bias = a.bias; p.gate = a.gate; p.rope_cos = a.rope_cos; p.rope_sin = a.rope_sin;
   p.ld_out = a.ld_out; p.gate_stride = a.gate_stride; p.rows_per_mod = a.rows_per_mod;
   p.M = a.M; p.N = a.N; p.K = a.K; p.seq_len = a.seq_len; p.rope_cols = a.rope_cols;
+  p.stats = reinterpret_cast<float2*>(a.stats); p.stats_ld = a.stats_ld; p.mask_col = a.stats_mask_col;
+  if (a.stats) {
+    DDG_REQUIRE(a.epilogue == DDG_EPI_STORE && a.stats_ld >= a.M &&
+                reinterpret_cast<uintptr_t>(a.stats) % 8 == 0, DDG_ERR_INVALID,
+                "gemm: softmax partials need the STORE epilogue and stats_ld >= M");
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a.dtype == DDG_F16) return dispatch_epi<__half>(a.epilogue, ta, tb, p, s);
   return dispatch_epi<__nv_bfloat16>(a.epilogue, ta, tb, p, s);

@@ -16,6 +16,7 @@
 #include "ddg_common.cuh"
 
 namespace ddg {
+int try_sample_fused(const ddg_sample_step_args& a, cudaStream_t s);   // sample_fused.cu
 namespace {
 
 constexpr float kNegInf = -1000000.0f;  // diffusion.py:141
@@ -564,6 +565,11 @@ extern "C" int ddg_sample_step(const ddg_sample_step_args* args, ddg_stream_t st
   if (a.q_out) DDG_REQUIRE(a.ld_q >= a.vocab, DDG_ERR_INVALID, "sample_step: ld_q < vocab");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool two = mode_two(mode);
+  {
+    // single-pass production kernel when the GEMM supplied its softmax partials
+    const int took = try_sample_fused(a, s);
+    if (took != 0) return took < 0 ? took : DDG_OK;
+  }
   if (a.logits_dtype == DDG_BF16) {
     const int64_t vpad = (a.vocab + 7) / 8 * 8;
     bool ok = (reinterpret_cast<uintptr_t>(a.logits_a) % 16 == 0) && a.ld_a % 8 == 0 && a.ld_a >= vpad;

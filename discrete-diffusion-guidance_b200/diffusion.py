@@ -65,6 +65,7 @@ class Diffusion:
     self.seed = int(config.get('seed', 1))
     self._call_count = 0
     self._loop = None
+    self._stats = {}            # logits data_ptr -> (stats tensor, row offset)
 
   # ---------------------------------------------------------------- weights
   def load_state_dict(self, state_dict, strict=True):
@@ -124,11 +125,21 @@ class Diffusion:
     return (_lib.SELECT_ARGMAX if ev.get('argmax_sampling', False)
             else _lib.SELECT_RACE)
 
+  @property
+  def _stats_mask_col(self):
+    return self.mask_index if self._mask_logit else -1
+
   def _logits(self, x, sigma, cond=None):
     """Backbone call of Diffusion.forward (diffusion.py:350-354): raw bf16
-    logits, shape (B, L, V) (strided view)."""
+    logits, shape (B, L, V) (strided view).  The vocab GEMM also leaves its
+    log-softmax partials for the fused sampler."""
     sigma = self._process_sigma(sigma)
-    return self.backbone.forward(x, sigma, cond)
+    B, L = x.shape
+    stats = self.backbone.alloc_stats(B * L)
+    logits = self.backbone.forward(x, sigma, cond, stats_out=stats,
+                                   stats_mask_col=self._stats_mask_col)
+    self._stats = {logits.data_ptr(): (stats, 0)}
+    return logits
 
   def forward(self, x, sigma, cond=None, x_emb=None, **kwargs):
     """Returns log-probs (B, L, V) fp32 like `Diffusion.forward`
@@ -176,8 +187,19 @@ class Diffusion:
                       mc_seq_stride=0, mc_step_stride=0, step_ptr=None, step=0,
                       guidance=_lib.GUIDE_NONE, gamma=1.0, q_out=None,
                       select=None, diffusion=None, logits_dtype=_lib.BF16,
-                      seed_ptr=None):
+                      seed_ptr=None, stats=None):
     V = self.vocab_size
+    # log-softmax partials of these logits, if our own vocab GEMM made them:
+    # stats = (tensor (chunks, rows_total, 2), row offset of a, row offset of b)
+    if stats is None and logits_a in self._stats:
+      st, off = self._stats[logits_a]
+      off_b = self._stats.get(logits_b, (None, 0))[1] if logits_b else 0
+      stats = (st, off, off_b)
+    st_a = st_b = st_ld = st_chunks = 0
+    if stats is not None:
+      st, off_a, off_b = stats
+      st_a, st_b = st.data_ptr() + off_a * 8, st.data_ptr() + off_b * 8
+      st_ld, st_chunks = st.shape[1], st.shape[0]
     a = _lib.SampleStepArgs(
       logits_a=logits_a, logits_b=logits_b or 0, clf=ptr(clf), noise=ptr(noise),
       xt=ptr(xt), mc_t=ptr(mc_t), mc_s=ptr(mc_s), step_ptr=ptr(step_ptr),
@@ -194,7 +216,8 @@ class Diffusion:
       select=self._select_code() if select is None else select,
       fast_math=1 if (self.fast_math and noise is None) else 0,
       gamma=float(gamma), seed=self.seed + 7919 * self._call_count,
-      step=int(step), reserved=0)
+      step=int(step), stats_chunks=st_chunks, stats_a=st_a,
+      stats_b=st_b if logits_b else 0, stats_ld=st_ld)
     check(lib.ddg_sample_step(a, stream_ptr()))
 
   def _mc(self, mc):
@@ -248,9 +271,12 @@ class Diffusion:
       mod = ModSpec(n_mod=2 * B, seqs_per_mod=1, sigma=torch.cat([sigma, sigma]),
                     sigma_row_stride=1, labels=torch.cat([cond, mask_cond]))
       buf = self.backbone.alloc_logits(2 * B * L)
-      self.backbone.run(xt, 2 * B, L, mod, buf, ids_period=B * L)
+      stats = self.backbone.alloc_stats(2 * B * L)
+      self.backbone.run(xt, 2 * B, L, mod, buf, ids_period=B * L,
+                        stats_out=stats, stats_mask_col=self._stats_mask_col)
       both = buf.view(2, B, L, self.backbone.vocab_ld)[..., :self.vocab_size]
       lc, lu = both[0], both[1]
+      self._stats = {lc.data_ptr(): (stats, 0), lu.data_ptr(): (stats, B * L)}
     xs = torch.empty_like(xt)
     q = (torch.empty(B, L, self.vocab_size, dtype=torch.float32, device=self.device)
          if self.return_q_xs else None)
@@ -447,6 +473,7 @@ class _GraphLoop:
     self.step = torch.zeros(1, dtype=torch.int32, device=dev)
     self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)  # Philox key
     self.logits = model.backbone.alloc_logits(self.n_fwd * B * L)
+    self.stats = model.backbone.alloc_stats(self.n_fwd * B * L)
     self.labels = (torch.zeros(self.n_fwd, dtype=torch.int64, device=dev)
                    if method == 'cfg' else None)
     self.tables = None
@@ -461,7 +488,8 @@ class _GraphLoop:
                   sigma_row_stride=0, sigma_step_stride=1, step_ptr=self.step,
                   labels=self.labels)
     m.backbone.run(self.xt, self.n_fwd * B, L, mod, self.logits,
-                   ids_period=B * L)
+                   ids_period=B * L, stats_out=self.stats,
+                   stats_mask_col=m._stats_mask_col)
     ld = m.backbone.vocab_ld
     m._launch_sampler(
       logits_a=self.logits.data_ptr(), ld_a=ld,
@@ -469,6 +497,7 @@ class _GraphLoop:
       ld_b=ld if self.two else 0, xt=self.xt, xs=self.xt, mc_t=mct, mc_s=mcs,
       rows=B * L, seq_len=L, mc_seq_stride=0, mc_step_stride=1,
       step_ptr=self.step, seed_ptr=self.seed_dev,
+      stats=(self.stats, 0, B * L if self.two else 0),
       guidance=_lib.GUIDE_CFG if self.two else _lib.GUIDE_NONE,
       gamma=self.gamma if self.two else 1.0)
     check(lib.ddg_step_advance(ptr(self.step), stream_ptr()))

@@ -184,10 +184,22 @@ class DIT:
     return torch.empty(rows, self.vocab_ld, dtype=self.head_dtype,
                        device=self.device)
 
+  @property
+  def stats_chunks(self) -> int:
+    return (self.vocab_size + 127) // 128
+
+  def alloc_stats(self, rows: int) -> torch.Tensor:
+    """(chunks, rows, 2) fp32 log-softmax partials written by the vocab GEMM
+    epilogue and consumed by the single-pass sampler."""
+    return torch.empty(self.stats_chunks, rows, 2, dtype=torch.float32,
+                       device=self.device)
+
   # ------------------------------------------------------------------ forward
   def run(self, ids: torch.Tensor, n_seqs: int, L: int, mod: ModSpec,
           logits_out: typing.Optional[torch.Tensor] = None,
-          ids_period: typing.Optional[int] = None):
+          ids_period: typing.Optional[int] = None,
+          stats_out: typing.Optional[torch.Tensor] = None,
+          stats_mask_col: int = -1):
     """Launches one forward over `n_seqs` sequences of length L.  `ids` holds
     `ids_period` (default n_seqs*L) int64 token ids, reused cyclically.
     Denoiser: writes logits (rows, vocab_ld) bf16 into `logits_out`.
@@ -237,13 +249,15 @@ class DIT:
       if (r0 % period) + n > period and not (r0 == 0 and n == M):
         raise ValueError('micro-batch straddles the id period')
       self._run_segment(ws, ids, r0, n, L, period, mod0, rpm_arg, mod_stride,
-                        cos, sin, logits_out, bcode, hcode, s)
+                        cos, sin, logits_out, bcode, hcode, s, stats_out,
+                        stats_mask_col)
     if self.classifier:
       return ws['x'][:M]
     return logits_out
 
   def _run_segment(self, ws, ids, r0, n, L, period, mod0, rpm, mod_stride, cos,
-                   sin, logits_out, bcode, hcode, s):
+                   sin, logits_out, bcode, hcode, s, stats_out=None,
+                   stats_mask_col=-1):
     h, nb = self.hidden, self.n_blocks
     x = ptr(ws['x']) + r0 * h * 4
     a16, qkv, h4 = ptr(ws['a16']), ptr(ws['qkv']), ptr(ws['h4'])
@@ -252,12 +266,13 @@ class DIT:
     ada = self.use_adaln
 
     def gemm(a, lda, w, ldw, out, ld_out, N, K, epi, dtype, bias=0, gate=0,
-             gate_stride=0):
+             gate_stride=0, stats=0, stats_ld=0):
       g = _lib.GemmArgs(
         a=a, w=w, out=out, bias=bias, gate=gate, rope_cos=ptr(cos),
         rope_sin=ptr(sin), lda=lda, ldw=ldw, ld_out=ld_out,
         gate_stride=gate_stride, rows_per_mod=rpm, M=n, N=N, K=K, dtype=dtype,
-        epilogue=epi, seq_len=L, head_dim=self.head_dim, rope_cols=2 * h)
+        epilogue=epi, seq_len=L, head_dim=self.head_dim, rope_cols=2 * h,
+        stats=stats, stats_ld=stats_ld, stats_mask_col=stats_mask_col)
       check(lib.ddg_gemm(g, s))
 
     for i in range(nb):
@@ -287,13 +302,16 @@ class DIT:
     check(lib.ddg_ln_modulate(
       x, n, h, 0, period, 0, ptr(self.ln_f), mf if fin else 0,
       mf + h * 2 if fin else 0, 2 * h, rpm, hcode, a16, s))
+    st, st_ld = 0, 0
+    if stats_out is not None:    # (chunks, rows_total, 2): this segment starts at row r0
+      st, st_ld = ptr(stats_out) + r0 * 8, stats_out.shape[1]
     gemm(a16, h, ptr(self.w_vocab), h, ptr(logits_out) + r0 * self.vocab_ld * 2,
          self.vocab_ld, self.vocab_size, h, _lib.EPI_STORE, hcode,
-         bias=ptr(self.b_vocab))
+         bias=ptr(self.b_vocab), stats=st, stats_ld=st_ld)
 
   # ------------------------------------------------------------------ API
   def forward(self, indices, sigma, cond=None, x_emb=None,
-              return_hidden_states=False):
+              return_hidden_states=False, stats_out=None, stats_mask_col=-1):
     """`DIT.forward(indices, sigma, cond)` (models/dit.py:426-468): logits
     (B, L, V) bf16 (a view of the padded buffer)."""
     if x_emb is not None or return_hidden_states:
@@ -308,7 +326,8 @@ class DIT:
     if cond is not None:
       mod.labels = cond.to(self.device, torch.int64).contiguous()
     logits = self.alloc_logits(B * L)
-    self.run(ids, B, L, mod, logits)
+    self.run(ids, B, L, mod, logits, stats_out=stats_out,
+             stats_mask_col=stats_mask_col)
     return logits.view(B, L, self.vocab_ld)[:, :, :self.vocab_size]
 
   __call__ = forward

@@ -114,7 +114,13 @@ typedef struct ddg_sample_step_args {
   float gamma;            /* guidance.gamma                                   */
   uint64_t seed;          /* Philox key                                       */
   int32_t step;           /* Philox counter word 3 when step_ptr == NULL      */
-  int32_t reserved;
+  int32_t stats_chunks;   /* number of 128-column chunks in stats_a/b         */
+  /* optional log-softmax partials written by ddg_gemm (see ddg_gemm_args):
+   * with them (bf16 logits, 16-byte-aligned rows, no q_out) the kernel reads
+   * every logit exactly once.                                               */
+  const void* stats_a;
+  const void* stats_b;
+  int64_t stats_ld;
 } ddg_sample_step_args;
 
 DDG_API int ddg_sample_step(const ddg_sample_step_args* args, ddg_stream_t stream);
@@ -206,6 +212,14 @@ typedef struct ddg_gemm_args {
   int32_t seq_len;      /* QKV_ROPE: position = m % seq_len                  */
   int32_t head_dim;     /* QKV_ROPE: 64                                      */
   int32_t rope_cols;    /* QKV_ROPE: columns [0, rope_cols) are q,k heads    */
+  /* STORE only, optional: log-softmax partials of the stored (rounded) rows.
+   * stats[(n / 128) * stats_ld + m] = (max_j v_mj, sum_j 2^((v_mj - max) log2 e))
+   * over the 128-column chunk, as float2; column stats_mask_col (or -1) is
+   * left out.  ddg_sample_step uses them to skip its normaliser pass.       */
+  void* stats;
+  int64_t stats_ld;
+  int32_t stats_mask_col;
+  int32_t reserved;
 } ddg_gemm_args;
 
 /* tcgen05 / TMEM / TMA GEMM: out = epilogue(a @ w^T). */

@@ -102,7 +102,8 @@ def sampler_kernel(*, logits_a, xt, mc_t, mc_s, vocab, seq_len, diffusion,
                    logits_b=None, clf=None, noise=None, guidance='none',
                    gamma=1.0, subs=False, mask_logit=False, mask_index=0,
                    round_bf16=False, select='race', fast_math=False, seed=0,
-                   step=0, want_q=False):
+                   step=0, want_q=False, stats_a=0, stats_b=0, stats_ld=0,
+                   stats_chunks=0):
   """Direct call of ddg_sample_step through the C ABI on torch CUDA tensors.
   logits (rows, ld) f32 or bf16; xt (rows,) int64; mc_* scalars or (n_seq,)."""
   from ddg_b200 import _lib
@@ -132,7 +133,8 @@ def sampler_kernel(*, logits_a, xt, mc_t, mc_s, vocab, seq_len, diffusion,
     guidance=gcode, subs=int(subs), mask_logit=int(mask_logit),
     mask_index=mask_index, round_bf16=int(round_bf16), select=scode,
     fast_math=int(fast_math), gamma=float(gamma), seed=int(seed),
-    step=int(step), reserved=0)
+    step=int(step), stats_chunks=stats_chunks, stats_a=stats_a, stats_b=stats_b,
+    stats_ld=stats_ld)
   _lib.check(_lib.lib.ddg_sample_step(a, _lib.stream_ptr()))
   torch.cuda.synchronize()
   return xs, q
@@ -175,3 +177,22 @@ def assert_close_frac(a, b, rtol, atol, loose_frac=0.0, loose_rtol=0.0):
   worst = (err[bad] / (atol + b.abs()[bad])).max().item()
   assert bool((err[bad] <= atol + loose_rtol * b.abs()[bad]).all()), (
     f'loose entries exceed rtol={loose_rtol}: worst {worst:.3e}')
+
+
+def make_stats(logits, vocab, mask_col=-1):
+  """Torch restatement of the vocab-GEMM epilogue's log-softmax partials
+  (ddg_gemm_args.stats): per 128-column chunk (max, sum 2^((v-max) log2 e)),
+  laid out (chunks, rows, 2) fp32."""
+  rows = logits.shape[0]
+  v = logits[:, :vocab].float()
+  if mask_col >= 0:
+    v = v.clone()
+    v[:, mask_col] = float('-inf')
+  chunks = (vocab + 127) // 128
+  pad = chunks * 128 - vocab
+  if pad:
+    v = torch.cat([v, torch.full((rows, pad), float('-inf'), device=v.device)], 1)
+  v = v.view(rows, chunks, 128)
+  m = v.amax(-1)
+  s = torch.exp2((v - m[..., None]) * 1.4426950408889634).sum(-1)
+  return torch.stack([m, s], -1).permute(1, 0, 2).contiguous()

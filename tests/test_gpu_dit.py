@@ -301,3 +301,35 @@ def test_gemm_rejects_bad_arguments():
                     epilogue=_lib.EPI_STORE, rows_per_mod=1, seq_len=1, head_dim=64)
   with pytest.raises(ValueError):
     _lib.check(_lib.lib.ddg_gemm(g, 0))
+
+
+@pytest.mark.parametrize('mask_col', [-1, 103])
+def test_gemm_vocab_softmax_partials(mask_col):
+  """STORE epilogue side output: per-(128-column chunk, row) log-softmax
+  partials of the stored bf16 logits; folding them must give logsumexp."""
+  M, N, K = 300, 30522, 128
+  g = torch.Generator().manual_seed(11)
+  a = torch.randn(M, K, generator=g).to(torch.bfloat16).to(DEV)
+  w = (torch.randn(N, K, generator=g) * 0.3).to(torch.bfloat16).to(DEV)
+  bias = torch.zeros(30720, dtype=torch.bfloat16, device=DEV)
+  bias[:N] = (torch.randn(N, generator=g)).to(torch.bfloat16)
+  out = torch.zeros(M, 30528, dtype=torch.bfloat16, device=DEV)
+  chunks = (N + 127) // 128
+  stats = torch.full((chunks, M, 2), float('nan'), device=DEV)
+  garg = _lib.GemmArgs(a=a.data_ptr(), w=w.data_ptr(), out=out.data_ptr(),
+                       bias=bias.data_ptr(), lda=K, ldw=K, ld_out=30528, M=M, N=N,
+                       K=K, dtype=_lib.BF16, epilogue=_lib.EPI_STORE, rows_per_mod=1,
+                       seq_len=1, head_dim=64, stats=stats.data_ptr(), stats_ld=M,
+                       stats_mask_col=mask_col)
+  _lib.check(_lib.lib.ddg_gemm(garg, _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  assert not bool(torch.isnan(stats).any())
+  ref = helpers.make_stats(out, N, mask_col)
+  torch.testing.assert_close(stats[..., 0], ref[..., 0], rtol=0, atol=0)
+  torch.testing.assert_close(stats[..., 1], ref[..., 1], rtol=2e-4, atol=1e-6)
+  m, s = stats[..., 0], stats[..., 1]
+  lse = torch.logsumexp(m + torch.log(s), dim=0)
+  v = out[:, :N].float()
+  if mask_col >= 0:
+    v[:, mask_col] = float('-inf')
+  torch.testing.assert_close(lse, torch.logsumexp(v, -1), rtol=1e-5, atol=1e-4)

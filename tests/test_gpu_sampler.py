@@ -278,3 +278,99 @@ def test_error_semantics():
   a.diffusion, a.guidance = 1, 9
   with pytest.raises(NotImplementedError):
     _lib.check(_lib.lib.ddg_sample_step(a, 0))
+
+
+FUSED_MODES = [('uniform', 'none'), ('uniform', 'cfg'), ('absorbing_state', 'none')]
+
+
+@pytest.mark.parametrize('diffusion,guidance', FUSED_MODES)
+@pytest.mark.parametrize('round_bf16', [True, False])
+def test_fused_single_pass_matches_generic_kernel(diffusion, guidance, round_bf16):
+  """The production single-pass kernel (GEMM-supplied softmax partials, base-2
+  intrinsics) against the careful generic kernel on the same logits and
+  injected uniforms: ids equal except near-ties (|score gap| <= 1e-3 rel. with
+  the intrinsics; 2e-2 when a bf16 rounding may flip)."""
+  B, L, V, ld = 4, 16, 30522, 30528
+  rows = B * L
+  dev = torch.device('cuda')
+  subs = diffusion == 'absorbing_state'
+  mask = 103
+  la = _rand_logits(rows, V, ld, torch.bfloat16, 21).to(dev)
+  lb = _rand_logits(rows, V, ld, torch.bfloat16, 22).to(dev)
+  g = torch.Generator().manual_seed(23)
+  U = torch.rand(B, L, V, generator=g)
+  if subs:
+    xt = torch.full((B, L), mask, dtype=torch.long)
+    xt[1, :3] = torch.tensor([5, 6, 7])
+  else:
+    xt = torch.randint(0, V, (B, L), generator=g)
+  st_a = helpers.make_stats(la, V, mask if subs else -1)
+  st_b = helpers.make_stats(lb, V, -1)
+  mc_t, mc_s = torch.tensor([0.61, 0.37, 0.9, 0.2]), torch.tensor([0.59, 0.33, 0.8, 0.1])
+  common = dict(logits_a=la, logits_b=lb if guidance == 'cfg' else None, noise=U,
+                xt=xt, mc_t=mc_t, mc_s=mc_s, vocab=V, seq_len=L, diffusion=diffusion,
+                guidance=guidance, gamma=2.0, subs=subs, mask_logit=subs,
+                mask_index=mask, round_bf16=round_bf16)
+  xs_ref, q_ref = helpers.sampler_kernel(fast_math=False, want_q=True, **common)
+  xs, _ = helpers.sampler_kernel(
+    fast_math=True, stats_a=st_a.data_ptr(),
+    stats_b=st_b.data_ptr() if guidance == 'cfg' else 0, stats_ld=rows,
+    stats_chunks=st_a.shape[0], **common)
+  # make sure the fused kernel (not the generic one) answered: it ignores q_out
+  helpers.assert_ids_match(xs.view(B, L), xs_ref.view(B, L).cpu(), q_ref.view(B, L, V).cpu(),
+                           U, f'fused {diffusion}/{guidance}',
+                           tol=2e-2 if round_bf16 else 1e-3)
+  if subs:
+    assert xs.view(B, L)[1, :3].tolist() == [5, 6, 7]
+
+
+@pytest.mark.parametrize('diffusion,guidance', FUSED_MODES)
+def test_fused_philox_matches_cpu_stream(diffusion, guidance):
+  B, L, V, ld = 2, 8, 30522, 30528
+  rows = B * L
+  dev = torch.device('cuda')
+  subs = diffusion == 'absorbing_state'
+  la = _rand_logits(rows, V, ld, torch.bfloat16, 31).to(dev)
+  lb = _rand_logits(rows, V, ld, torch.bfloat16, 32).to(dev)
+  xt = (torch.full((B, L), 103, dtype=torch.long) if subs
+        else torch.randint(0, V, (B, L), generator=torch.Generator().manual_seed(3)))
+  st_a = helpers.make_stats(la, V, 103 if subs else -1)
+  st_b = helpers.make_stats(lb, V, -1)
+  seed, step = 0xFEDCBA9876543210, 901
+  U = torch.from_numpy(helpers.philox_uniform(seed, step, rows, V))
+  common = dict(logits_a=la, logits_b=lb if guidance == 'cfg' else None, xt=xt,
+                mc_t=0.5, mc_s=0.05, vocab=V, seq_len=L, diffusion=diffusion,
+                guidance=guidance, gamma=2.0, subs=subs, mask_logit=subs,
+                mask_index=103, round_bf16=True, fast_math=True,
+                stats_a=st_a.data_ptr(), stats_b=st_b.data_ptr() if guidance == 'cfg' else 0,
+                stats_ld=rows, stats_chunks=st_a.shape[0])
+  xs_inj, _ = helpers.sampler_kernel(noise=U, **common)
+  xs_phx, _ = helpers.sampler_kernel(noise=None, seed=seed, step=step, **common)
+  assert torch.equal(xs_inj, xs_phx)
+
+
+def test_fused_sampler_statistics():
+  """Philox production path draws from the right distribution: empirical
+  token frequencies over many rows with identical logits match q_xs
+  (chi-square style bound on the 50 most likely tokens)."""
+  V, ld, n = 4096, 4096, 16384
+  dev = torch.device('cuda')
+  g = torch.Generator().manual_seed(5)
+  row = (torch.randn(V, generator=g) * 2.5).to(torch.bfloat16)
+  la = row[None].repeat(n, 1).contiguous().to(dev)
+  xt = torch.full((n,), 17, dtype=torch.long)
+  st = helpers.make_stats(la, V)
+  xs, _ = helpers.sampler_kernel(
+    logits_a=la, xt=xt, mc_t=0.8, mc_s=0.3, vocab=V, seq_len=1, diffusion='uniform',
+    round_bf16=False, fast_math=True, seed=77, step=0, stats_a=st.data_ptr(),
+    stats_ld=n, stats_chunks=st.shape[0])
+  x = torch.softmax(row.float(), -1)
+  from oracle import ref_sampler
+  q = ref_sampler.posterior_uniform(x[None, None], torch.tensor([[17]]),
+                                    torch.tensor(0.7), torch.tensor(0.2))[0, 0]
+  counts = torch.bincount(xs.cpu(), minlength=V).float()
+  top = q.topk(50).indices
+  exp = q[top] * n
+  zscore = (counts[top] - exp) / exp.clamp_min(1).sqrt()
+  assert zscore.abs().max().item() < 5.0, zscore
+  assert abs(counts[top].sum().item() - exp.sum().item()) < 5 * exp.sum().sqrt().item()
