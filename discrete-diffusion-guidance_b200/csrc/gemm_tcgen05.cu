@@ -3,10 +3,16 @@
 // autocast).  out = epilogue(A[M,K] @ W[N,K]^T), 16-bit operands, fp32
 // accumulation in tensor memory.
 //
-// Structure (one persistent CTA per SM, 384 threads):
-//   warp 0     TMA producer: A/W k-blocks -> 128B-swizzled smem ring (4 stages)
-//   warp 1     MMA issuer:   one thread issues tcgen05.mma 128x256x16, commits
-//                            stage-release and accumulator-ready mbarriers
+// Structure: persistent CTA pairs (cluster of 2 = the two SMs of a TPC), one
+// CTA per SM, 384 threads each.  A pair owns a 256 x 256 output tile: each CTA
+// stages 128 rows of A and 128 rows (half of N) of W per k-block, and the
+// leader CTA issues tcgen05.mma.cta_group::2 (M=256, N=256, K=16) over both
+// CTAs' shared memory, so every byte of W is fetched once per pair instead of
+// once per SM (L2 -> SM traffic per FLOP drops 1.5x, and 6 pipeline stages fit).
+//   warp 0     TMA producer: A/W k-blocks -> 128B-swizzled smem ring (6 stages);
+//              both CTAs signal the leader's "full" mbarrier
+//   warp 1     MMA issuer (leader CTA only): one thread issues the UMMAs and
+//              multicast-commits stage-release / accumulator-ready mbarriers
 //   warp 2     TMEM allocator (512 columns = 2 accumulators of 128x256 fp32)
 //   warps 4-11 epilogue: tcgen05.ld accumulator -> registers -> fused epilogue
 //              (bias / GELU-tanh / rotary / gate+residual) -> padded smem slab
@@ -24,13 +30,14 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;           // 64 x 16-bit = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int B_STAGE_BYTES = BN * BK * 2;
+constexpr int BNH = BN / 2;          // W rows staged by each CTA of the pair
+constexpr int B_STAGE_BYTES = BNH * BK * 2;
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_THREADS = 256;
+constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_ROW_BYTES = 80;                  // 64 B payload + 16 B pad: conflict-free 128-bit stores
 constexpr int EPI_SLAB_BYTES = 32 * EPI_ROW_BYTES;  // one warp's 32 accumulator rows
@@ -101,28 +108,60 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
                : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-CTA TMA load: data lands in this CTA's smem, bytes are credited to the
+// mbarrier at `bar_cluster_addr` (the leader's)
+__device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0,
+                                                 int c1) {
+  asm volatile(
+    "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+    ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+    : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
                : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
+// arrives (once all previously issued UMMAs retire) on the mbarrier at this
+// smem offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  asm volatile(
+    "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+      smem_u32(bar)), "h"((uint16_t)3)
+    : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, 128 x 256 x 16, 16-bit inputs, fp32 accumulate
+// D[tmem] (+)= A[smem] * B[smem]^T, 256 x 256 x 16 over the CTA pair (each CTA:
+// 128 rows of A, 128 rows of B, 128 x 256 fp32 of D), 16-bit inputs
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
     "{\n\t"
     ".reg .pred p;\n\t"
     "setp.ne.b32 p, %4, 0;\n\t"
-    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+    "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
     "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
     : "memory");
 }
@@ -166,10 +205,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(const void* p) {
 // 1 bf16) at bits 7-9 / 10-12, both K-major, N>>3 at 17-22, M>>4 at 24-28.
 template <typename T> __host__ __device__ constexpr uint32_t make_idesc();
 template <> __host__ __device__ constexpr uint32_t make_idesc<__half>() {
-  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 }
 template <> __host__ __device__ constexpr uint32_t make_idesc<__nv_bfloat16>() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 }
 
 // ------------------------------------------------------------------ 16-bit helpers
@@ -259,7 +298,7 @@ __device__ __forceinline__ float gelu_tanh(float v) {
 
 // ------------------------------------------------------------------ kernel
 template <typename T, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -276,7 +315,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (p.M + BM - 1) / BM;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -286,13 +329,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tma_prefetch_desc(&tma_b);
   }
   if (warp == 1 && lane == 0) {
+    // full: the leader producer's arrival + both CTAs' TMA bytes, leader's copy is the live one;
+    // empty / tmem_full: one multicast commit from the leader's MMA thread;
+    // tmem_empty (leader's copy): one arrival per epilogue warp of both CTAs
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_THREADS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * NUM_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -301,28 +347,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * BM;
-        const int n0 = (tile % num_n) * BN;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / num_n) * (2 * BM) + (int)cta_rank * BM;     // this CTA's A rows
+        const int nb0 = (tile % num_n) * BN + (int)cta_rank * BNH;         // this CTA's half of W
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(&tma_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BK, m0);
-          tma_load_2d(&tma_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BK, n0);
+          const uint32_t full_leader = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          // only the leader arrives; its expect-tx covers both CTAs' bytes
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+          tma_load_2d_2cta(&tma_a, full_leader, smem_a + stage * A_STAGE_BYTES, kb * BK, m0);
+          tma_load_2d_2cta(&tma_b, full_leader, smem_b + stage * B_STAGE_BYTES, kb * BK, nb0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && leader) {
       constexpr uint32_t idesc = make_idesc<T>();
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -366,8 +414,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const uint32_t stg_rd = stg + (uint32_t)crow * EPI_ROW_BYTES + (uint32_t)cchunk * 16;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * BM;
+    const uint32_t tmem_empty_leader0 = map_to_cta(smem_u32(&tmem_empty[0]), 0);
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / num_n) * (2 * BM) + (int)cta_rank * BM;
       const int n0 = (tile % num_n) * BN + chalf * (BN / 2);
       const int m = m0 + row_in_tile;
       const bool row_ok = m < p.M;
@@ -566,15 +615,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (EPI == DDG_EPI_STORE && p.stats != nullptr && row_ok && n0 < p.N)
           p.stats[(int64_t)(n0 / (BN / 2)) * p.stats_ld + m] = make_float2(st_m, st_s);
       }
+      // this warp has drained its part of the accumulator: one arrival per warp
+      // on the leader's barrier (the leader's MMA thread reuses both CTAs' TMEM)
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tmem_empty_leader0 + (uint32_t)acc * 8);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();     // neither CTA may exit while its pair can still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -624,9 +676,9 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
     DDG_CUDA(cudaFuncSetAttribute(gemm_kernel<T, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done[dev] = true;
   }
-  const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-  int grid = sm_count();
-  if (grid > num_tiles) grid = num_tiles;
+  const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
+  int grid = sm_count() & ~1;           // CTA pairs
+  if (grid > 2 * num_tiles) grid = 2 * num_tiles;
   gemm_kernel<T, EPI><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, p);
   return check_cuda(cudaGetLastError(), "gemm launch");
 }
@@ -678,7 +730,7 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
   CUtensorMap ta, tb;
   rc = make_tma_2d(&ta, a.a, a.M, a.K, a.lda, BM, a.dtype);
   if (rc) return rc;
-  rc = make_tma_2d(&tb, a.w, a.N, a.K, a.ldw, BN, a.dtype);
+  rc = make_tma_2d(&tb, a.w, a.N, a.K, a.ldw, BNH, a.dtype);
   if (rc) return rc;
   GemmParams p;
   p.out = a.out; p.bias = a.bias; p.gate = a.gate; p.rope_cos = a.rope_cos; p.rope_sin = a.rope_sin;
