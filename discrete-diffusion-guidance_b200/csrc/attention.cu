@@ -56,7 +56,14 @@ __device__ __forceinline__ uint32_t sw_off(int r, int ch) { return (uint32_t)(r 
 
 constexpr float kLog2e = 1.4426950408889634f;
 
-template <typename T, bool CAUSAL>
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// FULL: non-causal and L a multiple of 64 -> no masking code at all.
+template <typename T, bool CAUSAL, bool FULL>
 __global__ void __launch_bounds__(512)
 attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int L, int H) {
   extern __shared__ __align__(128) uint8_t sm[];
@@ -68,14 +75,16 @@ attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int L, int H) {
   const int64_t row_stride = (int64_t)3 * H * 64;
   const T* base = qkv + (int64_t)b * L * row_stride + (int64_t)h * 64;
 
-  // ---- q, k, v of this (batch, head) -> shared memory
-  const int chunks = 3 * L * 8;
-  for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
-    const int which = c / (L * 8);
-    const int r = (c / 8) % L;
-    const int ch = c & 7;
-    const T* src = base + (int64_t)r * row_stride + (int64_t)which * H * 64 + ch * 8;
-    cp_async16(sm_base + which * tile_bytes + sw_off(r, ch), src);
+  // ---- q, k, v of this (batch, head) -> shared memory (thread -> fixed 16 B chunk column)
+  {
+    const int ch = threadIdx.x & 7;
+    const int rstep = blockDim.x >> 3;
+    for (int which = 0; which < 3; ++which) {
+      const T* src = base + (int64_t)which * H * 64 + ch * 8;
+      const uint32_t dst = sm_base + which * tile_bytes;
+      for (int r = threadIdx.x >> 3; r < L; r += rstep)
+        cp_async16(dst + sw_off(r, ch), src + (int64_t)r * row_stride);
+    }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -84,96 +93,102 @@ attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int L, int H) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int q0 = warp * 16;
+  const int l7 = lane & 7;
 
-  // ---- Q fragments (A operand), 4 k-steps over d
+  // per-lane ldmatrix offsets: row & 7 == lane & 7 for every tile we address
+  // Q: rows q0 + l7 + 8*((lane>>3)&1), chunk 2ks + (lane>>4)
+  // K: rows kb + l7,                    chunk 4kp + (lane>>3)
+  // V: rows kb + l7 + 8*((lane>>3)&1), chunk 2dp + (lane>>4)
+  const uint32_t row_qv = (uint32_t)(l7 + ((lane >> 3) & 1) * 8) * 128u;
+  uint32_t off_q[4], off_k[2], off_v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    off_q[i] = row_qv + (uint32_t)(((2 * i + (lane >> 4)) ^ l7) << 4);
+    off_v[i] = off_q[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) off_k[i] = (uint32_t)l7 * 128u + (uint32_t)(((4 * i + (lane >> 3)) ^ l7) << 4);
+
   uint32_t qf[4][4];
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    const int r = q0 + (lane & 7) + ((lane >> 3) & 1) * 8;
-    const int ch = 2 * ks + (lane >> 4);
-    ldsm_x4(qf[ks], sq + sw_off(r, ch));
-  }
+  for (int ks = 0; ks < 4; ++ks) ldsm_x4(qf[ks], sq + (uint32_t)q0 * 128u + off_q[ks]);
 
   float o[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m_run[2] = {-INFINITY, -INFINITY};
   float l_run[2] = {0.f, 0.f};
+  constexpr float kScale2 = 0.125f * kLog2e;       // softmax scale 1/sqrt(64), in log2 units
 
   const int kv_end = CAUSAL ? (q0 + 16) : L;
   for (int kb0 = 0; kb0 < kv_end; kb0 += 64) {
-    const int nvalid = min(64, kv_end - kb0);       // keys in this block (multiple of 16)
+    const int nvalid = FULL ? 64 : min(64, kv_end - kb0);   // keys in this block (multiple of 16)
     float s[8][4];
+    const uint32_t kbase = sk + (uint32_t)kb0 * 128u;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      if (nt * 8 < nvalid) {
+      if (FULL || nt * 8 < nvalid) {
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {
           uint32_t kf[4];
-          const int r = kb0 + nt * 8 + (lane & 7);
-          const int ch = 4 * kp + (lane >> 3);
-          ldsm_x4(kf, sk + sw_off(r, ch));
+          ldsm_x4(kf, kbase + (uint32_t)(nt * 8) * 128u + off_k[kp]);
           Mma<T>::run(s[nt], qf[2 * kp], kf[0], kf[1]);
           Mma<T>::run(s[nt], qf[2 * kp + 1], kf[2], kf[3]);
         }
       }
     }
-    // ---- scale, mask, block row-max
+    // ---- mask (ragged / causal only) and block row-max of the raw scores
     float bm[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int key = kb0 + nt * 8 + 2 * t + (e & 1);
-        const int qrow = q0 + g + (e >> 1) * 8;
-        float v = s[nt][e] * 0.125f;
-        const bool dead = (nt * 8 >= nvalid) || (CAUSAL && key > qrow);
-        v = dead ? -INFINITY : v;
-        s[nt][e] = v;
-        bm[e >> 1] = fmaxf(bm[e >> 1], v);
+        if (!FULL) {
+          const int key = kb0 + nt * 8 + 2 * t + (e & 1);
+          const int qrow = q0 + g + (e >> 1) * 8;
+          const bool dead = (nt * 8 >= nvalid) || (CAUSAL && key > qrow);
+          if (dead) s[nt][e] = -INFINITY;
+        }
+        bm[e >> 1] = fmaxf(bm[e >> 1], s[nt][e]);
       }
     }
-    float alpha[2], mnew[2];
+    float msc[2];
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
       float v = bm[hrow];
       v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
       v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-      mnew[hrow] = fmaxf(m_run[hrow], v);
-      alpha[hrow] = exp2f((m_run[hrow] - mnew[hrow]) * kLog2e);   // m_run = -inf -> 0
-      m_run[hrow] = mnew[hrow];
-      l_run[hrow] *= alpha[hrow];
-    }
+      const float mnew = fmaxf(m_run[hrow], v);
+      const float alpha = ex2_approx((m_run[hrow] - mnew) * kScale2);   // m_run = -inf -> 0
+      m_run[hrow] = mnew;
+      msc[hrow] = mnew * kScale2;
+      l_run[hrow] *= alpha;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
-      o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
+      for (int i = 0; i < 8; ++i) { o[i][2 * hrow] *= alpha; o[i][2 * hrow + 1] *= alpha; }
     }
-    // ---- p = exp(s - m), O += P V
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float p = exp2f((s[nt][e] - mnew[e >> 1]) * kLog2e);
-        s[nt][e] = p;
-        l_run[e >> 1] += p;
-      }
-    }
+    // ---- p = exp(scale (s - m)), O += P V
+    const uint32_t vbase = sv + (uint32_t)kb0 * 128u;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      if (kk * 16 < nvalid) {
+      if (FULL || kk * 16 < nvalid) {
         uint32_t pf[4];
-        pf[0] = Mma<T>::pack(s[2 * kk][0], s[2 * kk][1]);
-        pf[1] = Mma<T>::pack(s[2 * kk][2], s[2 * kk][3]);
-        pf[2] = Mma<T>::pack(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        pf[3] = Mma<T>::pack(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int nt = 2 * kk + half;
+          const float p0 = ex2_approx(fmaf(s[nt][0], kScale2, -msc[0]));
+          const float p1 = ex2_approx(fmaf(s[nt][1], kScale2, -msc[0]));
+          const float p2 = ex2_approx(fmaf(s[nt][2], kScale2, -msc[1]));
+          const float p3 = ex2_approx(fmaf(s[nt][3], kScale2, -msc[1]));
+          l_run[0] += p0 + p1;
+          l_run[1] += p2 + p3;
+          pf[2 * half] = Mma<T>::pack(p0, p1);
+          pf[2 * half + 1] = Mma<T>::pack(p2, p3);
+        }
 #pragma unroll
         for (int dp = 0; dp < 4; ++dp) {
           uint32_t vf[4];
-          const int r = kb0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-          const int ch = 2 * dp + (lane >> 4);
-          ldsm_x4_trans(vf, sv + sw_off(r, ch));
+          ldsm_x4_trans(vf, vbase + (uint32_t)(kk * 16) * 128u + off_v[dp]);
           Mma<T>::run(o[2 * dp], pf, vf[0], vf[1]);
           Mma<T>::run(o[2 * dp + 1], pf, vf[2], vf[3]);
         }
@@ -208,20 +223,26 @@ attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int L, int H) {
   }
 }
 
-template <typename T, bool CAUSAL>
-int launch_attention(const void* qkv, void* out, int batch, int L, int H, cudaStream_t s) {
+template <typename T, bool CAUSAL, bool FULL>
+int launch_attention_k(const void* qkv, void* out, int batch, int L, int H, cudaStream_t s) {
   const int smem = 3 * L * 128;
   static bool attr_done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (smem > 48 * 1024 && dev >= 0 && dev < 64 && !attr_done[dev]) {
-    DDG_CUDA(cudaFuncSetAttribute(attention_kernel<T, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DDG_CUDA(cudaFuncSetAttribute(attention_kernel<T, CAUSAL, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   3 * 256 * 128));
     attr_done[dev] = true;
   }
-  attention_kernel<T, CAUSAL><<<batch * H, (L / 16) * 32, smem, s>>>(
+  attention_kernel<T, CAUSAL, FULL><<<batch * H, (L / 16) * 32, smem, s>>>(
     reinterpret_cast<const T*>(qkv), reinterpret_cast<T*>(out), L, H);
   return check_cuda(cudaGetLastError(), "attention launch");
+}
+
+template <typename T, bool CAUSAL>
+int launch_attention(const void* qkv, void* out, int batch, int L, int H, cudaStream_t s) {
+  if (!CAUSAL && L % 64 == 0) return launch_attention_k<T, false, true>(qkv, out, batch, L, H, s);
+  return launch_attention_k<T, CAUSAL, false>(qkv, out, batch, L, H, s);
 }
 
 }  // namespace
