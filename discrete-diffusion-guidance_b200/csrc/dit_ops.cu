@@ -60,26 +60,56 @@ __global__ void cond_embed_kernel(const float* __restrict__ sigma, int sigma_row
 // out[r, o] = round_T( sum_k round_T(c[r,k]) * round_T(W[o,k]) + round_T(b[o]) )
 // and round_T(1 + that) for the `scale` chunks.  One warp per output column,
 // looping over the (few) conditioning rows.
+// Thread = output column, loop over conditioning rows.  The per-step API
+// conditions every sequence separately, but callers almost always pass the same
+// (sigma, label) for long runs of rows: a row whose conditioning vector is
+// bit-identical to the previous row's reuses its result (flags computed per
+// CTA in shared memory), so the usual cost is one coalesced store per row.
+constexpr int kAdaRowsPerPass = 2048;
 template <typename T>
-__global__ void adaln_kernel(const float* __restrict__ c, int n_rows, int cond_dim,
-                             const float* __restrict__ w, const float* __restrict__ b, int n_out,
-                             int chunk, uint32_t one_plus_mask, int n_chunks,
-                             T* __restrict__ out, int64_t ld_out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= n_out) return;
-  const int o = warp;
-  const bool plus1 = (one_plus_mask >> ((o / chunk) % n_chunks)) & 1u;
-  const float bias = Cvt<T>::round(b[o]);
-  for (int r = 0; r < n_rows; ++r) {
-    float acc = 0.f;
-    for (int k = lane; k < cond_dim; k += 32)
-      acc += Cvt<T>::round(c[(int64_t)r * cond_dim + k]) * Cvt<T>::round(w[(int64_t)o * cond_dim + k]);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      float v = Cvt<T>::round(acc + bias);
-      if (plus1) v = Cvt<T>::round(1.f + v);
-      out[(int64_t)r * ld_out + o] = Cvt<T>::from_f32(v);
+__global__ void __launch_bounds__(256)
+adaln_kernel(const float* __restrict__ c, int n_rows, int cond_dim,
+             const float* __restrict__ w, const float* __restrict__ b, int n_out,
+             int chunk, uint32_t one_plus_mask, int n_chunks,
+             T* __restrict__ out, int64_t ld_out) {
+  __shared__ uint8_t same[kAdaRowsPerPass];
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = o < n_out;
+  const bool plus1 = live && ((one_plus_mask >> ((o / chunk) % n_chunks)) & 1u);
+  const float bias = live ? Cvt<T>::round(b[o]) : 0.f;
+  const float* wo = w + (int64_t)(live ? o : 0) * cond_dim;
+  float v = 0.f;
+  for (int r0 = 0; r0 < n_rows; r0 += kAdaRowsPerPass) {
+    const int nr = min(kAdaRowsPerPass, n_rows - r0);
+    __syncthreads();
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+      bool eq = (r0 + r) > 0;
+      if (eq) {
+        const float* cr = c + (int64_t)(r0 + r) * cond_dim;
+        for (int k = 0; k < cond_dim && eq; ++k) eq = cr[k] == cr[k - cond_dim];
+      }
+      same[r] = eq ? 1 : 0;
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int r = 0; r < nr; ++r) {
+      if (!same[r]) {
+        const float* cr = c + (int64_t)(r0 + r) * cond_dim;
+        float acc = 0.f;
+        if ((cond_dim & 3) == 0) {
+          for (int k = 0; k < cond_dim; k += 4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(cr + k);
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wo + k));
+            acc += Cvt<T>::round(c4.x) * Cvt<T>::round(w4.x) + Cvt<T>::round(c4.y) * Cvt<T>::round(w4.y) +
+                   Cvt<T>::round(c4.z) * Cvt<T>::round(w4.z) + Cvt<T>::round(c4.w) * Cvt<T>::round(w4.w);
+          }
+        } else {
+          for (int k = 0; k < cond_dim; ++k) acc += Cvt<T>::round(cr[k]) * Cvt<T>::round(wo[k]);
+        }
+        v = Cvt<T>::round(acc + bias);
+        if (plus1) v = Cvt<T>::round(1.f + v);
+      }
+      out[(int64_t)(r0 + r) * ld_out + o] = Cvt<T>::from_f32(v);
     }
   }
 }
@@ -250,8 +280,7 @@ extern "C" int ddg_adaln(const float* c, int32_t n_rows, int32_t cond_dim, const
   DDG_REQUIRE(chunk > 0 && n_chunks > 0 && n_chunks <= 32, DDG_ERR_INVALID, "adaln: bad chunking");
   DDG_REQUIRE(ld_out >= n_out, DDG_ERR_INVALID, "adaln: ld_out < n_out");
   if (n_rows == 0) return DDG_OK;
-  const int warps_per_cta = 8;
-  const unsigned grid = (unsigned)((n_out + warps_per_cta - 1) / warps_per_cta);
+  const unsigned grid = (unsigned)((n_out + 255) / 256);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == DDG_F16)
     adaln_kernel<__half><<<grid, 256, 0, s>>>(c, n_rows, cond_dim, w, b, n_out, chunk, one_plus_mask, n_chunks,

@@ -66,6 +66,7 @@ class Diffusion:
     self._call_count = 0
     self._loop = None
     self._stats = {}            # logits data_ptr -> (stats tensor, row offset)
+    self._step_graphs = {}
 
   # ---------------------------------------------------------------- weights
   def load_state_dict(self, state_dict, strict=True):
@@ -223,6 +224,20 @@ class Diffusion:
   def _mc(self, mc):
     return mc.to(self.device, torch.float32).reshape(-1).contiguous()
 
+  def _step_graph_ok(self, cache):
+    """Per-step API fast path: the whole step (forward + fused sampler) is one
+    captured CUDA graph fed through static input buffers."""
+    return (self.use_cuda_graph and cache is None and self.noise_fn is None
+            and not self.return_q_xs
+            and not self.config.sampling.get('use_float64', False))
+
+  def _get_step_graph(self, kind, B, L, gamma):
+    key = (kind, B, L, float(gamma), self.round_bf16, self.fast_math)
+    sg = self._step_graphs.get(key)
+    if sg is None:
+      sg = self._step_graphs[key] = _StepGraph(self, kind, B, L, float(gamma))
+    return sg
+
   def _step_noise(self, B, L):
     if self.noise_fn is None:
       return None
@@ -239,6 +254,11 @@ class Diffusion:
       raise NotImplementedError('sampling.use_float64 is not implemented')
     B, L = xt.shape
     xt = xt.to(self.device, torch.int64).contiguous()
+    if self._step_graph_ok(cache):
+      sg = self._get_step_graph('ddpm', B, L, 1.0)
+      xs = sg.run(xt, self._process_sigma(time_conditioning), None,
+                  move_chance_t, move_chance_s)
+      return xs, None, {'log_x_theta': sg.logits_view(0)}
     logits = (cache['log_x_theta'] if cache is not None
               else self._logits(xt, time_conditioning, None))
     xs = torch.empty_like(xt)
@@ -260,6 +280,20 @@ class Diffusion:
     cond = cond.to(self.device, torch.int64)
     mask_cond = torch.ones_like(cond) * self.config.data.num_classes
     lc = lu = None
+    if self._step_graph_ok(cache):
+      sigma = self._process_sigma(time_conditioning)
+      if gamma == 0.0 or gamma == 1.0:
+        sg = self._get_step_graph('cfg1', B, L, gamma)
+        xs = sg.run(xt, sigma, mask_cond if gamma == 0.0 else cond,
+                    move_chance_t, move_chance_s)
+        one = sg.logits_view(0)
+        return xs, None, {'log_x_theta_uncond': one if gamma == 0.0 else None,
+                          'log_x_theta_cond': one if gamma == 1.0 else None}
+      sg = self._get_step_graph('cfg2', B, L, gamma)
+      xs = sg.run(xt, sigma, torch.cat([cond, mask_cond]), move_chance_t,
+                  move_chance_s)
+      return xs, None, {'log_x_theta_uncond': sg.logits_view(1),
+                        'log_x_theta_cond': sg.logits_view(0)}
     if cache is not None:
       lu, lc = cache['log_x_theta_uncond'], cache['log_x_theta_cond']
     elif gamma == 0.0:
@@ -453,6 +487,83 @@ class Diffusion:
         select=_lib.SELECT_GUMBEL, step=i)
       x[:, i + 1] = y
     return x
+
+
+class _StepGraph:
+  """One reverse step of the per-step API (`_ddpm_denoise` / `_cfg_denoise`)
+  as a captured CUDA graph.  Inputs are copied into static buffers, the Philox
+  key / step index are read from device memory, so one graph serves every call
+  with the same shapes."""
+
+  def __init__(self, model, kind, B, L, gamma):
+    self.m, self.kind, self.B, self.L, self.gamma = model, kind, B, L, gamma
+    self.two = kind == 'cfg2'
+    self.n_fwd = 2 if self.two else 1
+    dev, n = model.device, self.n_fwd * B
+    self.xt = torch.empty(B, L, dtype=torch.int64, device=dev)
+    self.xs = torch.empty(B, L, dtype=torch.int64, device=dev)
+    self.sigma = torch.zeros(n, dtype=torch.float32, device=dev)
+    self.labels = (torch.zeros(n, dtype=torch.int64, device=dev)
+                   if kind != 'ddpm' else None)
+    self.mct = torch.empty(B, dtype=torch.float32, device=dev)
+    self.mcs = torch.empty(B, dtype=torch.float32, device=dev)
+    self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+    self.seed = torch.zeros(1, dtype=torch.int64, device=dev)
+    self.logits = model.backbone.alloc_logits(n * L)
+    self.stats = model.backbone.alloc_stats(n * L)
+    self.graph = None
+    self.ws_generation = -1
+
+  def logits_view(self, i):
+    bb = self.m.backbone
+    return self.logits.view(self.n_fwd, self.B, self.L, bb.vocab_ld)[
+      i, :, :, :self.m.vocab_size]
+
+  def _body(self):
+    m, B, L = self.m, self.B, self.L
+    mod = ModSpec(n_mod=self.n_fwd * B, seqs_per_mod=1, sigma=self.sigma,
+                  sigma_row_stride=1, labels=self.labels)
+    m.backbone.run(self.xt, self.n_fwd * B, L, mod, self.logits,
+                   ids_period=B * L, stats_out=self.stats,
+                   stats_mask_col=m._stats_mask_col)
+    ld = m.backbone.vocab_ld
+    m._launch_sampler(
+      logits_a=self.logits.data_ptr(), ld_a=ld,
+      logits_b=(self.logits.data_ptr() + B * L * ld * 2) if self.two else None,
+      ld_b=ld if self.two else 0, xt=self.xt, xs=self.xs, mc_t=self.mct,
+      mc_s=self.mcs, rows=B * L, seq_len=L, mc_seq_stride=1,
+      step_ptr=self.step, seed_ptr=self.seed,
+      stats=(self.stats, 0, B * L if self.two else 0),
+      guidance=_lib.GUIDE_CFG if self.two else _lib.GUIDE_NONE,
+      gamma=self.gamma if self.two else 1.0)
+
+  def run(self, xt, sigma, labels, mc_t, mc_s):
+    m, B = self.m, self.B
+    self.xt.copy_(xt, non_blocking=True)
+    sigma = sigma.to(m.device, torch.float32).reshape(-1)
+    self.sigma.copy_(sigma.repeat(self.n_fwd) if sigma.numel() == B
+                     else sigma.expand(self.n_fwd * B))
+    if self.labels is not None:
+      self.labels.copy_(labels.to(m.device, torch.int64).reshape(-1))
+    self.mct.copy_(m._mc(mc_t).expand(B))
+    self.mcs.copy_(m._mc(mc_s).expand(B))
+    self.step.fill_(int(m._step_index))
+    self.seed.fill_(m.seed + 7919 * m._call_count)
+    m._step_index += 1          # successive API calls draw fresh noise
+    if self.graph is not None and self.ws_generation != m.backbone.ws_generation:
+      self.graph = None
+    if self.graph is None:
+      self._body()              # eager (also warms lazy attributes), then capture
+      torch.cuda.current_stream().synchronize()
+      out = self.xs.clone()
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):
+        self._body()
+      self.graph = g
+      self.ws_generation = m.backbone.ws_generation
+      return out
+    self.graph.replay()
+    return self.xs.clone()
 
 
 class _GraphLoop:

@@ -156,3 +156,33 @@ def test_error_semantics_match_reference():
   cfg3.diffusion = 'uniform_data_marginals'
   with pytest.raises(NotImplementedError):
     ddg_b200.Diffusion(cfg3, tok, device=DEV)
+
+
+@pytest.mark.parametrize('name', ['udlm_null', 'mdlm_null', 'udlm_cfg_g2',
+                                  'udlm_cfg_g0', 'udlm_cfg_g1', 'bert_udlm_cfg_g2',
+                                  'bert_mdlm_null'])
+def test_step_api_graph_path_equals_eager_path(name):
+  """The per-step API's captured-graph fast path gives the ids of the eager
+  launches (same Philox key and step), also on replay with new inputs."""
+  case = cases.CASE_BY_NAME[name]
+  model, cfg, tok = _diffusion(case)
+  B, L = case.batch, case.length
+  sig, mct, mcs = model._step_scalars(8, 1e-5)
+  cond = torch.full((B,), case.condition, dtype=torch.long, device=DEV)
+
+  def call(xt, i, graph):
+    model.use_cuda_graph = graph
+    model._step_index = i
+    s = sig[i].expand(B).to(DEV)
+    a, b = mct[i].expand(B)[:, None, None].to(DEV), mcs[i].expand(B)[:, None, None].to(DEV)
+    if case.guidance == 'cfg':
+      return model._cfg_denoise(cond, case.gamma, xt, s, a, b)[0]
+    return model._ddpm_denoise(xt, s, a, b)[0]
+
+  xt = cases.prior_ids(case).to(DEV)
+  for i in range(3):          # call 0 captures, calls 1-2 replay
+    xe = call(xt, i, False)
+    xg = call(xt, i, True)
+    torch.cuda.synchronize()
+    assert torch.equal(xe, xg), f'step {i}'
+    xt = xe
