@@ -58,6 +58,9 @@ class Diffusion:
     # knobs that are not reference config keys
     self.round_bf16 = True      # reproduce the reference's bf16 log-softmax/exp
     self.fast_math = True       # ex2/lg2 intrinsics in the fused sampler
+    self.race_group = 8         # Philox path: hierarchical race over 8-column
+                                # groups (same distribution, 8x less noise
+                                # work); 0 = one exponential per vocab entry
     self.return_q_xs = False    # materialise q_xs (B, L, V) fp32 per step
     self.use_cuda_graph = True
     self.noise_fn = None        # i -> injected U (B, L, V); None -> Philox
@@ -218,7 +221,8 @@ class Diffusion:
       fast_math=1 if (self.fast_math and noise is None) else 0,
       gamma=float(gamma), seed=self.seed + 7919 * self._call_count,
       step=int(step), stats_chunks=st_chunks, stats_a=st_a,
-      stats_b=st_b if logits_b else 0, stats_ld=st_ld)
+      stats_b=st_b if logits_b else 0, stats_ld=st_ld,
+      race_group=int(self.race_group))
     check(lib.ddg_sample_step(a, stream_ptr()))
 
   def _mc(self, mc):
@@ -232,7 +236,8 @@ class Diffusion:
             and not self.config.sampling.get('use_float64', False))
 
   def _get_step_graph(self, kind, B, L, gamma):
-    key = (kind, B, L, float(gamma), self.round_bf16, self.fast_math)
+    key = (kind, B, L, float(gamma), self.round_bf16, self.fast_math,
+           self.race_group)
     sg = self._step_graphs.get(key)
     if sg is None:
       sg = self._step_graphs[key] = _StepGraph(self, kind, B, L, float(gamma))
@@ -418,7 +423,8 @@ class Diffusion:
 
   def _get_loop(self, B, L, method, guidance):
     gamma = None if guidance is None else float(guidance.gamma)
-    key = (B, L, method, gamma, self.round_bf16, self.fast_math)
+    key = (B, L, method, gamma, self.round_bf16, self.fast_math,
+           self.race_group)
     if self._loop is None or self._loop.key != key:
       self._loop = _GraphLoop(self, B, L, method, gamma, key)
     return self._loop

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DDG_ABI_VERSION 1
+#define DDG_ABI_VERSION 2
 #define DDG_API __attribute__((visibility("default")))
 
 typedef void* ddg_stream_t; /* cudaStream_t */
@@ -121,6 +121,16 @@ typedef struct ddg_sample_step_args {
   const void* stats_a;
   const void* stats_b;
   int64_t stats_ld;
+  /* Philox noise only (noise == NULL), select == DDG_SELECT_RACE:
+   *   0  one exponential per vocabulary entry, argmax_j q_j / E_j -- the
+   *      reference's race as written (diffusion.py:1752-1755);
+   *   8  hierarchical race: one exponential per group of 8 consecutive
+   *      columns, argmax over groups of (sum_G q) / E_G, then an inverse-CDF
+   *      pick inside the winning group.  Identical distribution (min of
+   *      independent exponentials), 8x less noise work; needs the stats_*
+   *      partials, bf16 logits and fast_math.  Other values: DDG_ERR_INVALID. */
+  int32_t race_group;
+  int32_t reserved;
 } ddg_sample_step_args;
 
 DDG_API int ddg_sample_step(const ddg_sample_step_args* args, ddg_stream_t stream);

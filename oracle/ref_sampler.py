@@ -357,3 +357,71 @@ class OracleSampler:
         trace.append({'xt': xt, 'xs': xs, 'q_xs': q, **lps})
       xt = xs
     return xt
+
+
+# --------------------------------------------------------------------------
+# hierarchical exponential race (CPU restatement of csrc/sample_group.cu)
+# --------------------------------------------------------------------------
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+  """Philox4x32-10 (Salmon et al., SC'11) on numpy uint32 arrays (broadcast);
+  returns the four output words."""
+  import numpy as np
+  M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+  W0, W1 = 0x9E3779B9, 0xBB67AE85
+  c0, c1, c2, c3 = np.broadcast_arrays(*(np.asarray(c, dtype=np.uint32) for c in (c0, c1, c2, c3)))
+  k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+  for _ in range(10):
+    p0 = M0 * c0.astype(np.uint64)
+    p1 = M1 * c2.astype(np.uint64)
+    hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), p0.astype(np.uint32)
+    hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), p1.astype(np.uint32)
+    c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint32(k0), lo1, hi0 ^ c3 ^ np.uint32(k1), lo0
+    k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+  return c0, c1, c2, c3
+
+
+def group_race_select(probs, seed, step, group=8, threads=256):
+  """Categorical draw by the hierarchical exponential race of the production
+  sampler (csrc/sample_group.cu), restated on the CPU in float64 with the same
+  Philox stream.  Distributionally identical to `sample_categorical`
+  (diffusion.py:1748-1755): the minimum of independent exponentials with rates
+  q_j over a group is Exp(sum q_j), and the arg-min inside the group is
+  q_j / sum q_j independent of the minimum.
+
+  probs: (rows, V) non-negative, any common scale per row.  Returns a dict:
+  ids (rows,), group scores (rows, n_groups) in log2 units, and for the winning
+  group the in-group cumulative sums / target so that a test can tell a real
+  mismatch from a near-tie."""
+  import numpy as np
+  p = probs.detach().double().cpu().numpy()
+  rows, V = p.shape
+  nG = (V + group - 1) // group
+  pad = nG * group - V
+  if pad:
+    p = np.concatenate([p, np.zeros((rows, pad))], 1)
+  p = p.reshape(rows, nG, group)
+  S = p.sum(-1)
+  G = np.arange(nG, dtype=np.int64)[None, :]
+  r = np.arange(rows, dtype=np.uint64)[:, None]
+  row_lo = (r & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+  row_hi = (r >> np.uint64(32)).astype(np.uint32)
+  k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+  shift = int(np.log2(threads))
+  ctr0 = ((G & (threads - 1)) | ((G >> (shift + 2)) << shift)).astype(np.uint32)
+  words = np.stack(philox4x32_10(ctr0, row_lo, row_hi, np.uint32(step & 0xFFFFFFFF), k0, k1), -1)
+  sel = ((G >> shift) & 3).astype(np.int64)
+  w = np.take_along_axis(words, np.broadcast_to(sel[..., None], (rows, nG, 1)), -1)[..., 0]
+  U = (w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+  E = 1e-10 - np.log(U.astype(np.float64) + 1e-10)
+  with np.errstate(divide='ignore'):
+    score = np.log2(S) - np.log2(E)
+  win = score.argmax(-1)
+  pw = p[np.arange(rows), win]                               # (rows, group)
+  w2 = philox4x32_10(win.astype(np.uint32), row_lo[:, 0],
+                     row_hi[:, 0] | np.uint32(0x80000000), np.uint32(step & 0xFFFFFFFF), k0, k1)[0]
+  u2 = (w2 >> np.uint32(8)).astype(np.float32).astype(np.float64) * 2.0 ** -24
+  cum = np.cumsum(pw, -1)
+  target = u2 * cum[:, -1]
+  pick = (cum > target[:, None]).argmax(-1)
+  return dict(ids=torch.from_numpy(win * group + pick), score=score, win=win, cum=cum,
+              target=target, u2=u2)

@@ -374,3 +374,155 @@ def test_fused_sampler_statistics():
   zscore = (counts[top] - exp) / exp.clamp_min(1).sqrt()
   assert zscore.abs().max().item() < 5.0, zscore
   assert abs(counts[top].sum().item() - exp.sum().item()) < 5 * exp.sum().sqrt().item()
+
+
+# --------------------------------------------------------------------------
+# hierarchical race (production Philox path, csrc/sample_group.cu)
+# --------------------------------------------------------------------------
+def _group_inputs(diffusion, guidance, B, L, V, ld, seed0, scale=3.0):
+  rows = B * L
+  subs = diffusion == 'absorbing_state'
+  la = _rand_logits(rows, V, ld, torch.bfloat16, seed0, scale)
+  lb = _rand_logits(rows, V, ld, torch.bfloat16, seed0 + 1, scale)
+  g = torch.Generator().manual_seed(seed0 + 2)
+  if subs:
+    xt = torch.full((B, L), 103, dtype=torch.long)
+    xt[0, :2] = torch.tensor([7, 9])
+  else:
+    xt = torch.randint(0, V, (B, L), generator=g)
+    xt[0, 0], xt[0, 1] = V - 1, V - 3          # z inside the ragged tail group
+  return la, lb, xt, subs
+
+
+def _oracle_probs(la, lb, xt, mc_t, mc_s, V, diffusion, guidance, gamma, round_bf16):
+  B, L = xt.shape
+  subs = diffusion == 'absorbing_state'
+  lp_dtype = torch.bfloat16 if round_bf16 else None
+
+  def lps(l):
+    return ref_sampler.log_probs_from_logits(
+      l[:, :V].float().view(B, L, V), torch.full_like(xt, 103) if subs else xt,
+      parameterization='subs' if subs else 'd3pm', mask_index=103, lp_dtype=lp_dtype)
+  U = torch.full((B, L, V), 0.5)
+  kw = dict(diffusion=diffusion, mask_index=103, lp_dtype=lp_dtype)
+  mct3, mcs3 = mc_t.view(-1, 1, 1), mc_s.view(-1, 1, 1)
+  xt_all_mask = torch.full_like(xt, 103) if subs else xt   # posterior of the masked rows
+  if guidance == 'cfg':
+    _, q = ref_sampler.cfg_update(lps(la), lps(lb), gamma, xt_all_mask, mct3, mcs3, U, **kw)
+  else:
+    _, q = ref_sampler.ddpm_update(lps(la), xt_all_mask, mct3, mcs3, U, **kw)
+  return q
+
+
+@pytest.mark.parametrize('diffusion,guidance', FUSED_MODES)
+@pytest.mark.parametrize('round_bf16', [True, False])
+def test_group_race_matches_cpu_restatement(diffusion, guidance, round_bf16):
+  """Production kernel (hierarchical race, in-kernel Philox) against the CPU
+  restatement fed with the oracle's posterior and the regenerated Philox
+  stream: ids bit-equal except near-ties -- a different group only if the two
+  group scores agree to `tol` (log2 units), a different column of the same
+  group only if the inverse-CDF target sits within `tol` of the boundary."""
+  B, L, V, ld = 4, 16, 30522, 30528
+  rows = B * L
+  dev = torch.device('cuda')
+  la, lb, xt, subs = _group_inputs(diffusion, guidance, B, L, V, ld, 41)
+  mc_t = torch.tensor([0.61, 0.37, 0.9, 0.2])
+  mc_s = torch.tensor([0.59, 0.33, 0.8, 0.1])
+  st_a = helpers.make_stats(la.to(dev), V, 103 if subs else -1)
+  st_b = helpers.make_stats(lb.to(dev), V, -1)
+  seed, step = 0x1234567ABCDEF01, 77
+  xs, _ = helpers.sampler_kernel(
+    logits_a=la.to(dev), logits_b=lb.to(dev) if guidance == 'cfg' else None, xt=xt,
+    mc_t=mc_t, mc_s=mc_s, vocab=V, seq_len=L, diffusion=diffusion, guidance=guidance,
+    gamma=2.0, subs=subs, mask_logit=subs, mask_index=103, round_bf16=round_bf16,
+    fast_math=True, seed=seed, step=step, stats_a=st_a.data_ptr(),
+    stats_b=st_b.data_ptr() if guidance == 'cfg' else 0, stats_ld=rows,
+    stats_chunks=st_a.shape[0], race_group=8)
+  xs = xs.cpu()
+  q = _oracle_probs(la, lb, xt, mc_t, mc_s, V, diffusion, guidance, 2.0, round_bf16)
+  ref = ref_sampler.group_race_select(q.view(rows, V), seed, step)
+  ids_ref = ref['ids']
+  xt_flat = xt.view(-1)
+  if subs:     # carry-over rows keep their token (diffusion.py:1414-1418)
+    keep = xt_flat != 103
+    assert torch.equal(xs[keep], xt_flat[keep])
+    ids_ref = torch.where(keep, xt_flat, ids_ref)
+  tol = 3e-2 if round_bf16 else 2e-3
+  bad = (xs != ids_ref).nonzero().flatten().tolist()
+  for r in bad:
+    gg, gr = int(xs[r]) // 8, int(ids_ref[r]) // 8
+    if gg != gr:
+      gap = abs(ref['score'][r, gg] - ref['score'][r, gr])
+      assert gap <= tol, f'row {r}: groups {gg} vs {gr}, score gap {gap:.3e}'
+    else:
+      cum, tgt = ref['cum'][r], ref['target'][r]
+      lo, hi = sorted((int(xs[r]) % 8, int(ids_ref[r]) % 8))
+      edge = cum[lo:hi]
+      assert (abs(edge - tgt) <= tol * cum[-1]).all(), f'row {r}: in-group pick not a near-tie'
+  assert len(bad) <= max(2, rows // 16), f'{len(bad)} near-ties of {rows}'
+
+
+@pytest.mark.parametrize('diffusion,guidance,round_bf16', [
+  ('uniform', 'none', False), ('uniform', 'cfg', True), ('uniform', 'cfg', False),
+  ('absorbing_state', 'none', True)])
+def test_group_race_statistics(diffusion, guidance, round_bf16):
+  """The hierarchical race draws from the reference's distribution: token
+  frequencies over many rows with identical logits match the oracle posterior
+  (z-scores of the 60 likeliest tokens and of the lumped remainder), and agree
+  with the per-column race kernel on the same logits."""
+  V, ld, n = 4096, 4096, 32768
+  dev = torch.device('cuda')
+  g = torch.Generator().manual_seed(11)
+  ra = (torch.randn(V, generator=g) * 2.5).to(torch.bfloat16)
+  rb = (ra.float() + torch.randn(V, generator=g) * 0.7).to(torch.bfloat16)
+  la = ra[None].repeat(n, 1).contiguous().to(dev)
+  lb = rb[None].repeat(n, 1).contiguous().to(dev)
+  subs = diffusion == 'absorbing_state'
+  z = 103 if subs else 17
+  xt = torch.full((n,), z, dtype=torch.long)
+  st_a = helpers.make_stats(la, V, 103 if subs else -1)
+  st_b = helpers.make_stats(lb, V, -1)
+  common = dict(
+    logits_a=la, logits_b=lb if guidance == 'cfg' else None, xt=xt, mc_t=0.8, mc_s=0.3,
+    vocab=V, seq_len=1, diffusion=diffusion, guidance=guidance, gamma=2.0, subs=subs,
+    mask_logit=subs, mask_index=103, round_bf16=round_bf16, fast_math=True, seed=991,
+    step=3, stats_a=st_a.data_ptr(), stats_b=st_b.data_ptr() if guidance == 'cfg' else 0,
+    stats_ld=n, stats_chunks=st_a.shape[0])
+  xs_grp, _ = helpers.sampler_kernel(race_group=8, **common)
+  xs_col, _ = helpers.sampler_kernel(race_group=0, **common)
+  q = _oracle_probs(ra[None], rb[None], xt[:1, None], torch.tensor([0.8]), torch.tensor([0.3]),
+                    V, diffusion, guidance, 2.0, round_bf16)[0, 0].double()
+  q = q / q.sum()
+  top = q.topk(60).indices
+  for xs, what in ((xs_grp, 'group'), (xs_col, 'column')):
+    counts = torch.bincount(xs.cpu(), minlength=V).double()
+    exp = q[top] * n
+    zs = (counts[top] - exp) / (exp * (1 - q[top])).clamp_min(1).sqrt()
+    assert zs.abs().max().item() < 5.0, (what, zs)
+    rest, rest_exp = n - counts[top].sum().item(), n * (1 - q[top].sum().item())
+    assert abs(rest - rest_exp) < 5 * max(rest_exp, 1) ** 0.5, (what, rest, rest_exp)
+
+
+def test_group_race_full_size_properties():
+  """Config-3 sized launch (64 x 128 rows of 30522) through the production
+  kernel: ids in range, absorbing carry-over exact, deterministic for a fixed
+  Philox key and different for another key."""
+  rows, V, ld = 8192, 30522, 30528
+  dev = torch.device('cuda')
+  g = torch.Generator(device=dev).manual_seed(5)
+  la = (torch.randn(rows, ld, device=dev, generator=g) * 2).to(torch.bfloat16)
+  lb = (torch.randn(rows, ld, device=dev, generator=g) * 2).to(torch.bfloat16)
+  xt = torch.randint(0, V, (rows,), device=dev, generator=g)
+  st_a, st_b = helpers.make_stats(la, V), helpers.make_stats(lb, V)
+  common = dict(logits_a=la, logits_b=lb, xt=xt, mc_t=0.5, mc_s=0.499, vocab=V, seq_len=128,
+                diffusion='uniform', guidance='cfg', gamma=2.0, round_bf16=True, fast_math=True,
+                stats_a=st_a.data_ptr(), stats_b=st_b.data_ptr(), stats_ld=rows,
+                stats_chunks=st_a.shape[0], race_group=8)
+  a1, _ = helpers.sampler_kernel(seed=1, step=5, **common)
+  a2, _ = helpers.sampler_kernel(seed=1, step=5, **common)
+  a3, _ = helpers.sampler_kernel(seed=2, step=5, **common)
+  assert torch.equal(a1, a2)
+  assert int(a1.min()) >= 0 and int(a1.max()) < V
+  # with dt = 1/1000 most tokens stay (UDLM posterior mass at z): sanity of the z term
+  assert (a1 == xt).float().mean().item() > 0.9
+  assert (a1 != a3).any()

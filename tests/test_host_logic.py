@@ -109,3 +109,25 @@ def test_oracle_mdlm_resolves_all_masks():
   V = cases.vocab_size(case)
   out = oracle.sample(xt, lambda i: torch.rand(case.batch, case.length, V, generator=g), 16)
   assert (out == cases.Tok(case.vocab).mask_token_id).float().mean().item() < 0.05
+
+
+def test_group_race_restatement_is_a_categorical_draw():
+  """oracle.group_race_select (the CPU restatement of the production
+  sampler's hierarchical exponential race) reproduces the categorical
+  distribution it is given, and is a pure function of (seed, step, row)."""
+  import torch
+  from oracle import ref_sampler
+  V, n = 83, 30000            # ragged last group (83 = 10 * 8 + 3)
+  g = torch.Generator().manual_seed(0)
+  q = torch.softmax(torch.randn(V, generator=g) * 2, 0)
+  q[5] = 0.0
+  r1 = ref_sampler.group_race_select(q[None].repeat(n, 1), 12345, 7)
+  r2 = ref_sampler.group_race_select(q[None].repeat(n, 1), 12345, 7)
+  r3 = ref_sampler.group_race_select(q[None].repeat(n, 1), 12345, 8)
+  assert torch.equal(r1['ids'], r2['ids']) and not torch.equal(r1['ids'], r3['ids'])
+  assert int(r1['ids'].max()) < V
+  c = torch.bincount(r1['ids'], minlength=V).double()
+  assert c[5] == 0
+  qn = (q / q.sum()).double()
+  z = (c - qn * n) / (qn * n * (1 - qn)).clamp_min(1).sqrt()
+  assert z.abs().max().item() < 4.5, z
