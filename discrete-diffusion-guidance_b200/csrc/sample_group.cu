@@ -12,17 +12,23 @@
 // arg-max of  log2(sum_G q~) - log2(E_G),  and the column inside the winning
 // group is drawn by inverse CDF from one more uniform.  The distribution of
 // the result is exactly the reference's; the Philox work and the two lg2 per
-// column of the noise drop by 8x, which is what keeps this kernel on the HBM
-// roofline instead of the MUFU / issue limit.  (With injected noise the
+// column of the noise drop by 8x, which is what moves this kernel from the
+// MUFU / issue limit towards the HBM roofline.  (With injected noise the
 // per-column race of sample_fused.cu / sample_step.cu is used: that is the
 // path that is bit-comparable with the reference.)
 //
 // round_bf16 = 1 (the reference's bf16 log-softmax / exp roundings, SURVEY
 // 8a' item 4): lp = bf16(l - lse) takes only ~2000 distinct values that matter,
-// so  gamma*log2(dA*bf16(exp(lp)) + c0)  is a 2048-entry shared-memory table
-// per forward (built per CTA, rebuilt if the schedule scalars change) and the
-// hot loop has no transcendental per column at all except the exp of the
-// group sum.
+// so the per-column factor of q~ is a 2048-entry shared-memory table per
+// forward (built per CTA, rebuilt when the schedule scalars change):
+//   linear tables  A[i] = (dA x_i + c0)^gamma / max,  B[i] = (..)^(1-gamma) / max
+//                  -> q~_j = A[ia_j] * B[ib_j], group sum by FFMA, no MUFU per column
+//                  (used when the dynamic range provably fits fp32),
+//   log2 tables    otherwise (q~_j = 2^(A + B), one ex2 per column).
+//
+// One CTA of 128 threads walks one row at a time; thread t owns the groups
+// G = t + 128 k.  The next row's ids and softmax partials are prefetched
+// (register / cp.async) while the current row streams.
 //
 // Philox stream (so tests can regenerate it; G = j / 8 is the group index):
 //   key     = (seed_lo, seed_hi)
@@ -37,9 +43,13 @@ namespace {
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+constexpr int kCtasPerSm = 5;
 constexpr int kLut = 2048;          // bf16 magnitudes 0x3B00 .. 0x42FF: |lp| in [2^-9, 128)
 constexpr int kLutBase = 0x3B00;
+constexpr int kMaxChunks = 256;     // softmax partials staged in smem (V <= 32768); else read from global
+constexpr float kLinearRange = 120.f;   // log2 dynamic range allowed for the linear tables
 
 enum GMode : int { G_UNI_NONE = 0, G_UNI_CFG = 1, G_ABS_NONE = 2 };
 
@@ -58,6 +68,14 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ float neg_log2_E(float u) {
   // E = 1e-10 - ln(u + 1e-10);  returns -log2(E)
@@ -107,7 +125,19 @@ __device__ __forceinline__ float g_elem(const RowConst& c, float la, float lb, i
   return __fadd_rn(__fmul_rn(c.gam, lg2a(na)), __fmul_rn(c.omg, lg2a(nb)));
 }
 
-// packed f32x2 subtract (one issue slot for two differences)
+template <int MODE, bool ROUND>
+__device__ __forceinline__ void group_careful(const RowConst& c, const uint4& ra, const uint4& rb, int j0,
+                                              float (&g)[8]) {
+  const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w};
+  const uint32_t wb[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    g[2 * p] = g_elem<MODE, ROUND>(c, bf16_lo(wa[p]), bf16_lo(wb[p]), j0 + 2 * p);
+    g[2 * p + 1] = g_elem<MODE, ROUND>(c, bf16_hi(wa[p]), bf16_hi(wb[p]), j0 + 2 * p + 1);
+  }
+}
+
+// packed f32x2 arithmetic (one issue slot for two results)
 __device__ __forceinline__ float2 sub2(float k, float l0, float l1) {
   float2 r;
   asm("{\n\t"
@@ -119,7 +149,6 @@ __device__ __forceinline__ float2 sub2(float k, float l0, float l1) {
       "}" : "=f"(r.x), "=f"(r.y) : "f"(k), "f"(l0), "f"(l1));
   return r;
 }
-
 __device__ __forceinline__ float2 add2(float2 x, float2 y) {
   float2 r;
   asm("{\n\t"
@@ -131,70 +160,41 @@ __device__ __forceinline__ float2 add2(float2 x, float2 y) {
       "}" : "=f"(r.x), "=f"(r.y) : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y));
   return r;
 }
+__device__ __forceinline__ float2 fma2(float2 x, float2 y, float2 z) {
+  float2 r;
+  asm("{\n\t"
+      ".reg .b64 a, b, c, d;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "mov.b64 c, {%6, %7};\n\t"
+      "fma.rn.f32x2 d, a, b, c;\n\t"
+      "mov.b64 {%0, %1}, d;\n\t"
+      "}" : "=f"(r.x), "=f"(r.y) : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y), "f"(z.x), "f"(z.y));
+  return r;
+}
 
 // Table byte offsets of a pair of differences d = lse - l >= 0: bf16 round,
 // (magnitude bits - 0x3B00) clamped to [0, 2047] with one DPX instruction for
-// the pair, times 8 = the stride of the interleaved (a-term, b-term) table
-// (both halves at once: 8 * 2047 still fits 16 bits).
+// the pair, times 4 (both halves at once: 4 * 2047 still fits 16 bits).
 constexpr uint32_t kNegBase2 = (uint32_t)(0x10000 - kLutBase) * 0x00010001u;   // (-0x3B00, -0x3B00) as s16x2
 __device__ __forceinline__ uint32_t lut_offsets2(float d0, float d1, uint32_t neg_base2) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(d0, d1);
   const uint32_t w = *reinterpret_cast<const uint32_t*>(&h);
   constexpr uint32_t kMaxIdx = (uint32_t)(kLut - 1) * 0x00010001u;
-  return __viaddmin_s16x2_relu(w, neg_base2, kMaxIdx) << 3;
+  return __viaddmin_s16x2_relu(w, neg_base2, kMaxIdx) << 2;
 }
 __device__ __forceinline__ float lut_at(const float* T, uint32_t byte_off) {
   return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(T) + byte_off);
 }
-
-// log2 of the unnormalised guided posterior of 8 ordinary columns (no z, no
-// mask column, all < V): branch-free
-template <int MODE, bool ROUND>
-__device__ __forceinline__ void group_hot(const RowConst& c, const uint4& ra, const uint4& rb, const float* T,
-                                          uint32_t neg_base2, float (&g)[8]) {
-  const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w};
-  const uint32_t wb[4] = {rb.x, rb.y, rb.z, rb.w};
+// table values of the four column pairs of one 16-byte vector
+__device__ __forceinline__ void lut_gather(const uint4& r, float K, const float* T, uint32_t neg_base2,
+                                           float2 (&v)[4]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    if (ROUND) {
-      const float2 da = sub2(c.Ka, bf16_lo(wa[p]), bf16_hi(wa[p]));
-      const uint32_t ta = lut_offsets2(da.x, da.y, neg_base2);
-      float2 gp = make_float2(lut_at(T, ta & 0xffffu), lut_at(T, ta >> 16));
-      if (MODE == G_UNI_CFG) {
-        const float2 db = sub2(c.Kb, bf16_lo(wb[p]), bf16_hi(wb[p]));
-        const uint32_t tb = lut_offsets2(db.x, db.y, neg_base2);
-        gp = add2(gp, make_float2(lut_at(T + 1, tb & 0xffffu), lut_at(T + 1, tb >> 16)));
-      }
-      g[2 * p] = gp.x;
-      g[2 * p + 1] = gp.y;
-    } else if (MODE == G_ABS_NONE) {
-      g[2 * p] = fmaf(bf16_lo(wa[p]), kLog2e, -c.ka2);
-      g[2 * p + 1] = fmaf(bf16_hi(wa[p]), kLog2e, -c.ka2);
-    } else {
-      float g0 = lg2a(fmaf(c.dA, ex2a(fmaf(bf16_lo(wa[p]), kLog2e, -c.ka2)), c.c0));
-      float g1 = lg2a(fmaf(c.dA, ex2a(fmaf(bf16_hi(wa[p]), kLog2e, -c.ka2)), c.c0));
-      if (MODE == G_UNI_CFG) {
-        const float h0 = lg2a(fmaf(c.dA, ex2a(fmaf(bf16_lo(wb[p]), kLog2e, -c.kb2)), c.c0));
-        const float h1 = lg2a(fmaf(c.dA, ex2a(fmaf(bf16_hi(wb[p]), kLog2e, -c.kb2)), c.c0));
-        g0 = __fadd_rn(__fmul_rn(c.gam, g0), __fmul_rn(c.omg, h0));
-        g1 = __fadd_rn(__fmul_rn(c.gam, g1), __fmul_rn(c.omg, h1));
-      }
-      g[2 * p] = g0;
-      g[2 * p + 1] = g1;
-    }
-  }
-}
-
-// the same for a group that may hold z / the mask column / columns >= V
-template <int MODE, bool ROUND>
-__device__ __forceinline__ void group_careful(const RowConst& c, const uint4& ra, const uint4& rb, int j0,
-                                              float (&g)[8]) {
-  const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w};
-  const uint32_t wb[4] = {rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    g[2 * p] = g_elem<MODE, ROUND>(c, bf16_lo(wa[p]), bf16_lo(wb[p]), j0 + 2 * p);
-    g[2 * p + 1] = g_elem<MODE, ROUND>(c, bf16_hi(wa[p]), bf16_hi(wb[p]), j0 + 2 * p + 1);
+    const float2 d = sub2(K, bf16_lo(w[p]), bf16_hi(w[p]));
+    const uint32_t t = lut_offsets2(d.x, d.y, neg_base2);
+    v[p] = make_float2(lut_at(T, t & 0xffffu), lut_at(T, t >> 16));
   }
 }
 
@@ -212,60 +212,195 @@ __device__ __forceinline__ float sum_ex2_8(const float (&g)[8], float gm) {
   return acc.x + acc.y;
 }
 
-// group exponential of group G (see the stream layout at the top of the file)
-__device__ __forceinline__ uint4 group_noise_words(int tid, int quad, int64_t row, int step, uint2 key) {
+// log2( sum over the 8 ordinary columns of one group of q~_j ) up to the
+// row-constant `goff` (no z, no mask column, all < V): branch-free.
+//   LIN  (ROUND only): tables hold linear factors, sum by FFMA
+//   !LIN: tables (ROUND) or MUFU math give log2 q~_j, sum of 2^(g - max)
+template <int MODE, bool ROUND, bool LIN>
+__device__ __forceinline__ float group_hot(const RowConst& c, const uint4& ra, const uint4& rb, const float* A,
+                                           const float* B, uint32_t neg_base2) {
+  if (ROUND && LIN) {
+    float2 va[4];
+    lut_gather(ra, c.Ka, A, neg_base2, va);
+    float2 acc;
+    if (MODE == G_UNI_CFG) {
+      float2 vb[4];
+      lut_gather(rb, c.Kb, B, neg_base2, vb);
+      acc = make_float2(va[0].x * vb[0].x, va[0].y * vb[0].y);
+#pragma unroll
+      for (int p = 1; p < 4; ++p) acc = fma2(va[p], vb[p], acc);
+    } else {
+      acc = add2(add2(va[0], va[1]), add2(va[2], va[3]));
+    }
+    return lg2a(acc.x + acc.y);
+  }
+  float g[8];
+  if (ROUND) {
+    float2 va[4];
+    lut_gather(ra, c.Ka, A, neg_base2, va);
+    if (MODE == G_UNI_CFG) {
+      float2 vb[4];
+      lut_gather(rb, c.Kb, B, neg_base2, vb);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) va[p] = add2(va[p], vb[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { g[2 * p] = va[p].x; g[2 * p + 1] = va[p].y; }
+  } else {
+    const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w};
+    const uint32_t wb[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (MODE == G_ABS_NONE) {
+        g[2 * p] = fmaf(bf16_lo(wa[p]), kLog2e, -c.ka2);
+        g[2 * p + 1] = fmaf(bf16_hi(wa[p]), kLog2e, -c.ka2);
+      } else {
+        float g0 = lg2a(fmaf(c.dA, ex2a(fmaf(bf16_lo(wa[p]), kLog2e, -c.ka2)), c.c0));
+        float g1 = lg2a(fmaf(c.dA, ex2a(fmaf(bf16_hi(wa[p]), kLog2e, -c.ka2)), c.c0));
+        if (MODE == G_UNI_CFG) {
+          const float h0 = lg2a(fmaf(c.dA, ex2a(fmaf(bf16_lo(wb[p]), kLog2e, -c.kb2)), c.c0));
+          const float h1 = lg2a(fmaf(c.dA, ex2a(fmaf(bf16_hi(wb[p]), kLog2e, -c.kb2)), c.c0));
+          g0 = __fadd_rn(__fmul_rn(c.gam, g0), __fmul_rn(c.omg, h0));
+          g1 = __fadd_rn(__fmul_rn(c.gam, g1), __fmul_rn(c.omg, h1));
+        }
+        g[2 * p] = g0;
+        g[2 * p + 1] = g1;
+      }
+    }
+  }
+  const float gm = max8(g);
+  return gm + lg2a(sum_ex2_8(g, gm));      // all -inf -> NaN, which never wins a '>' comparison
+}
+
+// group exponential words of (virtual thread vt, quad q): see the stream layout above
+__device__ __forceinline__ uint4 group_noise_words(int vt, int quad, int64_t row, int step, uint2 key) {
   return philox4x32_10(
-    make_uint4((uint32_t)(tid | (quad << 8)), (uint32_t)row, (uint32_t)((uint64_t)row >> 32), (uint32_t)step), key);
+    make_uint4((uint32_t)(vt | (quad << 8)), (uint32_t)row, (uint32_t)((uint64_t)row >> 32), (uint32_t)step), key);
+}
+__device__ __forceinline__ uint32_t group_noise_word(int G, int64_t row, int step, uint2 key) {
+  const uint4 r = group_noise_words(G & 255, G >> 10, row, step, key);
+  const int w = (G >> 8) & 3;
+  return w == 0 ? r.x : w == 1 ? r.y : w == 2 ? r.z : r.w;
+}
+
+// One pass over the full groups of a row: thread t takes G = t + 128 k.  Two
+// vector buffers alternate (even / odd k), each reloaded for k + 2 as soon as it
+// has been consumed, so every load has two group iterations to land.
+template <int MODE, bool ROUND, bool LIN>
+__device__ __forceinline__ void row_pass(const RowConst& c, const uint4* va, const uint4* vb, uint4 ra0, uint4 rb0,
+                                         uint4 ra1, uint4 rb1, const float* A, const float* B, uint32_t neg_base2,
+                                         int n_full, int special_grp, int64_t row, int step, uint2 key, float& best,
+                                         int& bgrp) {
+  const int tid = threadIdx.x;
+  uint4 ra[2] = {ra0, ra1}, rb[2] = {rb0, rb1};
+  // 8 consecutive k of this thread = virtual threads (tid, tid + 128) x one Philox quad each
+  for (int k8 = 0; tid + k8 * (8 * kThreads) < n_full; ++k8) {
+    const uint4 n0 = group_noise_words(tid, k8, row, step, key);
+    const uint4 n1 = group_noise_words(tid + kThreads, k8, row, step, key);
+    const uint32_t rw[8] = {n0.x, n1.x, n0.y, n1.y, n0.z, n1.z, n0.w, n1.w};
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int G = tid + (k8 * 8 + s) * kThreads;
+      if (G >= n_full) break;
+      const float lsum = group_hot<MODE, ROUND, LIN>(c, ra[s & 1], rb[s & 1], A, B, neg_base2);
+      {                                               // reload this buffer for k + 2 (clamped: always in bounds)
+        const int gn = min(G + 2 * kThreads, n_full - 1) - tid;
+        ra[s & 1] = ldg_stream(va + gn);
+        if (MODE == G_UNI_CFG) rb[s & 1] = ldg_stream(vb + gn);
+      }
+      const float sc = lsum + neg_log2_E(u01_from_bits(rw[s]));
+      if (sc > best && G != special_grp) { best = sc; bgrp = G; }
+    }
+  }
 }
 
 template <int MODE, bool ROUND>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 sample_group_kernel(const ddg_sample_step_args a) {
-  __shared__ __align__(16) float s_T[ROUND ? 2 * kLut : 4];   // (a-term, b-term) interleaved
+  constexpr int NT = MODE == G_UNI_CFG ? 2 : 1;        // logits tensors
+  __shared__ __align__(16) float s_A[ROUND ? kLut : 4];
+  __shared__ __align__(16) float s_B[(ROUND && MODE == G_UNI_CFG) ? kLut : 4];
+  __shared__ __align__(16) float2 s_st[2][NT][kMaxChunks];   // [buffer][tensor][chunk] softmax partials
   __shared__ float s_k[2];
-  __shared__ float s_red[kThreads / 32];
-  __shared__ int s_idx[kThreads / 32];
+  __shared__ float s_red[kWarps];
+  __shared__ int s_idx[kWarps];
   __shared__ int s_win;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = a.vocab;
   const int step = a.step_ptr ? *a.step_ptr : a.step;
   const uint64_t seed64 = a.seed_ptr ? *a.seed_ptr : a.seed;
   const uint2 key = make_uint2((uint32_t)seed64, (uint32_t)(seed64 >> 32));
-  const float2* st_a = reinterpret_cast<const float2*>(a.stats_a);
-  const float2* st_b = reinterpret_cast<const float2*>(a.stats_b);
+  const float2* st_mine = reinterpret_cast<const float2*>(warp == 0 ? a.stats_a : a.stats_b);  // warp w: tensor w
   const int n_full = V >> 3;                 // groups made of 8 valid columns
   const int n_groups = (V + 7) >> 3;
+  const bool stage = a.stats_chunks <= kMaxChunks;
   uint32_t neg_base2;                        // opaque to constant propagation: stays in one register
   asm volatile("mov.u32 %0, %1;" : "=r"(neg_base2) : "n"(kNegBase2));
   float tab_mct = -1.f, tab_mcs = -1.f;     // schedule scalars the table was built for
-  bool tab_ready = false;
+  bool tab_ready = false, lin = true;
+  float goff = 0.f;                          // row-constant offset of the linear tables (log2)
 
-  for (int64_t row = blockIdx.x; row < a.rows; row += gridDim.x) {
-    const int z = (int)a.xt[row];
+  // warp w < NT stages tensor w's partials of `row` into buffer `buf` (each lane copies what it reads later)
+  auto prefetch_stats = [&](int64_t r, int b) {
+    if (stage && warp < NT && r < a.rows) {
+      const float2* st = st_mine + r;
+      for (int ch = lane; ch < a.stats_chunks; ch += 32) cp_async8(&s_st[b][warp][ch], st + (int64_t)ch * a.stats_ld);
+    }
+    cp_async_commit();
+  };
+
+  int64_t row = blockIdx.x;
+  int z_next = row < a.rows ? (int)a.xt[row] : 0;
+  prefetch_stats(row, 0);
+  int buf = 0;
+  for (; row < a.rows; row += gridDim.x, buf ^= 1) {
+    const int z = z_next;
+    const int64_t row_n = row + gridDim.x;
+    if (row_n < a.rows) z_next = (int)a.xt[row_n];
+    prefetch_stats(row_n, buf ^ 1);
     if (MODE == G_ABS_NONE && z != a.mask_index) {      // carry-over (diffusion.py:1414-1418)
       if (tid == 0) a.xs[row] = z;
       continue;
     }
-    // this thread's groups: G = tid + 256 * it  ->  vector G of the row
-    const uint4* va = reinterpret_cast<const uint4*>(
-      reinterpret_cast<const __nv_bfloat16*>(a.logits_a) + row * a.ld_a) + tid;
-    const uint4* vb = MODE == G_UNI_CFG ? reinterpret_cast<const uint4*>(
-      reinterpret_cast<const __nv_bfloat16*>(a.logits_b) + row * a.ld_b) + tid : va;
-    // first vectors in flight while the normalisers and the table are prepared
-    uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
-    if (tid < n_full) {
-      ra = ldg_stream(va);
-      if (MODE == G_UNI_CFG) rb = ldg_stream(vb);
+    const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(a.logits_a) + row * a.ld_a;
+    const __nv_bfloat16* pb = MODE == G_UNI_CFG ? reinterpret_cast<const __nv_bfloat16*>(a.logits_b) + row * a.ld_b : pa;
+    const uint4* va = reinterpret_cast<const uint4*>(pa) + tid;   // this thread's groups: va[128 k]
+    const uint4* vb = reinterpret_cast<const uint4*>(pb) + tid;
+    // first vectors and the logits at z in flight while the normalisers / table are prepared
+    uint4 ra0, rb0 = make_uint4(0, 0, 0, 0), ra1, rb1 = make_uint4(0, 0, 0, 0);
+    {
+      const int g0 = min(tid, n_full - 1) - tid, g1 = min(tid + kThreads, n_full - 1) - tid;
+      ra0 = ldg_stream(va + g0);
+      ra1 = ldg_stream(va + g1);
+      if (MODE == G_UNI_CFG) {
+        rb0 = ldg_stream(vb + g0);
+        rb1 = ldg_stream(vb + g1);
+      }
     }
-    // ---- row normalisers from the GEMM partials (warps 0 and 1)
-    if (warp < (MODE == G_UNI_CFG ? 2 : 1)) {
-      const float2* st = (warp == 0 ? st_a : st_b) + row;
+    __nv_bfloat16 lz_a = pa[0], lz_b = pa[0];
+    if (MODE != G_ABS_NONE) {
+      lz_a = pa[z];
+      if (MODE == G_UNI_CFG) lz_b = pb[z];
+    }
+    // ---- row normalisers from the GEMM partials (warp w < NT: tensor w)
+    if (warp < NT) {
       float m = -INFINITY, s = 0.f;
-      for (int ch = lane; ch < a.stats_chunks; ch += 32) {
-        const float2 pr = st[(int64_t)ch * a.stats_ld];
-        const float nm = fmaxf(m, pr.x);
-        s = s * ex2a((m - nm) * kLog2e) + pr.y * ex2a((pr.x - nm) * kLog2e);
-        m = nm;
+      if (stage) {
+        cp_async_wait<1>();                              // this row's copies (the next row's may be in flight)
+        for (int ch = lane; ch < a.stats_chunks; ch += 32) {
+          const float2 pr = s_st[buf][warp][ch];
+          const float nm = fmaxf(m, pr.x);
+          s = s * ex2a((m - nm) * kLog2e) + pr.y * ex2a((pr.x - nm) * kLog2e);
+          m = nm;
+        }
+      } else {
+        const float2* st = st_mine + row;
+        for (int ch = lane; ch < a.stats_chunks; ch += 32) {
+          const float2 pr = st[(int64_t)ch * a.stats_ld];
+          const float nm = fmaxf(m, pr.x);
+          s = s * ex2a((m - nm) * kLog2e) + pr.y * ex2a((pr.x - nm) * kLog2e);
+          m = nm;
+        }
       }
       const float M = warp_max(m);
       s = (m == -INFINITY) ? 0.f : s * ex2a((m - M) * kLog2e);
@@ -293,28 +428,42 @@ sample_group_kernel(const ddg_sample_step_args a) {
       c.mask_score = 0.f;
     }
     if (ROUND) {
-      // ---- table of gamma * log2(dA * bf16(exp(-|lp|)) + c0) over the bf16 values of |lp|
+      // ---- per-column factor tables over the bf16 values of |lp| (see the header comment)
       const bool stale = MODE == G_ABS_NONE ? !tab_ready : (!tab_ready || mc_t != tab_mct || mc_s != tab_mcs);
       if (stale) {                                   // block-uniform
+        float mA = 0.f, mB = 0.f;
+        if (MODE == G_ABS_NONE) {
+          lin = true; goff = 0.f;
+        } else {
+          const float lq_hi = lg2a(c.dA + c.c0), lq_lo = lg2a(c.c0);   // x = 1 / x = 0
+          if (MODE == G_UNI_NONE) {
+            lin = (lq_hi - lq_lo) <= kLinearRange; mA = lq_hi;
+          } else {
+            lin = (fabsf(c.gam) + fabsf(c.omg)) * (lq_hi - lq_lo) <= kLinearRange;
+            mA = fmaxf(__fmul_rn(c.gam, lq_hi), __fmul_rn(c.gam, lq_lo));
+            mB = fmaxf(__fmul_rn(c.omg, lq_hi), __fmul_rn(c.omg, lq_lo));
+          }
+          goff = lin ? mA + mB : 0.f;
+        }
         for (int i = tid; i < kLut; i += kThreads) {
           const float mag = __uint_as_float((uint32_t)(kLutBase + i) << 16);
           const float x = bf16_round(ex2a(-mag * kLog2e));
           if (MODE == G_ABS_NONE) {
-            s_T[2 * i] = lg2a(x);
+            s_A[i] = x;                                             // q~ = x (bf16-exact), linear
           } else {
             const float lq = lg2a(fmaf(c.dA, x, c.c0));
+            const float ta = MODE == G_UNI_CFG ? __fmul_rn(c.gam, lq) : lq;
+            s_A[i] = lin ? ex2a(ta - mA) : ta;
             if (MODE == G_UNI_CFG) {
-              s_T[2 * i] = __fmul_rn(c.gam, lq);
-              s_T[2 * i + 1] = __fmul_rn(c.omg, lq);
-            } else {
-              s_T[2 * i] = lq;
+              const float tb = __fmul_rn(c.omg, lq);
+              s_B[i] = lin ? ex2a(tb - mB) : tb;
             }
           }
         }
         tab_ready = true; tab_mct = mc_t; tab_mcs = mc_s;
       }
     }
-    __syncthreads();
+    __syncthreads();                                     // B1: s_k and the tables are ready
     c.Ka = s_k[0];
     c.Kb = MODE == G_UNI_CFG ? s_k[1] : 0.f;
     c.ka2 = c.Ka * kLog2e;
@@ -324,41 +473,21 @@ sample_group_kernel(const ddg_sample_step_args a) {
       special = a.mask_index;
       c.zc_a = c.zc_b = 0.f;
     } else {
-      const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(a.logits_a) + row * a.ld_a;
-      const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(a.logits_b) + row * a.ld_b;
-      c.zc_a = atV * x_of<ROUND>(__bfloat162float(pa[z]), c.Ka, c.ka2) + zoff;
-      c.zc_b = MODE == G_UNI_CFG ? atV * x_of<ROUND>(__bfloat162float(pb[z]), c.Kb, c.kb2) + zoff : 0.f;
+      c.zc_a = atV * x_of<ROUND>(__bfloat162float(lz_a), c.Ka, c.ka2) + zoff;
+      c.zc_b = MODE == G_UNI_CFG ? atV * x_of<ROUND>(__bfloat162float(lz_b), c.Kb, c.kb2) + zoff : 0.f;
       special = z;
     }
     const int special_grp = special >> 3;
 
     // ---- one pass over the row: per full group of 8 columns, log2(sum q~) - log2(E).
     // The group holding z / the mask column is evaluated too (branch-free) but its
-    // score is discarded here and redone on the careful path below.
+    // score is discarded there and redone on the careful path below.
     float best = -INFINITY;
     int bgrp = 0x7fffffff;
-    for (int q = 0; tid + q * (4 * kThreads) < n_full; ++q) {
-      const uint4 rnd = group_noise_words(tid, q, row, step, key);
-      const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-      for (int s4 = 0; s4 < 4; ++s4) {
-        const int G = tid + (q * 4 + s4) * kThreads;
-        if (G >= n_full) break;
-        const uint4 ca = ra, cb = rb;
-        {                                               // prefetch the next vectors (clamped: always in bounds)
-          const int gn = min(G + kThreads, n_full - 1) - tid;
-          ra = ldg_stream(va + gn);
-          if (MODE == G_UNI_CFG) rb = ldg_stream(vb + gn);
-        }
-        float g[8];
-        group_hot<MODE, ROUND>(c, ca, cb, s_T, neg_base2, g);
-        const float gm = max8(g);
-        const float S = sum_ex2_8(g, gm);
-        const float sc = gm + lg2a(S) + neg_log2_E(u01_from_bits(rw[s4]));
-        // (gm == -inf gives NaN, which never compares greater)
-        if (sc > best && G != special_grp) { best = sc; bgrp = G; }
-      }
-    }
+    if (ROUND && lin)
+      row_pass<MODE, ROUND, true>(c, va, vb, ra0, rb0, ra1, rb1, s_A, s_B, neg_base2, n_full, special_grp, row, step, key, best, bgrp);
+    else
+      row_pass<MODE, ROUND, false>(c, va, vb, ra0, rb0, ra1, rb1, s_A, s_B, neg_base2, n_full, special_grp, row, step, key, best, bgrp);
     // ---- the (at most two) groups that need the careful path: the one holding z /
     // the mask column and the ragged tail; each is done by the thread that owns it
 #pragma unroll 1
@@ -372,11 +501,8 @@ sample_group_kernel(const ddg_sample_step_args a) {
         group_careful<MODE, ROUND>(c, ca, cb, G * 8, g);
         const float gm = max8(g);
         if (gm > -INFINITY) {
-          const float S = sum_ex2_8(g, gm);
-          const uint4 rnd = group_noise_words(tid, G >> 10, row, step, key);
-          const int wsel = (G >> 8) & 3;
-          const uint32_t word = wsel == 0 ? rnd.x : wsel == 1 ? rnd.y : wsel == 2 ? rnd.z : rnd.w;
-          const float sc = gm + lg2a(S) + neg_log2_E(u01_from_bits(word));
+          const float sc = (gm - goff) + lg2a(sum_ex2_8(g, gm)) +
+                           neg_log2_E(u01_from_bits(group_noise_word(G, row, step, key)));
           if (sc > best || (sc == best && G < bgrp)) { best = sc; bgrp = G; }
         }
       }
@@ -389,19 +515,19 @@ sample_group_kernel(const ddg_sample_step_args a) {
       if (os > best || (os == best && oi < bgrp)) { best = os; bgrp = oi; }
     }
     if (lane == 0) { s_red[warp] = best; s_idx[warp] = bgrp; }
-    __syncthreads();
+    __syncthreads();                                     // B2
     if (warp == 0) {
-      best = lane < kThreads / 32 ? s_red[lane] : -INFINITY;
-      bgrp = lane < kThreads / 32 ? s_idx[lane] : 0x7fffffff;
+      best = lane < kWarps ? s_red[lane] : -INFINITY;
+      bgrp = lane < kWarps ? s_idx[lane] : 0x7fffffff;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = kWarps / 2; o > 0; o >>= 1) {
         const float os = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bgrp, o);
         if (os > best || (os == best && oi < bgrp)) { best = os; bgrp = oi; }
       }
       if (lane == 0) s_win = bgrp;
     }
-    __syncthreads();
+    __syncthreads();                                     // B3
     const int win = s_win;
     if (win == 0x7fffffff) {
       if (tid == 0) a.xs[row] = 0;                      // all-zero row: cannot happen with finite logits
@@ -428,15 +554,16 @@ sample_group_kernel(const ddg_sample_step_args a) {
       }
       a.xs[row] = win * 8 + (pick < 0 ? last : pick);
     }
-    // s_k / s_red / the table are rewritten only after every thread has passed this
-    // row's last read of them (the barrier above); s_win is rewritten after the next
-    // row's second barrier.  No trailing barrier needed.
+    // Shared state is rewritten by the next row only before its B1 (s_k, tables, the other
+    // s_st buffer), before its B2 (s_red / s_idx) and before its B3 (s_win); every read of
+    // this row precedes the barrier after which those writes can happen.
   }
+  cp_async_wait<0>();
 }
 
 template <int MODE, bool ROUND>
 int launch(const ddg_sample_step_args& a, cudaStream_t s) {
-  int64_t grid = (int64_t)sm_count() * 4 * 4;     // a few waves of resident CTAs
+  int64_t grid = (int64_t)sm_count() * kCtasPerSm * 2;     // two waves of resident CTAs
   if (grid > a.rows) grid = a.rows;
   sample_group_kernel<MODE, ROUND><<<(unsigned)grid, kThreads, 0, s>>>(a);
   return check_cuda(cudaGetLastError(), "sample_group launch");
