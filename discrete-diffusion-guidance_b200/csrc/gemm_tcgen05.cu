@@ -41,7 +41,9 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_ROW_BYTES = 80;                  // 64 B payload + 16 B pad: conflict-free 128-bit stores
 constexpr int EPI_SLAB_BYTES = 32 * EPI_ROW_BYTES;  // one warp's 32 accumulator rows
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * EPI_SLAB_BYTES;
+constexpr int EPI_BIAS_BYTES = NUM_EPI_WARPS * (BN / 2) * 4;   // fp32 bias of each epilogue warp's 128 columns
+constexpr int SMEM_BYTES =
+  STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * EPI_SLAB_BYTES + EPI_BIAS_BYTES;
 
 struct GemmParams {
   void* out;
@@ -176,6 +178,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
     : "r"(taddr));
 }
+// load + wait in one statement: the outputs are only defined after the wait, so
+// nothing can be scheduled in between and no register copies are needed
+__device__ __forceinline__ void tmem_ld32_sync(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+    "tcgen05.wait::ld.sync.aligned;"
+    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+    : "r"(taddr)
+    : "memory");
+}
 // The registers are listed as in/out operands so that no use of them can be
 // scheduled ahead of the wait.
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
@@ -286,6 +303,66 @@ __device__ __forceinline__ float ex2f_approx(float x) {
   return y;
 }
 
+// packed f32x2 arithmetic: one issue slot for two results (sm_100 FADD2 / FMUL2 / FFMA2)
+__device__ __forceinline__ float2 add2(float2 x, float2 y) {
+  float2 r;
+  asm("{\n\t"
+      ".reg .b64 a, b, d;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "add.f32x2 d, a, b;\n\t"
+      "mov.b64 {%0, %1}, d;\n\t"
+      "}" : "=f"(r.x), "=f"(r.y) : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y));
+  return r;
+}
+__device__ __forceinline__ float2 sub2(float2 x, float2 y) {
+  float2 r;
+  asm("{\n\t"
+      ".reg .b64 a, b, d;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "sub.f32x2 d, a, b;\n\t"
+      "mov.b64 {%0, %1}, d;\n\t"
+      "}" : "=f"(r.x), "=f"(r.y) : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y));
+  return r;
+}
+__device__ __forceinline__ float2 mul2(float2 x, float2 y) {
+  float2 r;
+  asm("{\n\t"
+      ".reg .b64 a, b, d;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "mul.f32x2 d, a, b;\n\t"
+      "mov.b64 {%0, %1}, d;\n\t"
+      "}" : "=f"(r.x), "=f"(r.y) : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y));
+  return r;
+}
+__device__ __forceinline__ float2 fma2(float2 x, float2 y, float2 z) {
+  float2 r;
+  asm("{\n\t"
+      ".reg .b64 a, b, c, d;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "mov.b64 c, {%6, %7};\n\t"
+      "fma.rn.f32x2 d, a, b, c;\n\t"
+      "mov.b64 {%0, %1}, d;\n\t"
+      "}" : "=f"(r.x), "=f"(r.y) : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y), "f"(z.x), "f"(z.y));
+  return r;
+}
+
+// tanh-GELU of a column pair (same formula as gelu_tanh below)
+__device__ __forceinline__ float2 gelu_tanh2(float2 v) {
+  const float2 t = fma2(mul2(v, v), make_float2(-0.10294324f, -0.10294324f), make_float2(-2.3022082f, -2.3022082f));
+  const float2 z = mul2(v, t);
+  float ex, ey, rx, ry;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(z.y));
+  const float2 d = add2(make_float2(ex, ey), make_float2(1.f, 1.f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(d.y));
+  return mul2(v, make_float2(rx, ry));
+}
+
 __device__ __forceinline__ float gelu_tanh(float v) {
   // 0.5 v (1 + tanh(u)) == v * sigmoid(2u),  u = sqrt(2/pi) (v + 0.044715 v^3)
   // exp(-2u) = ex2(v * (c1 + c2 v^2)), c1 = -2 sqrt(2/pi) log2(e), c2 = 0.044715 c1
@@ -312,6 +389,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint8_t* smem_epi = smem + STAGES * STAGE_BYTES + 256;
+  uint8_t* smem_bias = smem_epi + NUM_EPI_WARPS * EPI_SLAB_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -500,120 +578,166 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           }
         }
       } else {
-        // -------- 16-bit outputs: store / rotary / bias+GELU
-        float cs[32], sn[32];
-        if (EPI == DDG_EPI_QKV_ROPE) {
-          const int pos = row_ok ? (m % p.seq_len) : 0;
-          load32<T>(reinterpret_cast<const T*>(p.rope_cos) + (int64_t)pos * 32, cs);
-          load32<T>(reinterpret_cast<const T*>(p.rope_sin) + (int64_t)pos * 32, sn);
-        }
+        // -------- 16-bit outputs: store / rotary / bias+GELU.  Register phase in packed
+        // f32x2 arithmetic on column pairs; the bias of this warp's 128 columns sits as
+        // fp32 in warp-private shared memory (one broadcast LDS.128 per 4 columns).
         T* oslab = reinterpret_cast<T*>(p.out) + (int64_t)mw * p.ld_out + cchunk * 8;
-        float st_m = -INFINITY, st_s = 0.f;      // running (max, sum 2^((v-max) log2e)) of this row chunk
-#pragma unroll 1
-        for (int g = 0; g < BN / 128; ++g) {
-          const int nc = n0 + g * 64;             // first column of this 64-wide group
-          uint32_t r0[32], r1[32];
-          tmem_ld32(taddr + (uint32_t)(g * 64), r0);
-          tmem_ld32(taddr + (uint32_t)(g * 64 + 32), r1);
-          tmem_ld_wait(r0);
-          tmem_ld_wait(r1);
-          if (nc >= p.N) continue;                 // warp-uniform
-          float v0[32], v1[32];
+        const bool have_bias = p.bias != nullptr;
+        const uint32_t bias_s = smem_u32(smem_bias) + (uint32_t)e * (BN / 2) * 4;   // shared-window address
+        if (have_bias && n0 < p.N) {
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(p.bias) + n0) + lane);
+          const float2 b01 = H2<T>::unpack(raw.x), b23 = H2<T>::unpack(raw.y);
+          st_shared_v4(bias_s + 16 * lane, __float_as_uint(b01.x), __float_as_uint(b01.y), __float_as_uint(b23.x),
+                       __float_as_uint(b23.y));
+        }
+        __syncwarp();
+        // stages 32 columns (16 packed words per row) through the slab and stores them coalesced
+        auto store_chunk = [&](const uint32_t (&w)[16], int nc) {
+          __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { v0[i] = __uint_as_float(r0[i]); v1[i] = __uint_as_float(r1[i]); }
-          if (p.bias) {
-            float b0[32], b1[32];
-            load32<T>(reinterpret_cast<const T*>(p.bias) + nc, b0);
-            load32<T>(reinterpret_cast<const T*>(p.bias) + nc + 32, b1);
+          for (int q = 0; q < 4; ++q) st_shared_v4(stg_wr + q * 16, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+          __syncwarp();
+          const int col = nc + cchunk * 8;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { v0[i] += b0[i]; v1[i] += b1[i]; }
-          }
-          if (EPI == DDG_EPI_QKV_ROPE) {
-            if (nc < p.rope_cols) {
-              // the GEMM output is a 16-bit tensor in the reference; the rotary
-              // then runs in fp32 on those values (NeoX: x1 = d < 32, x2 = d >= 32)
-              round32<T>(v0);
-              round32<T>(v1);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float x1 = v0[i], x2 = v1[i];
-                v0[i] = x1 * cs[i] - x2 * sn[i];
-                v1[i] = x1 * sn[i] + x2 * cs[i];
-              }
-            }
-          } else if (EPI == DDG_EPI_BIAS_GELU) {
-            round32<T>(v0);
-            round32<T>(v1);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { v0[i] = gelu_tanh(v0[i]); v1[i] = gelu_tanh(v1[i]); }
-          } else if (EPI == DDG_EPI_STORE && p.stats != nullptr) {
-            // log-softmax partials of the stored (rounded) logits, so that the
-            // fused sampler never needs its own normaliser pass over the row
-            round32<T>(v0);
-            round32<T>(v1);
-            const bool plain = (nc + 64 <= p.N) && !(p.mask_col >= nc && p.mask_col < nc + 64);
-            float gm = -INFINITY;
-            if (plain) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) gm = fmaxf(gm, fmaxf(v0[i], v1[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (nc + i < p.N && nc + i != p.mask_col) gm = fmaxf(gm, v0[i]);
-                if (nc + 32 + i < p.N && nc + 32 + i != p.mask_col) gm = fmaxf(gm, v1[i]);
-              }
-            }
-            const float nm = fmaxf(st_m, gm);
-            if (nm > -INFINITY) {
-              const float nml = nm * kLog2e;
-              st_s *= ex2f_approx(st_m * kLog2e - nml);
-              float add = 0.f;
-              if (plain) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  add += ex2f_approx(fmaf(v0[i], kLog2e, -nml)) + ex2f_approx(fmaf(v1[i], kLog2e, -nml));
+          for (int i = 0; i < 4; ++i) {
+            const int row = 8 * i + crow;
+            const uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
+            if (mw + row < p.M) {
+              T* dst = oslab + (int64_t)row * p.ld_out + nc;
+              if (col + 8 <= p.N) {
+                *reinterpret_cast<uint4*>(dst) = y;
               } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  if (nc + i < p.N && nc + i != p.mask_col) add += ex2f_approx(fmaf(v0[i], kLog2e, -nml));
-                  if (nc + 32 + i < p.N && nc + 32 + i != p.mask_col)
-                    add += ex2f_approx(fmaf(v1[i], kLog2e, -nml));
-                }
+                const T* ye = reinterpret_cast<const T*>(&y);
+                for (int k = 0; k < 8; ++k)
+                  if (col + k < p.N) dst[k] = ye[k];
               }
-              st_s += add;
-              st_m = nm;
             }
           }
+        };
+        auto add_bias = [&](float2 (&v)[16], int c) {
+          if (!have_bias) return;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float* vv = h ? v1 : v0;
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              st_shared_v4(stg_wr + q * 16, H2<T>::pack(vv[8 * q], vv[8 * q + 1]),
-                           H2<T>::pack(vv[8 * q + 2], vv[8 * q + 3]), H2<T>::pack(vv[8 * q + 4], vv[8 * q + 5]),
-                           H2<T>::pack(vv[8 * q + 6], vv[8 * q + 7]));
-            __syncwarp();
-            const int col = nc + h * 32 + cchunk * 8;
+          for (int i = 0; i < 8; ++i) {
+            const uint4 b = ld_shared_v4(bias_s + (uint32_t)(c * 128 + 16 * i));
+            v[2 * i] = add2(v[2 * i], make_float2(__uint_as_float(b.x), __uint_as_float(b.y)));
+            v[2 * i + 1] = add2(v[2 * i + 1], make_float2(__uint_as_float(b.z), __uint_as_float(b.w)));
+          }
+        };
+        if (EPI == DDG_EPI_QKV_ROPE) {
+          // rotary pairs column d with d + 32 of a 64-wide head: two 32-column chunks at a time
+          float2 cs[16], sn[16];
+          {
+            const int pos = row_ok ? (m % p.seq_len) : 0;
+            const uint4* pc = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.rope_cos) + (int64_t)pos * 32);
+            const uint4* ps = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.rope_sin) + (int64_t)pos * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int row = 8 * i + crow;
-              const uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
-              if (mw + row < p.M) {
-                T* dst = oslab + (int64_t)row * p.ld_out + nc + h * 32;
-                if (col + 8 <= p.N) {
-                  *reinterpret_cast<uint4*>(dst) = y;
-                } else {
-                  const T* ye = reinterpret_cast<const T*>(&y);
-                  for (int k = 0; k < 8; ++k)
-                    if (col + k < p.N) dst[k] = ye[k];
-                }
-              }
+              const uint4 a = __ldg(pc + i), b = __ldg(ps + i);
+              cs[4 * i] = H2<T>::unpack(a.x); cs[4 * i + 1] = H2<T>::unpack(a.y);
+              cs[4 * i + 2] = H2<T>::unpack(a.z); cs[4 * i + 3] = H2<T>::unpack(a.w);
+              sn[4 * i] = H2<T>::unpack(b.x); sn[4 * i + 1] = H2<T>::unpack(b.y);
+              sn[4 * i + 2] = H2<T>::unpack(b.z); sn[4 * i + 3] = H2<T>::unpack(b.w);
             }
           }
+#pragma unroll 1
+          for (int g = 0; g < BN / 128; ++g) {
+            const int nc = n0 + g * 64;
+            uint32_t r0[32], r1[32];
+            tmem_ld32(taddr + (uint32_t)(g * 64), r0);
+            tmem_ld32(taddr + (uint32_t)(g * 64 + 32), r1);
+            tmem_ld_wait(r0);
+            tmem_ld_wait(r1);
+            if (nc >= p.N) continue;                 // warp-uniform
+            float2 v0[16], v1[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v0[i] = make_float2(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+              v1[i] = make_float2(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1]));
+            }
+            add_bias(v0, 2 * g);
+            add_bias(v1, 2 * g + 1);
+            uint32_t w0[16], w1[16];
+            if (nc < p.rope_cols) {
+              // the GEMM output is a 16-bit tensor in the reference; the rotary then runs
+              // in fp32 on those values (NeoX: x1 = d < 32, x2 = d >= 32)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 x1 = H2<T>::unpack(H2<T>::pack(v0[i].x, v0[i].y));
+                const float2 x2 = H2<T>::unpack(H2<T>::pack(v1[i].x, v1[i].y));
+                const float2 o0 = sub2(mul2(x1, cs[i]), mul2(x2, sn[i]));
+                const float2 o1 = fma2(x1, sn[i], mul2(x2, cs[i]));
+                w0[i] = H2<T>::pack(o0.x, o0.y);
+                w1[i] = H2<T>::pack(o1.x, o1.y);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                w0[i] = H2<T>::pack(v0[i].x, v0[i].y);
+                w1[i] = H2<T>::pack(v1[i].x, v1[i].y);
+              }
+            }
+            store_chunk(w0, nc);
+            store_chunk(w1, nc + 32);
+          }
+        } else {
+          // 32-column chunks; the TMEM load of the next chunk is in flight while this one is processed
+          const bool want_stats = EPI == DDG_EPI_STORE && p.stats != nullptr;
+          float st_m = -INFINITY, st_s = 0.f;      // running (max, sum 2^((v-max) log2e)) of this row chunk
+#pragma unroll 1
+          for (int c = 0; c < BN / 64; ++c) {
+            const int nc = n0 + c * 32;
+            if (nc >= p.N) break;                    // warp-uniform
+            uint32_t r[32];
+            tmem_ld32_sync(taddr + (uint32_t)(c * 32), r);
+            float2 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            add_bias(v, c);
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = H2<T>::pack(v[i].x, v[i].y);
+            if (EPI == DDG_EPI_BIAS_GELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 y = gelu_tanh2(H2<T>::unpack(w[i]));
+                w[i] = H2<T>::pack(y.x, y.y);
+              }
+            } else if (want_stats) {
+              // log-softmax partials of the stored (rounded) logits, so that the
+              // fused sampler never needs its own normaliser pass over the row
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = H2<T>::unpack(w[i]);
+              const bool plain = (nc + 32 <= p.N) && !(p.mask_col >= nc && p.mask_col < nc + 32);
+              if (!plain) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  if (nc + 2 * i >= p.N || nc + 2 * i == p.mask_col) v[i].x = -INFINITY;
+                  if (nc + 2 * i + 1 >= p.N || nc + 2 * i + 1 == p.mask_col) v[i].y = -INFINITY;
+                }
+              }
+              float gm = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) gm = fmaxf(gm, fmaxf(v[i].x, v[i].y));
+              const float nm = fmaxf(st_m, gm);
+              if (nm > -INFINITY) {
+                const float nml = nm * kLog2e;
+                st_s *= ex2f_approx(st_m * kLog2e - nml);
+                float2 acc = make_float2(0.f, 0.f);
+                const float2 l2 = make_float2(kLog2e, kLog2e), off = make_float2(-nml, -nml);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float2 t = fma2(v[i], l2, off);
+                  acc = add2(acc, make_float2(ex2f_approx(t.x), ex2f_approx(t.y)));
+                }
+                st_s += acc.x + acc.y;
+                st_m = nm;
+              }
+            }
+            store_chunk(w, nc);
+          }
+          if (want_stats && row_ok && n0 < p.N)
+            p.stats[(int64_t)(n0 / (BN / 2)) * p.stats_ld + m] = make_float2(st_m, st_s);
         }
-        if (EPI == DDG_EPI_STORE && p.stats != nullptr && row_ok && n0 < p.N)
-          p.stats[(int64_t)(n0 / (BN / 2)) * p.stats_ld + m] = make_float2(st_m, st_s);
       }
       // this warp has drained its part of the accumulator: one arrival per warp
       // on the leader's barrier (the leader's MMA thread reuses both CTAs' TMEM)
