@@ -41,9 +41,9 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_ROW_BYTES = 80;                  // 64 B payload + 16 B pad: conflict-free 128-bit stores
 constexpr int EPI_SLAB_BYTES = 32 * EPI_ROW_BYTES;  // one warp's 32 accumulator rows
-constexpr int EPI_BIAS_BYTES = NUM_EPI_WARPS * (BN / 2) * 4;   // fp32 bias of each epilogue warp's 128 columns
+constexpr int EPI_BIAS_BYTES = NUM_EPI_WARPS * (BN / 2) * 4;   // fp32 bias (and gate) of each epilogue warp's 128 columns
 constexpr int SMEM_BYTES =
-  STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * EPI_SLAB_BYTES + EPI_BIAS_BYTES;
+  STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * EPI_SLAB_BYTES + 2 * EPI_BIAS_BYTES;
 
 struct GemmParams {
   void* out;
@@ -390,6 +390,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint8_t* smem_epi = smem + STAGES * STAGE_BYTES + 256;
   uint8_t* smem_bias = smem_epi + NUM_EPI_WARPS * EPI_SLAB_BYTES;
+  uint8_t* smem_gate = smem_bias + EPI_BIAS_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -505,12 +506,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chalf * (BN / 2));
 
       if (EPI == DDG_EPI_GATE_RESIDUAL) {
-        // -------- x += round(gate * round(acc + bias)), fp32 residual stream
+        // -------- x += round(gate * round(acc + bias)), fp32 residual stream.
+        // Bias and (when this warp's 32 rows share one conditioning row, the usual case)
+        // gate of the warp's 128 columns are staged once per tile as fp32 in warp-private
+        // shared memory; the register phase is packed f32x2 arithmetic.
+        const bool have_bias = p.bias != nullptr;
+        const uint32_t bias_s = smem_u32(smem_bias) + (uint32_t)e * (BN / 2) * 4;
+        const uint32_t gate_s = smem_u32(smem_gate) + (uint32_t)e * (BN / 2) * 4;
         const T* gate_row = nullptr;
+        bool gate_uniform = false;
         if (p.gate) {
-          const int64_t mrow = row_ok ? (int64_t)m / p.rows_per_mod : 0;
-          gate_row = reinterpret_cast<const T*>(p.gate) + mrow * p.gate_stride;
+          const int rpm = p.rows_per_mod > 0x7fffffff ? 0x7fffffff : (int)p.rows_per_mod;
+          // rows of this warp that exist: [mw, last]; a warp past the end of A uses row 0's gate
+          const int first = mw < p.M ? mw : 0;
+          const int last = mw < p.M ? (mw + 31 < p.M ? mw + 31 : p.M - 1) : 0;
+          const int mod_first = first / rpm, mod_last = last / rpm;
+          gate_uniform = mod_first == mod_last;
+          const int mrow = gate_uniform ? mod_first : (row_ok ? m / rpm : 0);
+          gate_row = reinterpret_cast<const T*>(p.gate) + (int64_t)mrow * p.gate_stride;
         }
+        if (n0 < p.N) {
+          if (have_bias) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(p.bias) + n0) + lane);
+            const float2 b01 = H2<T>::unpack(raw.x), b23 = H2<T>::unpack(raw.y);
+            st_shared_v4(bias_s + 16 * lane, __float_as_uint(b01.x), __float_as_uint(b01.y),
+                         __float_as_uint(b23.x), __float_as_uint(b23.y));
+          }
+          if (gate_uniform) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(gate_row + n0) + lane);
+            const float2 g01 = H2<T>::unpack(raw.x), g23 = H2<T>::unpack(raw.y);
+            st_shared_v4(gate_s + 16 * lane, __float_as_uint(g01.x), __float_as_uint(g01.y),
+                         __float_as_uint(g23.x), __float_as_uint(g23.y));
+          }
+        }
+        __syncwarp();
         float* xslab = reinterpret_cast<float*>(p.out) + (int64_t)mw * p.ld_out + cchunk * 4;
         float4 xn[2][4];                         // x of the next 32 columns
         auto prefetch_x = [&](int nc) {
@@ -528,33 +557,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll 1
         for (int g = 0; g < BN / 64; ++g) {
           const int nc = n0 + g * 32;
+          if (nc >= p.N) break;                  // warp-uniform
           uint32_t r0[32];
-          tmem_ld32(taddr + (uint32_t)(g * 32), r0);
-          tmem_ld_wait(r0);
-          if (nc >= p.N) continue;               // warp-uniform
+          tmem_ld32_sync(taddr + (uint32_t)(g * 32), r0);
           float4 xc[2][4];
 #pragma unroll
           for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int i = 0; i < 4; ++i) xc[h][i] = xn[h][i];
           if (g + 1 < BN / 64 && nc + 32 < p.N) prefetch_x(nc + 32);
-          float v0[32];
+          float2 v[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v0[i] = __uint_as_float(r0[i]);
-          if (p.bias) {
-            float b0[32];
-            load32<T>(reinterpret_cast<const T*>(p.bias) + nc, b0);
+          for (int i = 0; i < 16; ++i) v[i] = make_float2(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+          if (have_bias) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v0[i] += b0[i];
+            for (int i = 0; i < 8; ++i) {
+              const uint4 b = ld_shared_v4(bias_s + (uint32_t)(g * 128 + 16 * i));
+              v[2 * i] = add2(v[2 * i], make_float2(__uint_as_float(b.x), __uint_as_float(b.y)));
+              v[2 * i + 1] = add2(v[2 * i + 1], make_float2(__uint_as_float(b.z), __uint_as_float(b.w)));
+            }
           }
-          round32<T>(v0);
-          if (gate_row) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = H2<T>::unpack(H2<T>::pack(v[i].x, v[i].y));
+          if (gate_uniform) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 b = ld_shared_v4(gate_s + (uint32_t)(g * 128 + 16 * i));
+              v[2 * i] = mul2(v[2 * i], make_float2(__uint_as_float(b.x), __uint_as_float(b.y)));
+              v[2 * i + 1] = mul2(v[2 * i + 1], make_float2(__uint_as_float(b.z), __uint_as_float(b.w)));
+            }
+          } else if (gate_row) {                 // rows of this warp straddle two conditioning rows
             float g0[32];
             load32<T>(gate_row + nc, g0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v0[i] *= g0[i];
-            round32<T>(v0);
+            for (int i = 0; i < 16; ++i) v[i] = mul2(v[i], make_float2(g0[2 * i], g0[2 * i + 1]));
           }
+          if (gate_row) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = H2<T>::unpack(H2<T>::pack(v[i].x, v[i].y));
+          }
+          float v0[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v0[2 * i] = v[i].x; v0[2 * i + 1] = v[i].y; }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             __syncwarp();
