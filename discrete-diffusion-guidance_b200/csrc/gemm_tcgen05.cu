@@ -835,6 +835,16 @@ int make_tma_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t k, int
   return DDG_OK;
 }
 
+}  // namespace
+
+// 16-bit row-major matrix as a 2-D tensor map {cols, rows} with a {64 columns, box_rows} box and
+// the 128-byte swizzle (16-byte chunk index XOR row % 8); shared with attention.cu
+int make_tma_rows64(void* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int dtype) {
+  return make_tma_2d(reinterpret_cast<CUtensorMap*>(map), base, rows, cols, ld, box_rows, dtype);
+}
+
+namespace {
+
 template <typename T, int EPI>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
   static bool attr_done[64] = {false};
