@@ -24,7 +24,7 @@ DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
 EXPORTS = (
   'ddg_abi_version', 'ddg_last_error', 'ddg_device_check', 'ddg_sm_count',
-  'ddg_sample_step', 'ddg_log_probs', 'ddg_sample_prior', 'ddg_step_advance',
+  'ddg_sample_step', 'ddg_low_confidence_select', 'ddg_log_probs', 'ddg_sample_prior', 'ddg_step_advance',
   'ddg_cond_embed', 'ddg_adaln', 'ddg_ln_modulate', 'ddg_gemm',
   'ddg_attention', 'ddg_cast', 'ddg_classifier_head', 'ddg_cbg_candidates')
 
@@ -45,7 +45,7 @@ class SampleStepArgs(C.Structure):
     ('select', C.c_int32), ('fast_math', C.c_int32), ('gamma', C.c_float),
     ('seed', C.c_uint64), ('step', C.c_int32), ('stats_chunks', C.c_int32),
     ('stats_a', C.c_void_p), ('stats_b', C.c_void_p), ('stats_ld', C.c_int64),
-    ('race_group', C.c_int32), ('reserved', C.c_int32)]
+    ('race_group', C.c_int32), ('compute_f64', C.c_int32)]
 
 
 class GemmArgs(C.Structure):
@@ -74,6 +74,8 @@ def _load():
   lib.ddg_last_error.restype = C.c_char_p
   i32, i64, vp, u32, u64 = C.c_int32, C.c_int64, C.c_void_p, C.c_uint32, C.c_uint64
   lib.ddg_sample_step.argtypes = [C.POINTER(SampleStepArgs), vp]
+  lib.ddg_low_confidence_select.argtypes = [vp, i64, i64, i32, C.c_float, vp, i64, i32, u64, vp,
+                                            i32, vp, vp, i32, vp, vp]
   lib.ddg_log_probs.argtypes = [vp, i64, i32, vp, i64, i32, i32, i32, i32,
                                 i32, vp, i64, vp]
   lib.ddg_sample_prior.argtypes = [vp, i64, i32, i32, i32, u64, vp]

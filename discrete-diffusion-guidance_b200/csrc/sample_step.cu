@@ -17,6 +17,7 @@
 
 namespace ddg {
 int try_sample_fused(const ddg_sample_step_args& a, cudaStream_t s);   // sample_fused.cu
+int launch_sample_f64(const ddg_sample_step_args& a, cudaStream_t s);  // sample_aux.cu
 namespace {
 
 constexpr float kNegInf = -1000000.0f;  // diffusion.py:141
@@ -565,6 +566,7 @@ extern "C" int ddg_sample_step(const ddg_sample_step_args* args, ddg_stream_t st
   if (a.q_out) DDG_REQUIRE(a.ld_q >= a.vocab, DDG_ERR_INVALID, "sample_step: ld_q < vocab");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool two = mode_two(mode);
+  if (a.compute_f64) return launch_sample_f64(a, s);
   {
     // single-pass production kernel when the GEMM supplied its softmax partials
     const int took = try_sample_fused(a, s);

@@ -123,11 +123,39 @@ class Diffusion:
 
   def _select_code(self):
     ev = self.config.get('eval') or {}
-    if ev.get('low_confidence_sampling', False):
-      raise NotImplementedError(
-        'eval.low_confidence_sampling is not implemented in the fused sampler')
     return (_lib.SELECT_ARGMAX if ev.get('argmax_sampling', False)
             else _lib.SELECT_RACE)
+
+  @property
+  def _low_confidence(self):
+    """eval.low_confidence_sampling (diffusion.py:1738-1746)."""
+    ev = self.config.get('eval') or {}
+    return bool(ev.get('low_confidence_sampling', False))
+
+  @property
+  def _use_float64(self):
+    """sampling.use_float64: honoured, like the reference, only by
+    `_ddpm_denoise` and the AR sampler (diffusion.py:1393-1394, 1134-1135)."""
+    return bool(self.config.sampling.get('use_float64', False))
+
+  def _q_buffer(self, B, L):
+    """(B, L, V) fp32 posterior: returned when `return_q_xs`, and the input of
+    the low-confidence draw."""
+    if self.return_q_xs or self._low_confidence:
+      return torch.empty(B, L, self.vocab_size, dtype=torch.float32,
+                         device=self.device)
+    return None
+
+  def _low_confidence_draw(self, q, xt, xs, noise, carry):
+    """Replaces `xs` by the draw restricted to the low-confidence set
+    (diffusion.py:1738-1755), then the absorbing carry-over."""
+    B, L, V = q.shape
+    thr = float(self.config.eval.get('low_confidence_threshold', 0.3))
+    check(lib.ddg_low_confidence_select(
+      ptr(q), V, B * L, V, thr, ptr(noise), V if noise is not None else 0,
+      self._select_code(), self.seed + 7919 * self._call_count, 0,
+      int(self._step_index), 0, ptr(xt) if carry else 0,
+      self.mask_index if carry else -1, ptr(xs), stream_ptr()))
 
   @property
   def _stats_mask_col(self):
@@ -191,7 +219,7 @@ class Diffusion:
                       mc_seq_stride=0, mc_step_stride=0, step_ptr=None, step=0,
                       guidance=_lib.GUIDE_NONE, gamma=1.0, q_out=None,
                       select=None, diffusion=None, logits_dtype=_lib.BF16,
-                      seed_ptr=None, stats=None):
+                      seed_ptr=None, stats=None, compute_f64=False):
     V = self.vocab_size
     # log-softmax partials of these logits, if our own vocab GEMM made them:
     # stats = (tensor (chunks, rows_total, 2), row offset of a, row offset of b)
@@ -222,7 +250,7 @@ class Diffusion:
       gamma=float(gamma), seed=self.seed + 7919 * self._call_count,
       step=int(step), stats_chunks=st_chunks, stats_a=st_a,
       stats_b=st_b if logits_b else 0, stats_ld=st_ld,
-      race_group=int(self.race_group))
+      race_group=int(self.race_group), compute_f64=1 if compute_f64 else 0)
     check(lib.ddg_sample_step(a, stream_ptr()))
 
   def _mc(self, mc):
@@ -232,8 +260,8 @@ class Diffusion:
     """Per-step API fast path: the whole step (forward + fused sampler) is one
     captured CUDA graph fed through static input buffers."""
     return (self.use_cuda_graph and cache is None and self.noise_fn is None
-            and not self.return_q_xs
-            and not self.config.sampling.get('use_float64', False))
+            and not self.return_q_xs and not self._low_confidence
+            and not self._use_float64)
 
   def _get_step_graph(self, kind, B, L, gamma):
     key = (kind, B, L, float(gamma), self.round_bf16, self.fast_math,
@@ -255,8 +283,6 @@ class Diffusion:
   def _ddpm_denoise(self, xt, time_conditioning, move_chance_t, move_chance_s,
                     cache=None):
     """diffusion.py:1378-1420 -> (xs, q_xs | None, cache)."""
-    if self.config.sampling.get('use_float64', False):
-      raise NotImplementedError('sampling.use_float64 is not implemented')
     B, L = xt.shape
     xt = xt.to(self.device, torch.int64).contiguous()
     if self._step_graph_ok(cache):
@@ -267,14 +293,18 @@ class Diffusion:
     logits = (cache['log_x_theta'] if cache is not None
               else self._logits(xt, time_conditioning, None))
     xs = torch.empty_like(xt)
-    q = (torch.empty(B, L, self.vocab_size, dtype=torch.float32, device=self.device)
-         if self.return_q_xs else None)
+    q = self._q_buffer(B, L)
     mct, mcs = self._mc(move_chance_t), self._mc(move_chance_s)
+    noise = self._step_noise(B, L)
     self._launch_sampler(
       logits_a=logits.data_ptr(), ld_a=logits.stride(1), xt=xt, xs=xs, mc_t=mct,
       mc_s=mcs, rows=B * L, seq_len=L, mc_seq_stride=1 if mct.numel() > 1 else 0,
-      noise=self._step_noise(B, L), q_out=q, step=self._step_index)
-    return xs, q, {'log_x_theta': logits}
+      noise=noise, q_out=q, step=self._step_index,
+      compute_f64=self._use_float64)
+    if self._low_confidence:
+      self._low_confidence_draw(q, xt, xs, noise,
+                                carry=self.diffusion == 'absorbing_state')
+    return xs, q if self.return_q_xs else None, {'log_x_theta': logits}
 
   def _cfg_denoise(self, cond, gamma, xt, time_conditioning, move_chance_t,
                    move_chance_s, cache=None):
@@ -317,12 +347,12 @@ class Diffusion:
       lc, lu = both[0], both[1]
       self._stats = {lc.data_ptr(): (stats, 0), lu.data_ptr(): (stats, B * L)}
     xs = torch.empty_like(xt)
-    q = (torch.empty(B, L, self.vocab_size, dtype=torch.float32, device=self.device)
-         if self.return_q_xs else None)
+    q = self._q_buffer(B, L)
     mct, mcs = self._mc(move_chance_t), self._mc(move_chance_s)
+    noise = self._step_noise(B, L)
     common = dict(xt=xt, xs=xs, mc_t=mct, mc_s=mcs, rows=B * L, seq_len=L,
                   mc_seq_stride=1 if mct.numel() > 1 else 0,
-                  noise=self._step_noise(B, L), q_out=q, step=self._step_index)
+                  noise=noise, q_out=q, step=self._step_index)
     if lc is None or lu is None:
       one = lu if lu is not None else lc
       self._launch_sampler(logits_a=one.data_ptr(), ld_a=one.stride(1), **common)
@@ -330,7 +360,11 @@ class Diffusion:
       self._launch_sampler(logits_a=lc.data_ptr(), ld_a=lc.stride(1),
                            logits_b=lu.data_ptr(), ld_b=lu.stride(1),
                            guidance=_lib.GUIDE_CFG, gamma=gamma, **common)
-    return xs, q, {'log_x_theta_uncond': lu, 'log_x_theta_cond': lc}
+    if self._low_confidence:
+      self._low_confidence_draw(q, xt, xs, noise,
+                                carry=self.diffusion == 'absorbing_state')
+    return xs, q if self.return_q_xs else None, {
+      'log_x_theta_uncond': lu, 'log_x_theta_cond': lc}
 
   def _classifier_term(self, classifier_model, xt, time_conditioning,
                        conditioning_class, use_approx):
@@ -370,15 +404,19 @@ class Diffusion:
       term = self._classifier_term(classifier_model, xt, time_conditioning,
                                    conditioning_class, use_approx)
     xs = torch.empty_like(xt)
-    q = (torch.empty(B, L, self.vocab_size, dtype=torch.float32, device=self.device)
-         if self.return_q_xs else None)
+    q = self._q_buffer(B, L)
     mct, mcs = self._mc(move_chance_t), self._mc(move_chance_s)
+    noise = self._step_noise(B, L)
     self._launch_sampler(
       logits_a=logits.data_ptr(), ld_a=logits.stride(1), clf=term.contiguous(),
       xt=xt, xs=xs, mc_t=mct, mc_s=mcs, rows=B * L, seq_len=L,
-      mc_seq_stride=1 if mct.numel() > 1 else 0, noise=self._step_noise(B, L),
+      mc_seq_stride=1 if mct.numel() > 1 else 0, noise=noise,
       q_out=q, guidance=_lib.GUIDE_CBG, gamma=gamma, step=self._step_index)
-    return xs, q, {'log_x_theta': logits, 'classifier_log_prob': term}
+    if self._low_confidence:
+      self._low_confidence_draw(q, xt, xs, noise,
+                                carry=self.diffusion == 'absorbing_state')
+    return xs, q if self.return_q_xs else None, {
+      'log_x_theta': logits, 'classifier_log_prob': term}
 
   # ---------------------------------------------------------------- loops
   @torch.no_grad()
@@ -395,7 +433,8 @@ class Diffusion:
     xt = self._sample_prior(B, L)
     sigma_t, mc_t, mc_s = self._step_scalars(steps, eps)
     if self.noise_fn is not None or self.return_q_xs or method == 'cbg' \
-        or not self.use_cuda_graph:
+        or not self.use_cuda_graph or self._low_confidence \
+        or (self._use_float64 and method is None):
       return self._eager_loop(xt, sigma_t, mc_t, mc_s, method, guidance,
                               classifier_model, cond)
     loop = self._get_loop(B, L, method, guidance)
@@ -464,6 +503,9 @@ class Diffusion:
     method = None if guidance is None else guidance.method
     if method not in (None, 'cfg'):
       raise NotImplementedError(f'Guidance method {method} not implemented.')
+    if self._low_confidence:
+      raise NotImplementedError(
+        'eval.low_confidence_sampling is not implemented for the AR sampler')
     B = self.config.sampling.batch_size
     L = self.config.model.length
     V, ld = self.vocab_size, self.backbone.vocab_ld
@@ -490,7 +532,8 @@ class Diffusion:
         ld_b=L * ld if two else 0, noise=noise, xt=y, xs=y, rows=B, seq_len=1,
         guidance=_lib.GUIDE_CFG if two else _lib.GUIDE_NONE,
         gamma=guidance.gamma if two else 1.0, diffusion=_lib.AR,
-        select=_lib.SELECT_GUMBEL, step=i)
+        select=_lib.SELECT_GUMBEL, step=i,
+        compute_f64=self._use_float64 and method is None)
       x[:, i + 1] = y
     return x
 

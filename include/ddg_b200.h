@@ -130,10 +130,28 @@ typedef struct ddg_sample_step_args {
    *      independent exponentials), 8x less noise work; needs the stats_*
    *      partials, bf16 logits and fast_math.  Other values: DDG_ERR_INVALID. */
   int32_t race_group;
-  int32_t reserved;
+  /* 1: sampling.use_float64 (diffusion.py:1393-1394, 1110-1111, 1134-1135): the
+   * log-probs keep the forward's precision, everything after them runs in
+   * double.  Like the reference only without guidance (absorbing / uniform /
+   * AR); with guidance -> DDG_ERR_UNSUPPORTED ("not implemented").            */
+  int32_t compute_f64;
 } ddg_sample_step_args;
 
 DDG_API int ddg_sample_step(const ddg_sample_step_args* args, ddg_stream_t stream);
+
+/* eval.low_confidence_sampling (diffusion.py:1738-1755): from the posterior
+ * `probs` (rows, ld) fp32 -- what _sample_categorical receives, e.g. the q_out
+ * of ddg_sample_step -- keep the entries whose cumulative mass in ascending
+ * probability order is <= threshold (ties in index order, i.e. a stable sort),
+ * zero the rest, then draw by the exponential race (noise: injected U or NULL
+ * for the Philox stream of ddg_sample_step) or take the arg-max.  xt != NULL
+ * and carry_mask_index >= 0: rows with xt != carry_mask_index are copied
+ * through afterwards (absorbing carry-over, diffusion.py:1414-1418).          */
+DDG_API int ddg_low_confidence_select(const float* probs, int64_t ld, int64_t rows, int32_t vocab,
+                              float threshold, const float* noise, int64_t ld_noise,
+                              int32_t select, uint64_t seed, const uint64_t* seed_ptr,
+                              int32_t step, const int32_t* step_ptr, const int64_t* xt,
+                              int32_t carry_mask_index, int64_t* xs, ddg_stream_t stream);
 
 /* Log-probs the way Diffusion.forward returns them (diffusion.py:356-365,
  * 321-337): optional mask-logit, subs carry-over rows, log_softmax; fp32 out.
@@ -209,7 +227,8 @@ typedef struct ddg_gemm_args {
   const void* a;        /* (M, K) activations, 16-bit `dtype`, row-major     */
   const void* w;        /* (N, K) nn.Linear weight, 16-bit `dtype`           */
   void* out;            /* (M, ld_out) 16-bit, or the fp32 residual stream   */
-  const void* bias;     /* (N,) `dtype` or NULL                              */
+  const void* bias;     /* (N,) `dtype` or NULL; readable up to the next
+                           multiple of 256 columns                           */
   const void* gate;     /* GATE_RESIDUAL: adaLN gate rows (`dtype`) or NULL  */
   const void* rope_cos; /* QKV_ROPE: (L, head_dim/2) `dtype`                 */
   const void* rope_sin;

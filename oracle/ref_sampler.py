@@ -116,8 +116,16 @@ def posterior_absorbing(x, mc_t, mc_s, mask_index):
   return q / mc_t
 
 
-def sample_categorical(probs, U, argmax_sampling=False):
-  """`_sample_categorical` (diffusion.py:1748-1755) with injected U."""
+def sample_categorical(probs, U, argmax_sampling=False, low_confidence=None):
+  """`_sample_categorical` (diffusion.py:1738-1755) with injected U.
+  `low_confidence` = eval.low_confidence_threshold when
+  eval.low_confidence_sampling is on (:1739-1746), else None."""
+  if low_confidence is not None:
+    sorted_probs, sorted_idx = probs.sort(dim=-1, stable=True)
+    mask_sorted = sorted_probs.cumsum(dim=-1) <= low_confidence
+    mask = torch.zeros_like(mask_sorted)
+    mask.scatter_(dim=-1, index=sorted_idx, src=mask_sorted)
+    probs = probs.masked_fill(~mask, 0.0)
   if argmax_sampling:
     return probs.argmax(dim=-1)
   gumbel_norm = (1e-10 - (U + 1e-10).log()).to(probs.dtype)
@@ -135,32 +143,35 @@ def _carry_over(xs, q_xs, xt, mask_index):
 # per-step updates, from log-probs
 # --------------------------------------------------------------------------
 def ddpm_update(lp, xt, mc_t, mc_s, U, *, diffusion, mask_index,
-                lp_dtype=None, argmax_sampling=False, use_float64=False):
+                lp_dtype=None, argmax_sampling=False, use_float64=False,
+                low_confidence=None):
   """`_ddpm_denoise` after the forward (diffusion.py:1393-1420)."""
   if use_float64:
     lp = lp.to(torch.float64)
-  x = _exp(lp, lp_dtype)
+  x = lp.exp() if use_float64 else _exp(lp, lp_dtype)   # float64: no bf16 rounding of exp
   if diffusion == 'absorbing_state':
     q = posterior_absorbing(x, mc_t, mc_s, mask_index)
   elif diffusion == 'uniform':
     q = posterior_uniform(x, xt, 1 - mc_s, 1 - mc_t)
   else:
     raise NotImplementedError(diffusion)
-  xs = sample_categorical(q, U, argmax_sampling)
+  xs = sample_categorical(q, U, argmax_sampling, low_confidence)
   if diffusion == 'absorbing_state':
     xs, q = _carry_over(xs, q, xt, mask_index)
   return xs, q
 
 
 def cfg_update(lp_cond, lp_uncond, gamma, xt, mc_t, mc_s, U, *, diffusion,
-               mask_index, lp_dtype=None, argmax_sampling=False):
+               mask_index, lp_dtype=None, argmax_sampling=False,
+               low_confidence=None):
   """`_cfg_denoise` after the forwards (diffusion.py:1456-1509).  Pass
   lp_cond=None for gamma==0 and lp_uncond=None for gamma==1."""
   if lp_cond is None or lp_uncond is None:
     lp = lp_uncond if lp_uncond is not None else lp_cond
     return ddpm_update(lp, xt, mc_t, mc_s, U, diffusion=diffusion,
                        mask_index=mask_index, lp_dtype=lp_dtype,
-                       argmax_sampling=argmax_sampling)
+                       argmax_sampling=argmax_sampling,
+                       low_confidence=low_confidence)
   if diffusion == 'absorbing_state':
     if lp_dtype is None:
       mix = gamma * lp_cond + (1 - gamma) * lp_uncond
@@ -179,14 +190,15 @@ def cfg_update(lp_cond, lp_uncond, gamma, xt, mc_t, mc_s, U, *, diffusion,
     q = (gamma * lq_c + (1 - gamma) * lq_u).softmax(dim=-1)
   else:
     raise NotImplementedError(diffusion)
-  xs = sample_categorical(q, U, argmax_sampling)
+  xs = sample_categorical(q, U, argmax_sampling, low_confidence)
   if diffusion == 'absorbing_state':
     xs, q = _carry_over(xs, q, xt, mask_index)
   return xs, q
 
 
 def cbg_update(lp, clf_log_prob, gamma, xt, mc_t, mc_s, U, *, diffusion,
-               mask_index, lp_dtype=None, argmax_sampling=False):
+               mask_index, lp_dtype=None, argmax_sampling=False,
+               low_confidence=None):
   """`_cbg_denoise` after the forward and classifier term
   (diffusion.py:1587-1621).  clf_log_prob (B,L,V) fp32."""
   if diffusion == 'absorbing_state':
@@ -202,7 +214,7 @@ def cbg_update(lp, clf_log_prob, gamma, xt, mc_t, mc_s, U, *, diffusion,
   else:
     raise NotImplementedError(diffusion)
   p = g.softmax(dim=-1)
-  xs = sample_categorical(p, U, argmax_sampling)
+  xs = sample_categorical(p, U, argmax_sampling, low_confidence)
   if diffusion == 'absorbing_state':
     xs = torch.where(xt != mask_index, xt, xs)
   return xs, p
@@ -265,7 +277,8 @@ class OracleSampler:
                diffusion, n_heads, time_conditioning, subs_masking=False,
                T=0, noise_type='loglinear', num_classes=None,
                gpu_rounding=False, argmax_sampling=False,
-               clf_sd=None, clf_n_heads=None):
+               clf_sd=None, clf_n_heads=None, use_float64=False,
+               low_confidence=None):
     self.sd = sd
     self.V = vocab_size
     self.mask_index = mask_index
@@ -278,6 +291,8 @@ class OracleSampler:
     self.noise_type = noise_type
     self.num_classes = num_classes
     self.argmax_sampling = argmax_sampling
+    self.use_float64 = use_float64          # honoured by _ddpm_denoise only
+    self.low_confidence = low_confidence    # threshold or None
     self.rounding = (ref_dit.Rounding.gpu_denoiser() if gpu_rounding
                      else ref_dit.Rounding.none())
     self.clf_rounding = (ref_dit.Rounding.gpu_classifier() if gpu_rounding
@@ -308,10 +323,12 @@ class OracleSampler:
            gamma=1.0, condition=0, use_approx=False):
     """One reverse step -> (xs, q_xs, log-probs dict)."""
     kw = dict(diffusion=self.diffusion, mask_index=self.mask_index,
-              lp_dtype=self.lp_dtype, argmax_sampling=self.argmax_sampling)
+              lp_dtype=self.lp_dtype, argmax_sampling=self.argmax_sampling,
+              low_confidence=self.low_confidence)
     if guidance is None:
       lp = self.forward(xt, sigma_t)
-      xs, q = ddpm_update(lp, xt, mc_t, mc_s, U, **kw)
+      xs, q = ddpm_update(lp, xt, mc_t, mc_s, U, use_float64=self.use_float64,
+                          **kw)
       return xs, q, {'log_x_theta': lp}
     if guidance == 'cfg':
       lp_c = lp_u = None

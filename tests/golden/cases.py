@@ -29,6 +29,9 @@ class Case:
   num_classes: int = 2
   use_approx: bool = False
   argmax_sampling: bool = False
+  use_float64: bool = False
+  low_confidence: bool = False          # eval.low_confidence_sampling
+  low_confidence_threshold: float = 0.3
   batch: int = 2
   length: int = 32
   steps: int = 4
@@ -60,6 +63,17 @@ CASES = [
   Case('bert_mdlm_null', vocab='bert', parameterization='subs',
        diffusion='absorbing_state', time_conditioning=False, length=16,
        steps=3),
+  Case('udlm_f64', use_float64=True, steps=3),
+  Case('mdlm_f64', parameterization='subs', diffusion='absorbing_state',
+       time_conditioning=False, use_float64=True, steps=4),
+  Case('udlm_lowconf', low_confidence=True, steps=3),
+  Case('mdlm_lowconf', parameterization='subs', diffusion='absorbing_state',
+       time_conditioning=False, low_confidence=True,
+       low_confidence_threshold=0.6, steps=4),
+  Case('udlm_cfg_lowconf', guidance='cfg', gamma=2.0, low_confidence=True,
+       low_confidence_threshold=0.5, steps=2),
+  Case('bert_udlm_lowconf', vocab='bert', low_confidence=True, length=16,
+       steps=2),
   Case('ar_null', parameterization='ar', diffusion='absorbing_state',
        time_conditioning=False, length=16, steps=0),
 ]
@@ -109,14 +123,15 @@ def config_dict(case: Case) -> dict:
               num_classes=case.num_classes),
     sampling=dict(use_cache=False, steps=max(case.steps, 1),
                   batch_size=case.batch, num_sample_batches=1,
-                  use_float64=False),
+                  use_float64=case.use_float64),
     training=dict(guidance=(dict(cond_dropout=0.1)
                             if case.guidance == 'cfg' else None),
                   antithetic_sampling=True, importance_sampling=False,
                   sampling_eps=1e-3, change_of_variables=False,
                   label_smoothing=0.0),
     eval=dict(checkpoint_path='', disable_ema=True,
-              low_confidence_sampling=False, low_confidence_threshold=0.3,
+              low_confidence_sampling=case.low_confidence,
+              low_confidence_threshold=case.low_confidence_threshold,
               argmax_sampling=case.argmax_sampling),
     optim=dict(lr=3e-4, weight_decay=0, beta1=0.9, beta2=0.999, eps=1e-8),
     weights_averaging=dict(type='none'),

@@ -42,6 +42,8 @@ def make_oracle(case, gpu_rounding=False):
     n_heads=case.n_heads, time_conditioning=case.time_conditioning,
     subs_masking=case.subs_masking, T=case.T, num_classes=case.num_classes,
     gpu_rounding=gpu_rounding, argmax_sampling=case.argmax_sampling,
+    use_float64=case.use_float64,
+    low_confidence=case.low_confidence_threshold if case.low_confidence else None,
     clf_sd=csd, clf_n_heads=case.n_heads)
 
 
@@ -103,7 +105,7 @@ def sampler_kernel(*, logits_a, xt, mc_t, mc_s, vocab, seq_len, diffusion,
                    gamma=1.0, subs=False, mask_logit=False, mask_index=0,
                    round_bf16=False, select='race', fast_math=False, seed=0,
                    step=0, want_q=False, stats_a=0, stats_b=0, stats_ld=0,
-                   stats_chunks=0, race_group=0):
+                   stats_chunks=0, race_group=0, compute_f64=False):
   """Direct call of ddg_sample_step through the C ABI on torch CUDA tensors.
   logits (rows, ld) f32 or bf16; xt (rows,) int64; mc_* scalars or (n_seq,)."""
   from ddg_b200 import _lib
@@ -134,10 +136,40 @@ def sampler_kernel(*, logits_a, xt, mc_t, mc_s, vocab, seq_len, diffusion,
     mask_index=mask_index, round_bf16=int(round_bf16), select=scode,
     fast_math=int(fast_math), gamma=float(gamma), seed=int(seed),
     step=int(step), stats_chunks=stats_chunks, stats_a=stats_a, stats_b=stats_b,
-    stats_ld=stats_ld, race_group=race_group)
+    stats_ld=stats_ld, race_group=race_group, compute_f64=int(compute_f64))
   _lib.check(_lib.lib.ddg_sample_step(a, _lib.stream_ptr()))
   torch.cuda.synchronize()
   return xs, q
+
+
+def low_confidence_kernel(q, threshold, *, noise=None, select='race', xt=None,
+                          carry_mask_index=-1, seed=0, step=0):
+  """Direct call of ddg_low_confidence_select on a (rows, V) fp32 posterior."""
+  from ddg_b200 import _lib
+  dev = q.device
+  rows, V = q.shape
+  q = q.contiguous()
+  xs = torch.empty(rows, dtype=torch.int64, device=dev)
+  if noise is not None:
+    noise = noise.reshape(rows, V).to(dev, torch.float32).contiguous()
+  if xt is not None:
+    xt = xt.reshape(-1).to(dev, torch.int64).contiguous()
+  scode = {'race': _lib.SELECT_RACE, 'argmax': _lib.SELECT_ARGMAX}[select]
+  _lib.check(_lib.lib.ddg_low_confidence_select(
+    q.data_ptr(), V, rows, V, float(threshold), _lib.ptr(noise), V if noise is not None else 0,
+    scode, int(seed), 0, int(step), 0, _lib.ptr(xt), int(carry_mask_index), xs.data_ptr(),
+    _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  return xs
+
+
+def low_confidence_mask(q, threshold):
+  """The reference's kept set (diffusion.py:1739-1746) for a (..., V) posterior."""
+  sp, si = q.sort(dim=-1, stable=True)
+  ms = sp.cumsum(dim=-1) <= threshold
+  mask = torch.zeros_like(ms)
+  mask.scatter_(dim=-1, index=si, src=ms)
+  return mask
 
 
 def race_scores(q, U):

@@ -45,7 +45,8 @@ def test_step_api_ids_follow_own_logits(name):
   torch.testing.assert_close(m3, mcs, rtol=1e-6, atol=1e-7)
   xt = cases.prior_ids(case)
   kw = dict(diffusion=case.diffusion, mask_index=tok.mask_token_id,
-            lp_dtype=torch.bfloat16, argmax_sampling=case.argmax_sampling)
+            lp_dtype=torch.bfloat16, argmax_sampling=case.argmax_sampling,
+            low_confidence=case.low_confidence_threshold if case.low_confidence else None)
   param = case.parameterization
   for i in range(case.steps):
     U = cases.step_noise(case, i)
@@ -61,7 +62,8 @@ def test_step_api_ids_follow_own_logits(name):
         lp_dtype=torch.bfloat16)
     if case.guidance is None:
       xs, q, cache = model._ddpm_denoise(xt.to(DEV), sigma_t, mc_t.to(DEV), mc_s.to(DEV))
-      xs_ref, q_ref = ref_sampler.ddpm_update(lps(cache['log_x_theta']), xt, mc_t, mc_s, U, **kw)
+      xs_ref, q_ref = ref_sampler.ddpm_update(lps(cache['log_x_theta']), xt, mc_t, mc_s, U,
+                                              use_float64=case.use_float64, **kw)
     elif case.guidance == 'cfg':
       cond = torch.full((B,), case.condition, dtype=torch.long, device=DEV)
       xs, q, cache = model._cfg_denoise(cond, case.gamma, xt.to(DEV), sigma_t,
@@ -81,7 +83,14 @@ def test_step_api_ids_follow_own_logits(name):
     assert xs.dtype == torch.int64 and tuple(xs.shape) == (B, L)
     helpers.assert_close_frac(q, q_ref, rtol=3e-4, atol=1e-6, loose_frac=2e-3,
                               loose_rtol=2e-2)
-    helpers.assert_ids_match(xs, xs_ref, q_ref,
+    q_sel = q_ref
+    if case.low_confidence:   # the draw only sees the kept set (diffusion.py:1739-1746)
+      q_sel = q_ref.masked_fill(
+        ~helpers.low_confidence_mask(q_ref, case.low_confidence_threshold), 0.0)
+      if case.diffusion == 'absorbing_state':
+        keep = xt != tok.mask_token_id
+        q_sel[keep] = torch.nn.functional.one_hot(xt[keep], V).to(q_sel.dtype)
+    helpers.assert_ids_match(xs, xs_ref, q_sel,
                              None if case.argmax_sampling else U,
                              f'{name} step {i}', tol=2e-2)
     xt = xs_ref

@@ -46,7 +46,8 @@ def test_kernel_replays_reference_goldens(name):
               subs=case.parameterization == 'subs',
               mask_logit=case.parameterization == 'subs' or case.subs_masking,
               mask_index=tok.mask_token_id, round_bf16=False, fast_math=False,
-              select='argmax' if case.argmax_sampling else 'race', want_q=True)
+              select='argmax' if case.argmax_sampling else 'race', want_q=True,
+              compute_f64=case.use_float64)
     if case.guidance == 'cfg':
       cond = torch.full((B,), case.condition, dtype=torch.long)
       la = lb = None
@@ -81,6 +82,17 @@ def test_kernel_replays_reference_goldens(name):
     # the 30522-vocab fixtures store q_xs as a summary only: score near-ties
     # with the (just verified) kernel posterior there
     q_ref = q.cpu() if big else torch.from_numpy(gold[f's{i}_q_xs'])
+    if case.low_confidence:
+      # eval.low_confidence_sampling: the draw is redone on the kept set
+      absorbing = case.diffusion == 'absorbing_state'
+      xs = helpers.low_confidence_kernel(
+        q.reshape(B * L, V), case.low_confidence_threshold, noise=U,
+        select='argmax' if case.argmax_sampling else 'race', xt=xt if absorbing else None,
+        carry_mask_index=tok.mask_token_id if absorbing else -1)
+      q_ref = q_ref.masked_fill(~helpers.low_confidence_mask(q_ref, case.low_confidence_threshold), 0.0)
+      if absorbing:   # carried-over rows: compare through their one-hot posterior
+        keep = xt != tok.mask_token_id
+        q_ref[keep] = torch.nn.functional.one_hot(xt[keep], V).float()
     near += helpers.assert_ids_match(
       xs.view(B, L), gold_xs, q_ref, None if case.argmax_sampling else U,
       f'{name} step {i}')
@@ -526,3 +538,38 @@ def test_group_race_full_size_properties():
   # with dt = 1/1000 most tokens stay (UDLM posterior mass at z): sanity of the z term
   assert (a1 == xt).float().mean().item() > 0.9
   assert (a1 != a3).any()
+
+
+@pytest.mark.parametrize('diffusion', ['uniform', 'absorbing_state'])
+@pytest.mark.parametrize('round_bf16', [True, False])
+def test_float64_kernel_vs_oracle(diffusion, round_bf16):
+  """sampling.use_float64 (diffusion.py:1393-1394): log-probs at the forward's
+  precision (bf16 when round_bf16), everything after them in double."""
+  B, L, V, ld = 2, 6, 1000, 1000
+  rows = B * L
+  dev = torch.device('cuda')
+  subs = diffusion == 'absorbing_state'
+  mask = 103
+  la = _rand_logits(rows, V, ld, torch.bfloat16, 5)
+  g = torch.Generator().manual_seed(6)
+  U = torch.rand(B, L, V, generator=g)
+  xt = (torch.full((B, L), mask, dtype=torch.long) if subs
+        else torch.randint(0, V, (B, L), generator=g))
+  if subs:
+    xt[1, :2] = torch.tensor([3, 8])
+  mc_t, mc_s = torch.tensor([0.61, 0.37]), torch.tensor([0.59, 0.33])
+  lp_dtype = torch.bfloat16 if round_bf16 else None
+  lp = ref_sampler.log_probs_from_logits(
+    la[:, :V].float().view(B, L, V), xt, parameterization='subs' if subs else 'd3pm',
+    mask_index=mask, lp_dtype=lp_dtype)
+  xs_ref, q_ref = ref_sampler.ddpm_update(
+    lp, xt, mc_t[:, None, None], mc_s[:, None, None], U, diffusion=diffusion, mask_index=mask,
+    lp_dtype=lp_dtype, use_float64=True)
+  assert q_ref.dtype == torch.float64
+  xs, q = helpers.sampler_kernel(
+    logits_a=la.to(dev), noise=U, xt=xt, mc_t=mc_t, mc_s=mc_s, vocab=V, seq_len=L,
+    diffusion=diffusion, subs=subs, mask_logit=subs, mask_index=mask, round_bf16=round_bf16,
+    want_q=True, compute_f64=True)
+  helpers.assert_close_frac(q.view(B, L, V), q_ref, rtol=3e-4, atol=1e-7,
+                            loose_frac=1e-3 if round_bf16 else 0.0, loose_rtol=2e-2)
+  helpers.assert_ids_match(xs.view(B, L), xs_ref, q_ref.float(), U, f'f64 {diffusion}', tol=2e-5)
