@@ -172,6 +172,18 @@ def build_model(batch, device, seed):
   return model, cfg
 
 
+def ncu_traffic(batch):
+  """DRAM bytes per launch of each kernel family from the committed ncu
+  capture (profiles/r01_traffic.json); None when the capture was taken at
+  another batch size."""
+  try:
+    with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+      t = json.load(f)
+    return t['bytes_per_launch'] if t.get('batch_per_gpu') == batch else None
+  except Exception:
+    return None
+
+
 def flops_per_step(cfg, batch):
   h, nb = cfg.model.hidden_size, cfg.model.n_blocks
   rows = 2 * batch * L
@@ -330,6 +342,13 @@ def run_gpu_arm(args, rank, world, local_rank):
   samp_gbs = samp_bytes / (samp_ms * 1e-3) / 1e9
   gemm_tf = gemm_total_flops / (gemm_ms * 1e-3) / 1e12
   n_launch = sum(d['launches'] for d in kb.values())
+  traffic = ncu_traffic(B)
+  gemm_traffic = samp_traffic = None
+  if traffic:
+    # per launch, averaged over the 49 GEMM launches of a step like `achieved`
+    gemm_traffic = sum(traffic[k] * kb[k]['launches'] for k in kb if k.startswith('gemm_')) / sum(
+      kb[k]['launches'] for k in kb if k.startswith('gemm_'))
+    samp_traffic = traffic['sample_step']
   line = {
     'metric': METRIC, 'value': value, 'unit': 'sequences/s', 'n_gpus': world,
     'steps': K, 'warmup': W, 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -343,13 +362,15 @@ def run_gpu_arm(args, rank, world, local_rank):
     'roofline': {
       'kernel': 'gemm_kernel (tcgen05; all DiT linears of one step)', 'bound': 'tensor',
       'achieved': round(gemm_tf, 1), 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
-      'frac': round(gemm_tf / pk['tf_sustained'], 4), 'traffic': None,
+      'frac': round(gemm_tf / pk['tf_sustained'], 4), 'traffic': gemm_traffic,
+      'traffic_note': 'ncu dram bytes per launch, mean over the 49 GEMM launches of a step (profiles/r01_traffic.json)',
+      'flops_per_launch': gemm_total_flops / 49.0, 'ms_per_launch': gemm_ms / 49.0,
       'peak_source': f"{pk['src']} sustained bf16 (kernel timed inside a long step)",
       'share_of_step': round(gemm_ms / step_kernel_ms, 4)},
     'roofline_sampler': {
-      'kernel': 'sample_step_kernel (fused sampler)', 'bound': 'hbm',
+      'kernel': 'sample_group_kernel (fused sampler, hierarchical race)', 'bound': 'hbm',
       'achieved': round(samp_gbs, 1), 'peak': pk['hbm'], 'unit': 'GB/s',
-      'frac': round(samp_gbs / pk['hbm'], 4), 'traffic': None,
+      'frac': round(samp_gbs / pk['hbm'], 4), 'traffic': samp_traffic,
       'algorithmic_bytes': samp_bytes, 'peak_source': pk['src'],
       'share_of_step': round(samp_ms / step_kernel_ms, 4)},
     'step_roofline': {
