@@ -18,7 +18,7 @@ F32, F16, BF16 = 0, 1, 2
 ABSORBING, UNIFORM, AR = 0, 1, 2
 GUIDE_NONE, GUIDE_CFG, GUIDE_CBG = 0, 1, 2
 SELECT_RACE, SELECT_ARGMAX, SELECT_GUMBEL = 0, 1, 2
-EPI_STORE, EPI_QKV_ROPE, EPI_BIAS_GELU, EPI_GATE_RESIDUAL = 0, 1, 2, 3
+EPI_STORE, EPI_QKV_ROPE, EPI_BIAS_GELU, EPI_GATE_RESIDUAL, EPI_ACCUM_F32 = 0, 1, 2, 3, 4
 
 DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
@@ -26,7 +26,10 @@ EXPORTS = (
   'ddg_abi_version', 'ddg_last_error', 'ddg_device_check', 'ddg_sm_count',
   'ddg_sample_step', 'ddg_low_confidence_select', 'ddg_log_probs', 'ddg_sample_prior', 'ddg_step_advance',
   'ddg_cond_embed', 'ddg_adaln', 'ddg_ln_modulate', 'ddg_gemm',
-  'ddg_attention', 'ddg_cast', 'ddg_classifier_head', 'ddg_cbg_candidates')
+  'ddg_attention', 'ddg_cast', 'ddg_classifier_head', 'ddg_cbg_candidates',
+  'ddg_classifier_head_backward', 'ddg_gate_mul', 'ddg_gelu_backward',
+  'ddg_ln_modulate_backward', 'ddg_attention_backward', 'ddg_split16',
+  'ddg_cbg_first_order')
 
 
 class SampleStepArgs(C.Structure):
@@ -58,7 +61,7 @@ class GemmArgs(C.Structure):
     ('K', C.c_int32), ('dtype', C.c_int32), ('epilogue', C.c_int32),
     ('seq_len', C.c_int32), ('head_dim', C.c_int32), ('rope_cols', C.c_int32),
     ('stats', C.c_void_p), ('stats_ld', C.c_int64),
-    ('stats_mask_col', C.c_int32), ('reserved', C.c_int32)]
+    ('stats_mask_col', C.c_int32), ('accumulate', C.c_int32)]
 
 
 def _load():
@@ -92,6 +95,13 @@ def _load():
   lib.ddg_classifier_head.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp,
                                       vp]
   lib.ddg_cbg_candidates.argtypes = [vp, i32, i32, i64, i64, vp, vp]
+  lib.ddg_classifier_head_backward.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp]
+  lib.ddg_gate_mul.argtypes = [vp, vp, i64, i64, i64, i32, i32, vp, vp]
+  lib.ddg_gelu_backward.argtypes = [vp, vp, vp, i64, i32, vp]
+  lib.ddg_ln_modulate_backward.argtypes = [vp, vp, i64, i32, vp, vp, i64, i64, i32, vp, vp]
+  lib.ddg_attention_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+  lib.ddg_split16.argtypes = [vp, vp, vp, i64, i32, vp]
+  lib.ddg_cbg_first_order.argtypes = [vp, i64, vp, vp, i32, i32, i32, i32, i64, vp, i64, vp]
   return lib
 
 

@@ -57,6 +57,7 @@ struct GemmParams {
   float2* stats;        // optional per-(128-column chunk, row) softmax partials
   int64_t stats_ld;
   int mask_col;         // column excluded from the partials (-1: none)
+  int accumulate;       // ACCUM_F32: add to the existing output
 };
 
 // ------------------------------------------------------------------ PTX
@@ -505,17 +506,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const uint32_t taddr =
         tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chalf * (BN / 2));
 
-      if (EPI == DDG_EPI_GATE_RESIDUAL) {
+      if (EPI == DDG_EPI_GATE_RESIDUAL || EPI == DDG_EPI_ACCUM_F32) {
+        // ACCUM_F32: out = (accumulate ? out : 0) + acc, no rounding (fp32 dgrad outputs).
+        constexpr bool PLAIN = EPI == DDG_EPI_ACCUM_F32;
         // -------- x += round(gate * round(acc + bias)), fp32 residual stream.
         // Bias and (when this warp's 32 rows share one conditioning row, the usual case)
         // gate of the warp's 128 columns are staged once per tile as fp32 in warp-private
         // shared memory; the register phase is packed f32x2 arithmetic.
-        const bool have_bias = p.bias != nullptr;
+        const bool have_bias = !PLAIN && p.bias != nullptr;
         const uint32_t bias_s = smem_u32(smem_bias) + (uint32_t)e * (BN / 2) * 4;
         const uint32_t gate_s = smem_u32(smem_gate) + (uint32_t)e * (BN / 2) * 4;
         const T* gate_row = nullptr;
         bool gate_uniform = false;
-        if (p.gate) {
+        if (!PLAIN && p.gate) {
           const int rpm = p.rows_per_mod > 0x7fffffff ? 0x7fffffff : (int)p.rows_per_mod;
           // rows of this warp that exist: [mw, last]; a warp past the end of A uses row 0's gate
           const int first = mw < p.M ? mw : 0;
@@ -548,7 +551,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int row = 8 * i + crow;
-              const bool ok = (mw + row < p.M) && (nc + h * 16 + cchunk * 4 < p.N);
+              const bool ok = (mw + row < p.M) && (nc + h * 16 + cchunk * 4 < p.N) && (!PLAIN || p.accumulate);
               xn[h][i] = ok ? *reinterpret_cast<const float4*>(xslab + (int64_t)row * p.ld_out + nc + h * 16)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -577,8 +580,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               v[2 * i + 1] = add2(v[2 * i + 1], make_float2(__uint_as_float(b.z), __uint_as_float(b.w)));
             }
           }
+          if (!PLAIN) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = H2<T>::unpack(H2<T>::pack(v[i].x, v[i].y));
+            for (int i = 0; i < 16; ++i) v[i] = H2<T>::unpack(H2<T>::pack(v[i].x, v[i].y));
+          }
           if (gate_uniform) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -868,6 +873,7 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     case DDG_EPI_QKV_ROPE: return launch_gemm<T, DDG_EPI_QKV_ROPE>(ta, tb, p, s);
     case DDG_EPI_BIAS_GELU: return launch_gemm<T, DDG_EPI_BIAS_GELU>(ta, tb, p, s);
     case DDG_EPI_GATE_RESIDUAL: return launch_gemm<T, DDG_EPI_GATE_RESIDUAL>(ta, tb, p, s);
+    case DDG_EPI_ACCUM_F32: return launch_gemm<T, DDG_EPI_ACCUM_F32>(ta, tb, p, s);
   }
   set_error("gemm: bad epilogue %d", epi);
   return DDG_ERR_INVALID;
@@ -894,6 +900,9 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
   if (a.epilogue == DDG_EPI_GATE_RESIDUAL)
     DDG_REQUIRE(a.ld_out % 4 == 0 && a.N % 4 == 0, DDG_ERR_INVALID,
                 "gemm: fp32 residual N and ld_out must be multiples of 4");
+  else if (a.epilogue == DDG_EPI_ACCUM_F32)   // columns up to the next multiple of 4 may be written
+    DDG_REQUIRE(a.ld_out % 4 == 0 && a.ld_out >= (a.N + 3) / 4 * 4, DDG_ERR_INVALID,
+                "gemm: fp32 output ld_out must be a multiple of 4 and cover N rounded up to 4");
   else
     DDG_REQUIRE(a.ld_out % 8 == 0, DDG_ERR_INVALID, "gemm: 16-bit ld_out must be a multiple of 8");
   if (a.bias) DDG_REQUIRE(reinterpret_cast<uintptr_t>(a.bias) % 16 == 0, DDG_ERR_INVALID, "gemm: bias alignment");
@@ -915,6 +924,7 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
   p.ld_out = a.ld_out; p.gate_stride = a.gate_stride; p.rows_per_mod = a.rows_per_mod;
   p.M = a.M; p.N = a.N; p.K = a.K; p.seq_len = a.seq_len; p.rope_cols = a.rope_cols;
   p.stats = reinterpret_cast<float2*>(a.stats); p.stats_ld = a.stats_ld; p.mask_col = a.stats_mask_col;
+  p.accumulate = a.accumulate;
   if (a.stats) {
     DDG_REQUIRE(a.epilogue == DDG_EPI_STORE && a.stats_ld >= a.M &&
                 reinterpret_cast<uintptr_t>(a.stats) % 8 == 0, DDG_ERR_INVALID,

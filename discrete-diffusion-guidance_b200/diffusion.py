@@ -236,7 +236,7 @@ class Diffusion:
       logits_a=logits_a, logits_b=logits_b or 0, clf=ptr(clf), noise=ptr(noise),
       xt=ptr(xt), mc_t=ptr(mc_t), mc_s=ptr(mc_s), step_ptr=ptr(step_ptr),
       seed_ptr=ptr(seed_ptr), xs=ptr(xs), q_out=ptr(q_out), rows=rows, ld_a=ld_a, ld_b=ld_b,
-      ld_clf=V if clf is not None else 0,
+      ld_clf=clf.stride(-2) if clf is not None else 0,
       ld_noise=(noise.stride(-2) if noise is not None else 0),
       ld_q=V if q_out is not None else 0, seq_len=seq_len, vocab=V,
       mc_seq_stride=mc_seq_stride, mc_step_stride=mc_step_stride,
@@ -370,9 +370,10 @@ class Diffusion:
                        conditioning_class, use_approx):
     """(B, L, V) fp32 classifier log-prob term of D-CBG."""
     if use_approx:
-      raise NotImplementedError(
-        'guidance.use_approx (first-order D-CBG) needs the classifier '
-        'backward; not implemented yet')
+      # first order (diffusion.py:1532-1548): one classifier forward + backward
+      term, _ = classifier_model.first_order_term(xt, time_conditioning,
+                                                  conditioning_class)
+      return term
     # exact: every single-token edit of xt (diffusion.py:1549-1585), generated
     # chunk by chunk on the device and never materialised as a whole.
     B, L = xt.shape
@@ -408,7 +409,8 @@ class Diffusion:
     mct, mcs = self._mc(move_chance_t), self._mc(move_chance_s)
     noise = self._step_noise(B, L)
     self._launch_sampler(
-      logits_a=logits.data_ptr(), ld_a=logits.stride(1), clf=term.contiguous(),
+      logits_a=logits.data_ptr(), ld_a=logits.stride(1),
+      clf=term if term.stride(-1) == 1 else term.contiguous(),
       xt=xt, xs=xs, mc_t=mct, mc_s=mcs, rows=B * L, seq_len=L,
       mc_seq_stride=1 if mct.numel() > 1 else 0, noise=noise,
       q_out=q, guidance=_lib.GUIDE_CBG, gamma=gamma, step=self._step_index)

@@ -137,6 +137,20 @@ class DIT:
       self.ada_b = torch.cat(ada_b, 0).to(self.device, torch.float32).contiguous()
     if self.classifier:
       self.cls_w, self.cls_b = f32('output_layer.weight'), f32('output_layer.bias')
+      # first-order D-CBG: input gradients are GEMMs on the transposed weights
+      # (dX = dY @ W), and the last one, G @ E^T, runs as three 16-bit GEMMs on
+      # (hi, lo) halves of the fp32 operands
+      def tcast(k):
+        return self._cast(get(k).t().contiguous(), bd)
+      self.w_qkv_t = [tcast(f'blocks.{i}.attn_qkv.weight') for i in range(self.n_blocks)]
+      self.w_out_t = [tcast(f'blocks.{i}.attn_out.weight') for i in range(self.n_blocks)]
+      self.w_fc1_t = [tcast(f'blocks.{i}.mlp.0.weight') for i in range(self.n_blocks)]
+      self.w_fc2_t = [tcast(f'blocks.{i}.mlp.2.weight') for i in range(self.n_blocks)]
+      self.emb_hi = torch.empty(V * h, dtype=bd, device=self.device)
+      self.emb_lo = torch.empty(V * h, dtype=bd, device=self.device)
+      check(lib.ddg_split16(ptr(self.embedding), ptr(self.emb_hi), ptr(self.emb_lo),
+                            V * h, _lib.DTYPE_CODE[bd], stream_ptr()))
+      torch.cuda.current_stream().synchronize()
     else:
       self.ln_f = f32('output_layer.norm_final.weight')
       self.w_vocab = self._cast(get('output_layer.linear.weight'), self.head_dtype)
@@ -199,7 +213,8 @@ class DIT:
           logits_out: typing.Optional[torch.Tensor] = None,
           ids_period: typing.Optional[int] = None,
           stats_out: typing.Optional[torch.Tensor] = None,
-          stats_mask_col: int = -1):
+          stats_mask_col: int = -1,
+          save_for_backward: typing.Optional[list] = None):
     """Launches one forward over `n_seqs` sequences of length L.  `ids` holds
     `ids_period` (default n_seqs*L) int64 token ids, reused cyclically.
     Denoiser: writes logits (rows, vocab_ld) bf16 into `logits_out`.
@@ -237,7 +252,8 @@ class DIT:
       raise ValueError('Conditioning variable provided, but Model was not '
                        'initialized with condition embedding layer.')
     cos, sin = self._rope_tables(L)
-    seg_rows = M if self.seg_seqs is None else max(1, self.seg_seqs) * L
+    seg_rows = M if (self.seg_seqs is None or save_for_backward is not None) \
+        else max(1, self.seg_seqs) * L
     for r0 in range(0, M, seg_rows):
       n = min(seg_rows, M - r0)
       if r0 % rpm == 0:
@@ -250,14 +266,14 @@ class DIT:
         raise ValueError('micro-batch straddles the id period')
       self._run_segment(ws, ids, r0, n, L, period, mod0, rpm_arg, mod_stride,
                         cos, sin, logits_out, bcode, hcode, s, stats_out,
-                        stats_mask_col)
+                        stats_mask_col, save_for_backward)
     if self.classifier:
       return ws['x'][:M]
     return logits_out
 
   def _run_segment(self, ws, ids, r0, n, L, period, mod0, rpm, mod_stride, cos,
                    sin, logits_out, bcode, hcode, s, stats_out=None,
-                   stats_mask_col=-1):
+                   stats_mask_col=-1, saved=None):
     h, nb = self.hidden, self.n_blocks
     x = ptr(ws['x']) + r0 * h * 4
     a16, qkv, h4 = ptr(ws['a16']), ptr(ws['qkv']), ptr(ws['h4'])
@@ -283,10 +299,15 @@ class DIT:
         mod_stride, rpm, bcode, a16, s))
       gemm(a16, h, ptr(self.w_qkv[i]), h, qkv, 3 * h, 3 * h, h,
            _lib.EPI_QKV_ROPE, bcode)
+      if saved is not None:   # block input (set by the gather above for i == 0) and rotated QKV
+        saved.append([ws['x'][:n].clone(), None,
+                      ws['qkv'][:n].view(self.block_dtype).clone()])
       check(lib.ddg_attention(qkv, a16, n // L, L, self.n_heads, self.head_dim,
                               1 if self.causal else 0, bcode, s))
       gemm(a16, h, ptr(self.w_out[i]), h, x, h, h, h, _lib.EPI_GATE_RESIDUAL,
            bcode, gate=mb + 2 * h * 2 if ada else 0, gate_stride=mod_stride)
+      if saved is not None:
+        saved[-1][1] = ws['x'][:n].clone()
       check(lib.ddg_ln_modulate(
         x, n, h, 0, period, 0, ptr(self.ln2[i]), mb + 3 * h * 2 if ada else 0,
         mb + 4 * h * 2 if ada else 0, mod_stride, rpm, bcode, a16, s))
@@ -352,3 +373,93 @@ class DIT:
                                   1 if round_bf16 else 0, ptr(out),
                                   stream_ptr()))
     return out
+
+  def first_order_term(self, indices, sigma, target, round_bf16=True):
+    """First-order D-CBG classifier term (diffusion.py:1532-1548): one forward
+    and the backward of log p(target | x) w.r.t. the one-hot input, then
+    `grad - grad[xt] + log p(target | xt)` -> (n, L, V) fp32.  The forward is
+    the one of `classify` (a one-hot input times the embedding matrix is the
+    embedding gather, models/dit.py:518-522) with each block's residual-stream
+    inputs and rotated QKV kept for the backward."""
+    assert self.classifier
+    n, L = indices.shape
+    h, nb, V, M = self.hidden, self.n_blocks, self.vocab_size, n * L
+    dev, s = self.device, stream_ptr()
+    bcode = _lib.DTYPE_CODE[self.block_dtype]
+    ids = indices.to(dev, torch.int64).contiguous()
+    mod = ModSpec(n_mod=n, seqs_per_mod=1)
+    if not self.causal:
+      mod.sigma = sigma.to(dev, torch.float32).reshape(-1).contiguous()
+      mod.sigma_row_stride = 1 if mod.sigma.numel() > 1 else 0
+      if mod.sigma.numel() == 1:
+        mod.n_mod, mod.seqs_per_mod = 1, n
+    saved = []
+    x = self.run(ids, n, L, mod, save_for_backward=saved)
+    ws = self._ws
+    rpm = mod.seqs_per_mod * L
+    mod_stride = nb * 6 * h
+    ada = self.use_adaln
+    cos, sin = self._rope_tables(L)
+    lp = torch.empty(n, self.num_classes, dtype=torch.float32, device=dev)
+    g = torch.empty(M, h, dtype=torch.float32, device=dev)
+    check(lib.ddg_classifier_head_backward(
+      ptr(x), n, L, h, ptr(self.cls_w), ptr(self.cls_b), self.num_classes,
+      int(target), 1 if round_bf16 else 0, ptr(lp), ptr(g), s))
+    g16 = torch.empty(M, h, dtype=self.block_dtype, device=dev)
+    g_a = torch.empty(M, h, dtype=self.block_dtype, device=dev)
+    g_h = torch.empty(M, 4 * h, dtype=self.block_dtype, device=dev)
+    g_qkv = torch.empty(M, 3 * h, dtype=self.block_dtype, device=dev)
+    a16, pre = ptr(ws['a16']), ptr(ws['h4'])
+
+    def gemm(a, lda, w, ldw, out, ld_out, N, K, epi=_lib.EPI_STORE, bias=0,
+             accumulate=0):
+      ga = _lib.GemmArgs(
+        a=a, w=w, out=out, bias=bias, gate=0, rope_cos=ptr(cos), rope_sin=ptr(sin),
+        lda=lda, ldw=ldw, ld_out=ld_out, gate_stride=0, rows_per_mod=rpm, M=M, N=N,
+        K=K, dtype=bcode, epilogue=epi, seq_len=L, head_dim=self.head_dim,
+        rope_cols=0, stats=0, stats_ld=0, stats_mask_col=-1, accumulate=accumulate)
+      check(lib.ddg_gemm(ga, s))
+
+    for i in reversed(range(nb)):
+      mb = ptr(ws['mod_blk']) + i * 6 * h * 2
+      x_in, x_mid, qkv_i = saved[i]
+      # ---- MLP branch: x_out = x_mid + gate_mlp * fc2(gelu(fc1(mod(LN(x_mid)))))
+      check(lib.ddg_gate_mul(ptr(g), mb + 5 * h * 2 if ada else 0, mod_stride, rpm,
+                             M, h, bcode, ptr(g16), s))
+      gemm(ptr(g16), h, ptr(self.w_fc2_t[i]), h, ptr(g_h), 4 * h, 4 * h, h)
+      check(lib.ddg_ln_modulate(
+        ptr(x_mid), M, h, 0, M, 0, ptr(self.ln2[i]), mb + 3 * h * 2 if ada else 0,
+        mb + 4 * h * 2 if ada else 0, mod_stride, rpm, bcode, a16, s))
+      gemm(a16, h, ptr(self.w_fc1[i]), h, pre, 4 * h, 4 * h, h,
+           bias=ptr(self.b_fc1[i]))
+      check(lib.ddg_gelu_backward(ptr(g_h), pre, ptr(g_h), M * 4 * h, bcode, s))
+      gemm(ptr(g_h), 4 * h, ptr(self.w_fc1_t[i]), 4 * h, ptr(g_a), h, h, 4 * h)
+      check(lib.ddg_ln_modulate_backward(
+        ptr(x_mid), ptr(g_a), M, h, ptr(self.ln2[i]), mb + 4 * h * 2 if ada else 0,
+        mod_stride, rpm, bcode, ptr(g), s))
+      # ---- attention branch: x_mid = x_in + gate_msa * out(attn(rope(qkv(mod(LN(x_in))))))
+      check(lib.ddg_gate_mul(ptr(g), mb + 2 * h * 2 if ada else 0, mod_stride, rpm,
+                             M, h, bcode, ptr(g16), s))
+      gemm(ptr(g16), h, ptr(self.w_out_t[i]), h, ptr(g_a), h, h, h)
+      check(lib.ddg_attention_backward(
+        ptr(qkv_i), ptr(g_a), ptr(cos), ptr(sin), n, L, self.n_heads,
+        self.head_dim, 1 if self.causal else 0, bcode, ptr(g_qkv), s))
+      gemm(ptr(g_qkv), 3 * h, ptr(self.w_qkv_t[i]), 3 * h, ptr(g_a), h, h, 3 * h)
+      check(lib.ddg_ln_modulate_backward(
+        ptr(x_in), ptr(g_a), M, h, ptr(self.ln1[i]), mb + 1 * h * 2 if ada else 0,
+        mod_stride, rpm, bcode, ptr(g), s))
+    # ---- d / d one-hot = G @ E^T in (almost) fp32: hi*hi + lo*hi + hi*lo
+    g_lo = g16
+    g_hi = g_a
+    check(lib.ddg_split16(ptr(g), ptr(g_hi), ptr(g_lo), M * h, bcode, s))
+    ldv = _pad_to(V, 4)
+    term = torch.empty(M, ldv, dtype=torch.float32, device=dev)
+    gemm(ptr(g_hi), h, ptr(self.emb_hi), h, ptr(term), ldv, V, h, epi=_lib.EPI_ACCUM_F32)
+    gemm(ptr(g_lo), h, ptr(self.emb_hi), h, ptr(term), ldv, V, h, epi=_lib.EPI_ACCUM_F32,
+         accumulate=1)
+    gemm(ptr(g_hi), h, ptr(self.emb_lo), h, ptr(term), ldv, V, h, epi=_lib.EPI_ACCUM_F32,
+         accumulate=1)
+    check(lib.ddg_cbg_first_order(
+      ptr(term), ldv, ptr(ids), ptr(lp), self.num_classes, int(target), L, V, M,
+      ptr(term), ldv, s))
+    return term.view(n, L, ldv)[:, :, :V], lp

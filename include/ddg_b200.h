@@ -220,7 +220,9 @@ enum ddg_epilogue {
   DDG_EPI_STORE = 0,        /* out = round(acc [+ bias])            16-bit   */
   DDG_EPI_QKV_ROPE = 1,     /* round, then NeoX rotary on q,k heads 16-bit   */
   DDG_EPI_BIAS_GELU = 2,    /* round(gelu_tanh(round(acc + bias)))  16-bit   */
-  DDG_EPI_GATE_RESIDUAL = 3 /* x += round(gate * round(acc [+ bias])) fp32   */
+  DDG_EPI_GATE_RESIDUAL = 3, /* x += round(gate * round(acc [+ bias])) fp32  */
+  DDG_EPI_ACCUM_F32 = 4     /* out = (accumulate ? out : 0) + acc, fp32, no
+                               rounding (classifier dgrad outputs)            */
 };
 
 typedef struct ddg_gemm_args {
@@ -248,7 +250,7 @@ typedef struct ddg_gemm_args {
   void* stats;
   int64_t stats_ld;
   int32_t stats_mask_col;
-  int32_t reserved;
+  int32_t accumulate;   /* ACCUM_F32: 1 = add to the existing output         */
 } ddg_gemm_args;
 
 /* tcgen05 / TMEM / TMA GEMM: out = epilogue(a @ w^T). */
@@ -273,6 +275,46 @@ DDG_API int ddg_classifier_head(const float* x, int32_t n, int32_t seq_len,
                         int32_t hidden, const float* w, const float* b,
                         int32_t n_classes, int32_t round_bf16,
                         float* log_probs, ddg_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * First-order D-CBG (diffusion.py:1532-1548): one classifier forward and the
+ * backward of log p(y | x) w.r.t. the one-hot input.  Only activation
+ * gradients are propagated.  The linears' input gradients are ddg_gemm calls on
+ * transposed weights (16-bit STORE, or ACCUM_F32 for the final G @ E^T); the
+ * entry points below are the other pieces of models/dit.py:221-325, 470-556
+ * run backwards.
+ * ---------------------------------------------------------------------- */
+/* head: log_probs (n, classes) as ddg_classifier_head, and
+ * g_x[(n*L), hidden] = d log_probs[:, target] / d x  (mean-pool + Linear).   */
+DDG_API int ddg_classifier_head_backward(const float* x, int32_t n, int32_t seq_len, int32_t hidden,
+                                 const float* w, const float* b, int32_t n_classes, int32_t target,
+                                 int32_t round_bf16, float* log_probs, float* g_x, ddg_stream_t stream);
+/* out = dtype(g * gate[row / rows_per_mod]) (gate == NULL: plain cast): the
+ * gradient entering a gated branch (models/dit.py:312-316, 324-325).          */
+DDG_API int ddg_gate_mul(const float* g, const void* gate, int64_t gate_stride, int64_t rows_per_mod,
+                 int64_t rows, int32_t hidden, int32_t dtype, void* out, ddg_stream_t stream);
+/* out = g_h * gelu_tanh'(pre)  (models/dit.py:243).                          */
+DDG_API int ddg_gelu_backward(const void* g_h, const void* pre, void* out, int64_t n, int32_t dtype,
+                      ddg_stream_t stream);
+/* g_resid += (d [LN(x) * w * one_plus_scale + shift] / d x)^T g_a
+ * (models/dit.py:131-139, 47-50); statistics are recomputed from x.          */
+DDG_API int ddg_ln_modulate_backward(const float* x, const void* g_a, int64_t rows, int32_t hidden,
+                             const float* ln_weight, const void* one_plus_scale, int64_t mod_stride,
+                             int64_t rows_per_mod, int32_t dtype, float* g_resid, ddg_stream_t stream);
+/* qkv: the forward's (rotated) QKV tensor; g_out: gradient of the attention
+ * output; g_qkv: gradient of the QKV GEMM output (rotary undone)
+ * (models/dit.py:284-307).                                                    */
+DDG_API int ddg_attention_backward(const void* qkv, const void* g_out, const void* rope_cos, const void* rope_sin,
+                           int32_t batch, int32_t seq_len, int32_t n_heads, int32_t head_dim,
+                           int32_t causal, int32_t dtype, void* g_qkv, ddg_stream_t stream);
+/* src = hi + lo with hi = dtype(src), lo = dtype(src - hi): three 16-bit
+ * GEMMs (hi*hi + lo*hi + hi*lo) then reproduce an fp32 matmul to ~2^-16.      */
+DDG_API int ddg_split16(const float* src, void* hi, void* lo, int64_t n, int32_t dtype, ddg_stream_t stream);
+/* term[row, v] = grad[row, v] - grad[row, xt[row]] + log_probs[row / L, target]
+ * (diffusion.py:1541-1548).                                                   */
+DDG_API int ddg_cbg_first_order(const float* grad, int64_t ld_grad, const int64_t* xt, const float* log_probs,
+                        int32_t n_classes, int32_t target, int32_t seq_len, int32_t vocab, int64_t rows,
+                        float* term, int64_t ld_term, ddg_stream_t stream);
 
 /* Exact D-CBG candidate batch (diffusion.py:1551-1585): for candidate c of
  * chunk [c0, c0+n): seq b = c / (L*V), l = (c / V) % L, v = c % V;

@@ -54,6 +54,11 @@ CASES = [
   Case('udlm_cbg', guidance='cbg', gamma=1.5, length=16, steps=2),
   Case('mdlm_cbg', parameterization='subs', diffusion='absorbing_state',
        time_conditioning=False, guidance='cbg', gamma=1.5, length=16, steps=3),
+  Case('udlm_cbg_approx', guidance='cbg', gamma=1.5, use_approx=True, length=16,
+       steps=2),
+  Case('mdlm_cbg_approx', parameterization='subs', diffusion='absorbing_state',
+       time_conditioning=False, guidance='cbg', gamma=1.5, use_approx=True,
+       length=16, steps=3),
   Case('udlm_T1000', T=1000, steps=3),
   Case('d3pm_abs_submask', diffusion='absorbing_state', subs_masking=True,
        steps=4),

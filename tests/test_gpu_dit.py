@@ -278,6 +278,69 @@ def test_classifier_matches_oracle():
   assert torch.allclose(got.exp().sum(-1).cpu(), torch.ones(n), atol=2e-2)
 
 
+@pytest.mark.parametrize('name', ['udlm_cbg_approx', 'mdlm_cbg_approx'])
+def test_first_order_cbg_term_matches_oracle(name):
+  """First-order D-CBG term (diffusion.py:1532-1548): CUDA classifier forward +
+  hand-written backward against autograd through the CPU oracle (fp32 and with
+  the bf16 forward roundings).  Tolerance: the block GEMMs / gradients are
+  bf16 like the reference's autocast backward."""
+  from oracle import ref_sampler
+  case = cases.CASE_BY_NAME[name]
+  m, cfg, tok, sd, csd = _model(case, classifier=True)
+  V, L = tok.vocab_size, case.length
+  g = torch.Generator().manual_seed(9)
+  n = 5
+  xt = torch.randint(0, V, (n, L), generator=g)
+  sigma = torch.rand(n, generator=g) * 3 if case.time_conditioning else torch.zeros(n)
+  term, lp = m.first_order_term(xt.to(DEV), sigma.to(DEV), case.condition, round_bf16=True)
+  torch.cuda.synchronize()
+  term, lp = term.float().cpu(), lp.cpu()
+  for rounding, tol in ((ref_dit.Rounding.none(), 0.08), (ref_dit.Rounding.gpu_classifier(), 0.08)):
+    def clf(x, s):
+      return ref_dit.classifier_log_probs(csd, x, s, n_heads=case.n_heads,
+                                          time_conditioning=case.time_conditioning,
+                                          rounding=rounding)
+    ref = ref_sampler.cbg_classifier_term_approx(clf, xt, sigma, V, case.condition)
+    lp_ref = clf(xt, sigma)
+    torch.testing.assert_close(lp, lp_ref, rtol=3e-2, atol=3e-2)
+    # the informative part is the ratio grad_v - grad_xt: compare it at its own scale
+    ratio, ratio_ref = term - lp[:, case.condition][:, None, None], ref - lp_ref[:, case.condition][:, None, None]
+    scale = ratio_ref.abs().max().item()
+    err = (ratio - ratio_ref).abs().max().item()
+    assert err <= tol * scale + 1e-4, (err, scale)
+    # term at xt itself is log p(y | xt) exactly (ratio 0)
+    at = term.gather(-1, xt[..., None])[..., 0]
+    torch.testing.assert_close(at, lp[:, case.condition][:, None].expand(n, L), rtol=0, atol=1e-6)
+
+
+def test_gemm_accum_f32_split_matches_fp32_matmul():
+  """ACCUM_F32 epilogue + (hi, lo) operand split: three 16-bit GEMMs reproduce
+  an fp32 matmul to ~1e-5 relative (used for G @ E^T of first-order D-CBG)."""
+  M, N, K = 300, 1002, 256
+  g = torch.Generator().manual_seed(4)
+  a = torch.randn(M, K, generator=g).to(DEV)
+  w = torch.randn(N, K, generator=g).to(DEV)
+  parts = {}
+  for nm, t in (('a', a), ('w', w)):
+    hi = torch.empty_like(t, dtype=torch.bfloat16)
+    lo = torch.empty_like(t, dtype=torch.bfloat16)
+    _lib.check(_lib.lib.ddg_split16(t.data_ptr(), hi.data_ptr(), lo.data_ptr(), t.numel(), _lib.BF16,
+                                    _lib.stream_ptr()))
+    parts[nm] = (hi, lo)
+  ld = (N + 3) // 4 * 4
+  out = torch.full((M, ld), 7.0, dtype=torch.float32, device=DEV)
+  for k, (x, y) in enumerate(((parts['a'][0], parts['w'][0]), (parts['a'][1], parts['w'][0]),
+                              (parts['a'][0], parts['w'][1]))):
+    ga = _lib.GemmArgs(a=x.data_ptr(), w=y.data_ptr(), out=out.data_ptr(), lda=K, ldw=K, ld_out=ld,
+                       M=M, N=N, K=K, dtype=_lib.BF16, epilogue=_lib.EPI_ACCUM_F32, seq_len=1,
+                       head_dim=64, rows_per_mod=1 << 40, stats_mask_col=-1, accumulate=1 if k else 0)
+    _lib.check(_lib.lib.ddg_gemm(ga, _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  ref = (a.double() @ w.double().t()).float()
+  err = (out[:, :N] - ref).abs().max().item()
+  assert err <= 2e-4 * ref.abs().max().item(), err
+
+
 def test_cbg_candidates():
   L, V, B = 5, 7, 3
   xt = torch.randint(0, V, (B, L))

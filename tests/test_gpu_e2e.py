@@ -75,7 +75,7 @@ def test_step_api_ids_follow_own_logits(name):
     else:
       xs, q, cache = model._cbg_denoise(
         case.condition, case.gamma, model.classifier_model, xt.to(DEV), sigma_t,
-        mc_t.to(DEV), mc_s.to(DEV), use_approx=False)
+        mc_t.to(DEV), mc_s.to(DEV), use_approx=case.use_approx)
       xs_ref, q_ref = ref_sampler.cbg_update(
         lps(cache['log_x_theta']), cache['classifier_log_prob'].cpu(), case.gamma,
         xt, mc_t, mc_s, U, **kw)
@@ -123,8 +123,9 @@ def test_graph_loop_equals_eager_loop(name):
   assert int(a.min()) >= 0 and int(a.max()) < tok.vocab_size
 
 
-def test_cbg_sample_runs_and_guides():
-  case = cases.CASE_BY_NAME['udlm_cbg']
+@pytest.mark.parametrize('name', ['udlm_cbg', 'udlm_cbg_approx'])
+def test_cbg_sample_runs_and_guides(name):
+  case = cases.CASE_BY_NAME[name]
   model, cfg, tok = _diffusion(case, **{'sampling.steps': 3})
   out = model.sample()
   torch.cuda.synchronize()

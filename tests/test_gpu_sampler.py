@@ -67,8 +67,9 @@ def test_kernel_replays_reference_goldens(name):
           guidance='cfg', gamma=case.gamma, **kw)
     elif case.guidance == 'cbg':
       la = _oracle_logits(case, oracle, xt, sigma_t, None)
-      term = ref_sampler.cbg_classifier_term_exact(
-        oracle.clf_log_probs, xt, sigma_t, V, case.condition)
+      term_fn = (ref_sampler.cbg_classifier_term_approx if case.use_approx
+                 else ref_sampler.cbg_classifier_term_exact)
+      term = term_fn(oracle.clf_log_probs, xt, sigma_t, V, case.condition)
       xs, q = helpers.sampler_kernel(
         logits_a=la.reshape(B * L, V).to(dev).contiguous(), clf=term,
         guidance='cbg', gamma=case.gamma, **kw)
