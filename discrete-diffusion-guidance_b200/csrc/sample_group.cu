@@ -45,7 +45,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
-constexpr int kCtasPerSm = 5;
+constexpr int kCtasPerSm = 6;
 constexpr int kLut = 2048;          // bf16 magnitudes 0x3B00 .. 0x42FF: |lp| in [2^-9, 128)
 constexpr int kLutBase = 0x3B00;
 constexpr int kMaxChunks = 256;     // softmax partials staged in smem (V <= 32768); else read from global
@@ -283,7 +283,8 @@ __device__ __forceinline__ uint32_t group_noise_word(int G, int64_t row, int ste
   return w == 0 ? r.x : w == 1 ? r.y : w == 2 ? r.z : r.w;
 }
 
-// One pass over the full groups of a row: thread t takes G = t + 128 k.  Two
+// One pass over the full groups of a row (va / vb: the row's vectors, CTA-uniform):
+// thread t takes G = t + 128 k.  Two
 // vector buffers alternate (even / odd k), each reloaded for k + 2 as soon as it
 // has been consumed, so every load has two group iterations to land.
 template <int MODE, bool ROUND, bool LIN>
@@ -304,9 +305,9 @@ __device__ __forceinline__ void row_pass(const RowConst& c, const uint4* va, con
       if (G >= n_full) break;
       const float lsum = group_hot<MODE, ROUND, LIN>(c, ra[s & 1], rb[s & 1], A, B, neg_base2);
       {                                               // reload this buffer for k + 2 (clamped: always in bounds)
-        const int gn = min(G + 2 * kThreads, n_full - 1) - tid;
-        ra[s & 1] = ldg_stream(va + gn);
-        if (MODE == G_UNI_CFG) rb[s & 1] = ldg_stream(vb + gn);
+        const uint32_t off = (uint32_t)min(G + 2 * kThreads, n_full - 1) << 4;
+        ra[s & 1] = ldg_stream(reinterpret_cast<const char*>(va) + off);
+        if (MODE == G_UNI_CFG) rb[s & 1] = ldg_stream(reinterpret_cast<const char*>(vb) + off);
       }
       const float sc = lsum + neg_log2_E(u01_from_bits(rw[s]));
       if (sc > best && G != special_grp) { best = sc; bgrp = G; }
@@ -334,8 +335,9 @@ sample_group_kernel(const ddg_sample_step_args a) {
   const int n_full = V >> 3;                 // groups made of 8 valid columns
   const int n_groups = (V + 7) >> 3;
   const bool stage = a.stats_chunks <= kMaxChunks;
-  uint32_t neg_base2;                        // opaque to constant propagation: stays in one register
-  asm volatile("mov.u32 %0, %1;" : "=r"(neg_base2) : "n"(kNegBase2));
+  // a value the compiler cannot fold (race_group == 8 on this path), so the constant
+  // lives in one register instead of being re-materialised in front of every VIADDMNMX
+  const uint32_t neg_base2 = kNegBase2 ^ (uint32_t)(a.race_group ^ 8);
   float tab_mct = -1.f, tab_mcs = -1.f;     // schedule scalars the table was built for
   bool tab_ready = false, lin = true;
   float goff = 0.f;                          // row-constant offset of the linear tables (log2)
@@ -485,9 +487,9 @@ sample_group_kernel(const ddg_sample_step_args a) {
     float best = -INFINITY;
     int bgrp = 0x7fffffff;
     if (ROUND && lin)
-      row_pass<MODE, ROUND, true>(c, va, vb, ra0, rb0, ra1, rb1, s_A, s_B, neg_base2, n_full, special_grp, row, step, key, best, bgrp);
+      row_pass<MODE, ROUND, true>(c, reinterpret_cast<const uint4*>(pa), reinterpret_cast<const uint4*>(pb), ra0, rb0, ra1, rb1, s_A, s_B, neg_base2, n_full, special_grp, row, step, key, best, bgrp);
     else
-      row_pass<MODE, ROUND, false>(c, va, vb, ra0, rb0, ra1, rb1, s_A, s_B, neg_base2, n_full, special_grp, row, step, key, best, bgrp);
+      row_pass<MODE, ROUND, false>(c, reinterpret_cast<const uint4*>(pa), reinterpret_cast<const uint4*>(pb), ra0, rb0, ra1, rb1, s_A, s_B, neg_base2, n_full, special_grp, row, step, key, best, bgrp);
     // ---- the (at most two) groups that need the careful path: the one holding z /
     // the mask column and the ragged tail; each is done by the thread that owns it
 #pragma unroll 1
