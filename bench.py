@@ -295,11 +295,13 @@ def run_gpu_arm(args, rank, world, local_rank):
   host_xs = torch.empty(B, L, dtype=torch.int64).pin_memory()
   dev = device
 
+  # schedule scalars are constants of the run, resident on the device; the per-step INPUT is xt
+  sig_d, mct_d, mcs_d = (t.to(dev, torch.float32) for t in (sig, mct, mcs))
+
   def e2e_step(i):
     x = host_xt.to(dev, non_blocking=True)
-    s = sig[i].to(dev).expand(B)
-    xs, _, _ = model._cfg_denoise(cond, GAMMA, x, s, mct[i].to(dev).expand(B)[:, None, None],
-                                  mcs[i].to(dev).expand(B)[:, None, None])
+    xs, _, _ = model._cfg_denoise(cond, GAMMA, x, sig_d[i].expand(B), mct_d[i].expand(B)[:, None, None],
+                                  mcs_d[i].expand(B)[:, None, None])
     host_xs.copy_(xs, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     host_xt.copy_(host_xs)
