@@ -368,26 +368,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
   if (warp == 4) {
     if (lane == 0) {
       constexpr uint32_t id_s = idesc<T>(128, 0), id_o = idesc<T>(64, 1);
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const uint32_t ph = (uint32_t)(it & 1);
+      auto load_qk = [&](int item) {
         const int bb = item / H, hh = item % H;
-        // q, k of this item (their buffers were released by s_full of the previous item); v after o_full
-        if (it > 0) mbar_wait(b_s, ph ^ 1);
         mbar_expect_tx(b_qk, 2 * TILE);
         tma_load_2d(&tma_qkv, b_qk, sq, hh * 64, bb * L_TC);
         tma_load_2d(&tma_qkv, b_qk, sk, (H + hh) * 64, bb * L_TC);
-        if (it > 0) mbar_wait(b_o, ph ^ 1);
+      };
+      auto load_v = [&](int item) {
+        const int bb = item / H, hh = item % H;
         mbar_expect_tx(b_v, TILE);
         tma_load_2d(&tma_qkv, b_v, sv, (2 * H + hh) * 64, bb * L_TC);
-        // ---- S = Q K^T (the softmax warps have read the previous S once p_ready fired)
-        if (it > 0) mbar_wait(b_p, ph ^ 1);
+      };
+      if ((int)blockIdx.x < n_items) { load_qk(blockIdx.x); load_v(blockIdx.x); }
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t ph = (uint32_t)(it & 1);
+        const int next = item + (int)gridDim.x;
+        // ---- S = Q K^T (tensor memory S was released by p_ready of the previous item, waited below)
         mbar_wait(b_qk, ph);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(tm_s, smem_desc(sq) + (uint64_t)(2 * k), smem_desc(sk) + (uint64_t)(2 * k), id_s, (uint32_t)(k != 0));
         umma_commit(b_s);
+        // q, k are free as soon as those MMAs retire: fetch the next item's while this one is in softmax
+        mbar_wait(b_s, ph);
+        if (next < n_items) load_qk(next);
         // ---- O = P V
         mbar_wait(b_p, ph);
         mbar_wait(b_v, ph);
@@ -398,6 +404,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
           umma_f16(tm_o, smem_desc(sp + (k >> 2) * TILE) + (uint64_t)(2 * (k & 3)),
                    smem_desc(sv) + (uint64_t)(k * 128), id_o, (uint32_t)(k != 0));
         umma_commit(b_o);
+        mbar_wait(b_o, ph);                            // v (and P) consumed
+        if (next < n_items) load_v(next);
       }
     }
     __syncwarp();
