@@ -176,6 +176,121 @@ ln_modulate_kernel(float* __restrict__ x, int64_t rows, int hidden,
   }
 }
 
+// packed f32x2 helpers (sm_100 FADD2 / FMUL2 / FFMA2)
+__device__ __forceinline__ float2 f2add(float2 x, float2 y) {
+  float2 r;
+  asm("{\n\t.reg .b64 a, b, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y));
+  return r;
+}
+__device__ __forceinline__ float2 f2mul(float2 x, float2 y) {
+  float2 r;
+  asm("{\n\t.reg .b64 a, b, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmul.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y));
+  return r;
+}
+__device__ __forceinline__ float2 f2fma(float2 x, float2 y, float2 z) {
+  float2 r;
+  asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%6, %7};\n\t"
+      "fma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y), "f"(z.x), "f"(z.y));
+  return r;
+}
+template <typename T> __device__ __forceinline__ uint32_t pack16(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack16<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack16<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Streaming variant of ln_modulate_kernel for hidden == 128 * NV (no gather): every warp
+// owns a contiguous run of rows and keeps ln_w and the fp32 copies of (1 + scale, shift) of
+// the current conditioning row in registers, so a row costs its loads, ~4 packed
+// arithmetic instructions per column pair and one packed conversion -- about half the
+// issue slots of the generic kernel, which matters at the ~1.3 GHz the SMs run at inside
+// a long power-capped step.  Same arithmetic order as the generic kernel (bit-identical).
+template <typename T, int NV>
+__global__ void __launch_bounds__(128, 3)
+ln_modulate_stream_kernel(const float* __restrict__ x, int64_t rows, const float* __restrict__ ln_w,
+                          const T* __restrict__ shift, const T* __restrict__ ops, int64_t mod_stride,
+                          int64_t rows_per_mod, T* __restrict__ out) {
+  constexpr int hidden = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t per = (rows + n_warps - 1) / n_warps;
+  const int64_t r0 = wid * per, r1 = r0 + per < rows ? r0 + per : rows;
+  if (r0 >= rows) return;
+  float2 w2[NV][2], g2[NV][2], s2[NV][2];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 w4 = *reinterpret_cast<const float4*>(ln_w + (i * 32 + lane) * 4);
+    w2[i][0] = make_float2(w4.x, w4.y);
+    w2[i][1] = make_float2(w4.z, w4.w);
+    g2[i][0] = g2[i][1] = make_float2(1.f, 1.f);
+    s2[i][0] = s2[i][1] = make_float2(0.f, 0.f);
+  }
+  int64_t cur_mod = -1;
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(x + r0 * hidden + (i * 32 + lane) * 4);
+  for (int64_t row = r0; row < r1; ++row) {
+    if (shift) {
+      const int64_t mrow = rows_per_mod > 0 ? row / rows_per_mod : 0;
+      if (mrow != cur_mod) {               // warp-uniform
+        cur_mod = mrow;
+        const T* sh = shift + mrow * mod_stride;
+        const T* sc = ops + mrow * mod_stride;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int col = (i * 32 + lane) * 4;
+          g2[i][0] = make_float2(Cvt<T>::to_f32(sc[col]), Cvt<T>::to_f32(sc[col + 1]));
+          g2[i][1] = make_float2(Cvt<T>::to_f32(sc[col + 2]), Cvt<T>::to_f32(sc[col + 3]));
+          s2[i][0] = make_float2(Cvt<T>::to_f32(sh[col]), Cvt<T>::to_f32(sh[col + 1]));
+          s2[i][1] = make_float2(Cvt<T>::to_f32(sh[col + 2]), Cvt<T>::to_f32(sh[col + 3]));
+        }
+      }
+    }
+    float4 c[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) c[i] = v[i];
+    if (row + 1 < r1) {                    // next row in flight while this one is reduced
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        v[i] = *reinterpret_cast<const float4*>(x + (row + 1) * hidden + (i * 32 + lane) * 4);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sum += (c[i].x + c[i].y) + (c[i].z + c[i].w);
+    const float mean = warp_sum(sum) / (float)hidden;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      c[i].x -= mean; c[i].y -= mean; c[i].z -= mean; c[i].w -= mean;
+      sq += (c[i].x * c[i].x + c[i].y * c[i].y) + (c[i].z * c[i].z + c[i].w * c[i].w);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)hidden + 1e-5f);
+    const float2 rs = make_float2(rstd, rstd);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      // ((x - mean) * rstd) * w, then * (1 + scale) + shift: the generic kernel's order
+      float2 y0 = f2mul(f2mul(make_float2(c[i].x, c[i].y), rs), w2[i][0]);
+      float2 y1 = f2mul(f2mul(make_float2(c[i].z, c[i].w), rs), w2[i][1]);
+      if (shift) {
+        y0 = f2fma(y0, g2[i][0], s2[i][0]);
+        y1 = f2fma(y1, g2[i][1], s2[i][1]);
+      }
+      uint2 o;
+      o.x = pack16<T>(y0.x, y0.y);
+      o.y = pack16<T>(y1.x, y1.y);
+      *reinterpret_cast<uint2*>(out + row * hidden + (i * 32 + lane) * 4) = o;
+    }
+  }
+}
+
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,8 +423,24 @@ extern "C" int ddg_ln_modulate(float* x, int64_t rows, int32_t hidden, const int
               "ln_modulate: shift and one_plus_scale go together");
   if (ids) DDG_REQUIRE(embedding && ids_period > 0, DDG_ERR_INVALID, "ln_modulate: ids without embedding/period");
   if (rows == 0) return DDG_OK;
-  const unsigned grid = (unsigned)((rows + 7) / 8);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (!ids && rows >= 4096 && (hidden == 512 || hidden == 768) &&
+      (dtype == DDG_F16 || dtype == DDG_BF16)) {
+    // streaming variant: contiguous rows per warp, modulation vectors cached in registers
+    const unsigned sgrid = (unsigned)(sm_count() * 3);
+#define DDG_LNS_LAUNCH(T, NV)                                                                        \
+  ln_modulate_stream_kernel<T, NV><<<sgrid, 128, 0, s>>>(x, rows, ln_weight, reinterpret_cast<const T*>(shift), \
+                                                         reinterpret_cast<const T*>(one_plus_scale), mod_stride, \
+                                                         rows_per_mod, reinterpret_cast<T*>(out))
+    if (dtype == DDG_F16) {
+      if (hidden == 512) DDG_LNS_LAUNCH(__half, 4); else DDG_LNS_LAUNCH(__half, 6);
+    } else {
+      if (hidden == 512) DDG_LNS_LAUNCH(__nv_bfloat16, 4); else DDG_LNS_LAUNCH(__nv_bfloat16, 6);
+    }
+#undef DDG_LNS_LAUNCH
+    return check_cuda(cudaGetLastError(), "ln_modulate_stream launch");
+  }
+  const unsigned grid = (unsigned)((rows + 7) / 8);
 #define DDG_LN_LAUNCH(T, MAXV)                                                                      \
   ln_modulate_kernel<T, MAXV><<<grid, 256, 0, s>>>(x, rows, hidden, ids, ids_period, embedding, ln_weight,      \
                                                    reinterpret_cast<const T*>(shift),               \

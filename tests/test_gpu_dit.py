@@ -200,6 +200,42 @@ def test_ln_modulate(hidden, dtype):
   torch.testing.assert_close(out.float(), y.to(dtype).float(), rtol=rtol, atol=atol)
 
 
+@pytest.mark.parametrize('hidden', [512, 768])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('ada', [True, False])
+def test_ln_modulate_streaming_variant(hidden, dtype, ada):
+  """Large row counts take the streaming kernel (contiguous rows per warp,
+  modulation vectors cached in registers): bit-identical to the generic kernel
+  and within tolerance of torch."""
+  rpm, rows = 100, 5000
+  n_mod = rows // rpm
+  g = torch.Generator().manual_seed(hidden + 1)
+  x = (torch.randn(rows, hidden, generator=g) * 2 + 0.3).to(DEV)
+  lnw = (1 + 0.1 * torch.randn(hidden, generator=g)).to(DEV)
+  mod = torch.randn(n_mod, 3 * hidden, generator=g).to(dtype).to(DEV)
+  shift, ops = mod[:, :hidden], mod[:, hidden:2 * hidden]
+  out = torch.empty(rows, hidden, dtype=dtype, device=DEV)
+  code = _lib.DTYPE_CODE[dtype]
+
+  def run(xp, n, sh, op, outp):
+    _lib.check(_lib.lib.ddg_ln_modulate(
+      xp, n, hidden, 0, n, 0, lnw.data_ptr(), sh if ada else 0, op if ada else 0,
+      mod.stride(0), rpm, code, outp, _lib.stream_ptr()))
+  run(x.data_ptr(), rows, shift.data_ptr(), ops.data_ptr(), out.data_ptr())       # streaming
+  ref = torch.empty_like(out)
+  half = 2500                                                                     # generic (< 4096 rows)
+  for r0 in (0, half):
+    m0 = r0 // rpm
+    run(x[r0:].data_ptr(), half, shift[m0:].data_ptr(), ops[m0:].data_ptr(), ref[r0:].data_ptr())
+  torch.cuda.synchronize()
+  assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
+  y = torch.nn.functional.layer_norm(x, [hidden]) * lnw
+  if ada:
+    y = y * ops.float().repeat_interleave(rpm, 0) + shift.float().repeat_interleave(rpm, 0)
+  rtol, atol = _tol(dtype)
+  torch.testing.assert_close(out.float(), y.to(dtype).float(), rtol=rtol, atol=atol)
+
+
 def _model(case, classifier=False):
   cfg, tok, sd, csd = helpers.case_state(case)
   m = ddg_b200.DIT(cfg, tok.vocab_size, device=DEV, classifier=classifier)
