@@ -4,7 +4,7 @@
 # usage: gpu_profile.sh [tag]
 TAG=${1:-r01}
 mkdir -p gpurun_out
-KRE='gemm_kernel|attention_kernel|ln_modulate_kernel|sample_step_kernel|sample_fused_kernel|sample_group_kernel|cond_embed_kernel|adaln_kernel|step_advance_kernel'
+KRE='gemm_kernel|attention_kernel|attention_tc_kernel|ln_modulate_kernel|ln_modulate_stream_kernel|sample_step_kernel|sample_fused_kernel|sample_group_kernel|cond_embed_kernel|adaln_kernel|step_advance_kernel'
 # (1) launch list of bench.py itself: 3 steps' worth of our kernels (91 launches per step)
 BENCH="python -W ignore bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $BENCH > gpurun_out/${TAG}_bench_plain.log 2>&1 || { echo "plain bench failed"; tail -20 gpurun_out/${TAG}_bench_plain.log; exit 1; }
@@ -20,9 +20,9 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 9
 echo "gemm rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:'sample_fused_kernel|sample_step_kernel|sample_group_kernel' -s 1 -c 1 -f -o gpurun_out/${TAG}_sampler $CMD > gpurun_out/ncu_sampler.log 2>&1
 echo "sampler rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 12 -c 1 -f -o gpurun_out/${TAG}_attn $CMD > gpurun_out/ncu_attn.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'attention_kernel|attention_tc_kernel' -s 12 -c 1 -f -o gpurun_out/${TAG}_attn $CMD > gpurun_out/ncu_attn.log 2>&1
 echo "attn rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:ln_modulate_kernel -s 26 -c 1 -f -o gpurun_out/${TAG}_ln $CMD > gpurun_out/ncu_ln.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'ln_modulate_kernel|ln_modulate_stream_kernel' -s 26 -c 1 -f -o gpurun_out/${TAG}_ln $CMD > gpurun_out/ncu_ln.log 2>&1
 echo "ln rc=$?"
 rm -f gpurun_out/${TAG}_ncu_full_summary.csv
 for f in gemm sampler attn ln; do python scripts/ncu_summary.py gpurun_out/${TAG}_$f.ncu-rep gpurun_out/${TAG}_ncu_full_summary.csv; done
