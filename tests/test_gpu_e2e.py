@@ -196,3 +196,28 @@ def test_step_api_graph_path_equals_eager_path(name):
     torch.cuda.synchronize()
     assert torch.equal(xe, xg), f'step {i}'
     xt = xe
+
+
+@pytest.mark.parametrize('B,guidance', [(1, 'cfg'), (17, 'cfg'), (33, None), (64, 'cfg')])
+def test_production_shapes_graph_equals_eager(B, guidance):
+  """DiT-small-width model (hidden 768, 12 heads, L = 128, V = 30522) at batch sizes that
+  are not multiples of anything: this is the shape family that takes the production
+  kernels (tcgen05 attention, streaming LayerNorm from 4096 rows up, hierarchical-race
+  sampler).  The captured-graph loop must equal the eager loop bit for bit (same Philox
+  key) and a second sample() must differ."""
+  import dataclasses
+  base = cases.CASE_BY_NAME['bert_udlm_cfg_g2']
+  case = dataclasses.replace(base, name=f'prod_{B}', batch=B, length=128, hidden=768, n_heads=12,
+                             n_blocks=2, guidance=guidance, steps=3)
+  model, cfg, tok = _diffusion(case)
+  a = model.sample()
+  model._call_count -= 1
+  model.use_cuda_graph = False
+  b = model.sample()
+  torch.cuda.synchronize()
+  assert tuple(a.shape) == (B, 128) and a.dtype == torch.int64
+  assert torch.equal(a, b)
+  assert int(a.min()) >= 0 and int(a.max()) < tok.vocab_size
+  model.use_cuda_graph = True
+  c = model.sample()
+  assert not torch.equal(a, c)
