@@ -274,6 +274,28 @@ def test_dit_forward_matches_oracle(name):
   assert (logits.float().cpu() - ref32).abs().mean().item() <= 0.03
 
 
+def test_dit_forward_l128_takes_tcgen05_attention():
+  """L = 128 non-causal is the shape of the tensor-memory attention kernel (and, at
+  hidden 512, 40 x 128 rows, of the streaming LayerNorm): whole forward vs the oracle
+  with the GPU roundings, same bound as above."""
+  import dataclasses
+  case = dataclasses.replace(cases.CASE_BY_NAME['udlm_cfg_g2'], name='l128', length=128, hidden=512,
+                             n_heads=8, batch=40)
+  m, cfg, tok, sd, _ = _model(case)
+  B, L = 40, 128
+  g = torch.Generator().manual_seed(5)
+  ids = torch.randint(0, tok.vocab_size, (B, L), generator=g)
+  sigma = torch.rand(B, generator=g) * 3
+  cond = torch.randint(0, 3, (B,), generator=g)
+  logits = m.forward(ids.to(DEV), sigma.to(DEV), cond.to(DEV))
+  torch.cuda.synchronize()
+  ref = ref_dit.dit_forward(sd, ids, sigma, cond, n_heads=case.n_heads,
+                            rounding=ref_dit.Rounding.gpu_denoiser())
+  d = (logits.float().cpu() - ref).abs()
+  assert bool((d <= 0.06 + 0.03 * ref.abs()).all()), d.max().item()
+  assert d.mean().item() <= 0.01, d.mean().item()
+
+
 def test_conditioning_and_adaln_tables():
   case = cases.CASE_BY_NAME['udlm_cfg_g2']
   m, cfg, tok, sd, _ = _model(case)
