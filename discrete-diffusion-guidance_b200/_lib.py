@@ -26,7 +26,7 @@ EXPORTS = (
   'ddg_abi_version', 'ddg_last_error', 'ddg_device_check', 'ddg_sm_count',
   'ddg_sample_step', 'ddg_low_confidence_select', 'ddg_log_probs', 'ddg_sample_prior', 'ddg_step_advance',
   'ddg_cond_embed', 'ddg_adaln', 'ddg_ln_modulate', 'ddg_gemm',
-  'ddg_attention', 'ddg_cast', 'ddg_classifier_head', 'ddg_cbg_candidates',
+  'ddg_attention', 'ddg_attention_decode', 'ddg_cast', 'ddg_classifier_head', 'ddg_cbg_candidates',
   'ddg_classifier_head_backward', 'ddg_gate_mul', 'ddg_gelu_backward',
   'ddg_ln_modulate_backward', 'ddg_attention_backward', 'ddg_split16',
   'ddg_cbg_first_order')
@@ -61,7 +61,8 @@ class GemmArgs(C.Structure):
     ('K', C.c_int32), ('dtype', C.c_int32), ('epilogue', C.c_int32),
     ('seq_len', C.c_int32), ('head_dim', C.c_int32), ('rope_cols', C.c_int32),
     ('stats', C.c_void_p), ('stats_ld', C.c_int64),
-    ('stats_mask_col', C.c_int32), ('accumulate', C.c_int32)]
+    ('stats_mask_col', C.c_int32), ('accumulate', C.c_int32),
+    ('rope_pos0', C.c_int32), ('reserved', C.c_int32)]
 
 
 def _load():
@@ -91,6 +92,7 @@ def _load():
                                   i64, i32, vp, vp]
   lib.ddg_gemm.argtypes = [C.POINTER(GemmArgs), vp]
   lib.ddg_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+  lib.ddg_attention_decode.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
   lib.ddg_cast.argtypes = [vp, vp, i64, i32, vp]
   lib.ddg_classifier_head.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp,
                                       vp]

@@ -274,6 +274,45 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__ ou
 }
 
 // ---------------------------------------------------------------------------
+// One decode step against the KV cache (AR sampling): one warp per (sequence, head),
+// lanes own two of the 64 dims, online softmax over the pos + 1 cached keys.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+attention_decode_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n_pairs, int cache_len, int pos, int H) {
+  const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pair >= n_pairs) return;
+  const int lane = threadIdx.x & 31;
+  const int b = pair / H, h = pair % H;
+  const int64_t row_stride = (int64_t)3 * H * 64;
+  const T* base = qkv + (int64_t)b * cache_len * row_stride + (int64_t)h * 64 + 2 * lane;
+  const float q0 = Cvt<T>::to_f32(base[(int64_t)pos * row_stride]);
+  const float q1 = Cvt<T>::to_f32(base[(int64_t)pos * row_stride + 1]);
+  constexpr float kScale2 = 0.125f * kLog2e;
+  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int j = 0; j <= pos; ++j) {
+    const T* kr = base + (int64_t)j * row_stride + (int64_t)H * 64;
+    const T* vr = base + (int64_t)j * row_stride + (int64_t)2 * H * 64;
+    float s = q0 * Cvt<T>::to_f32(kr[0]) + q1 * Cvt<T>::to_f32(kr[1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, s);
+    const float alpha = ex2_approx((m - mn) * kScale2);
+    // P is rounded to the 16-bit type before it multiplies V, like the prefill kernels
+    const float p = ex2_approx((s - mn) * kScale2);
+    const float pr = Cvt<T>::round(p);
+    l = l * alpha + p;
+    o0 = o0 * alpha + pr * Cvt<T>::to_f32(vr[0]);
+    o1 = o1 * alpha + pr * Cvt<T>::to_f32(vr[1]);
+    m = mn;
+  }
+  const float inv = 1.f / l;
+  T* dst = out + (int64_t)b * H * 64 + (int64_t)h * 64 + 2 * lane;
+  dst[0] = Cvt<T>::from_f32(o0 * inv);
+  dst[1] = Cvt<T>::from_f32(o1 * inv);
+}
+
+// ---------------------------------------------------------------------------
 // tcgen05 variant for the benchmark shape (non-causal, L == 128, d == 64):
 //   S = Q K^T   one 128x128x64 UMMA chain, fp32 scores in tensor memory
 //   softmax     128 threads, thread i = query row i = TMEM lane i (tcgen05.ld 32x32b),
@@ -549,6 +588,32 @@ int launch_attention(const void* qkv, void* out, int batch, int L, int H, int dt
 
 }  // namespace
 }  // namespace ddg
+
+extern "C" int ddg_attention_decode(const void* qkv_cache, void* out, int32_t batch, int32_t cache_len, int32_t pos,
+                                    int32_t n_heads, int32_t head_dim, int32_t dtype, ddg_stream_t stream) {
+  using namespace ddg;
+  int rc = ddg_device_check();
+  if (rc) return rc;
+  DDG_REQUIRE(qkv_cache && out && batch >= 0 && n_heads > 0 && cache_len > 0 && pos >= 0 && pos < cache_len,
+              DDG_ERR_INVALID, "attention_decode: bad args");
+  DDG_REQUIRE(head_dim == 64, DDG_ERR_UNSUPPORTED, "attention_decode: head_dim must be 64 (got %d)", head_dim);
+  if (batch == 0) return DDG_OK;
+  const int n_pairs = batch * n_heads;
+  const unsigned grid = (unsigned)((n_pairs + 3) / 4);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == DDG_F16)
+    attention_decode_kernel<__half><<<grid, 128, 0, s>>>(reinterpret_cast<const __half*>(qkv_cache),
+                                                         reinterpret_cast<__half*>(out), n_pairs, cache_len, pos, n_heads);
+  else if (dtype == DDG_BF16)
+    attention_decode_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_cache),
+                                                                reinterpret_cast<__nv_bfloat16*>(out), n_pairs,
+                                                                cache_len, pos, n_heads);
+  else {
+    set_error("attention_decode: dtype must be f16 or bf16");
+    return DDG_ERR_INVALID;
+  }
+  return check_cuda(cudaGetLastError(), "attention_decode launch");
+}
 
 extern "C" int ddg_attention(const void* qkv, void* out, int32_t batch, int32_t seq_len, int32_t n_heads,
                              int32_t head_dim, int32_t causal, int32_t dtype, ddg_stream_t stream) {

@@ -58,6 +58,7 @@ struct GemmParams {
   int64_t stats_ld;
   int mask_col;         // column excluded from the partials (-1: none)
   int accumulate;       // ACCUM_F32: add to the existing output
+  int rope_pos0;        // QKV_ROPE: position offset
 };
 
 // ------------------------------------------------------------------ PTX
@@ -676,7 +677,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           // rotary pairs column d with d + 32 of a 64-wide head: two 32-column chunks at a time
           float2 cs[16], sn[16];
           {
-            const int pos = row_ok ? (m % p.seq_len) : 0;
+            const int pos = row_ok ? (p.rope_pos0 + m % p.seq_len) : 0;
             const uint4* pc = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.rope_cos) + (int64_t)pos * 32);
             const uint4* ps = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.rope_sin) + (int64_t)pos * 32);
 #pragma unroll
@@ -925,6 +926,7 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
   p.M = a.M; p.N = a.N; p.K = a.K; p.seq_len = a.seq_len; p.rope_cols = a.rope_cols;
   p.stats = reinterpret_cast<float2*>(a.stats); p.stats_ld = a.stats_ld; p.mask_col = a.stats_mask_col;
   p.accumulate = a.accumulate;
+  p.rope_pos0 = a.rope_pos0;
   if (a.stats) {
     DDG_REQUIRE(a.epilogue == DDG_EPI_STORE && a.stats_ld >= a.M &&
                 reinterpret_cast<uintptr_t>(a.stats) % 8 == 0, DDG_ERR_INVALID,

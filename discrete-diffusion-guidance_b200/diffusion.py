@@ -58,6 +58,9 @@ class Diffusion:
     # knobs that are not reference config keys
     self.round_bf16 = True      # reproduce the reference's bf16 log-softmax/exp
     self.fast_math = True       # ex2/lg2 intrinsics in the fused sampler
+    self.ar_kv_cache = True     # AR sampler: incremental decode against a KV
+                                # cache; False = re-encode the prefix per
+                                # token like the reference (diffusion.py:1132)
     self.race_group = 8         # Philox path: hierarchical race over 8-column
                                 # groups (same distribution, 8x less noise
                                 # work); 0 = one exponential per vocab entry
@@ -498,9 +501,11 @@ class Diffusion:
   @torch.no_grad()
   def _ar_sample(self, classifier_model=None, cond=None):
     """diffusion.py:1085-1186 (+ _ar_cfg_denoise :1188-1236) for the DiT
-    backbone.  The reference re-encodes the growing prefix; with causal
-    attention a fixed full-length forward gives the same row i, so every step
-    has one shape."""
+    backbone.  The reference re-encodes the growing prefix for every token
+    (diffusion.py:1132); here each step pushes ONE token per sequence through the
+    network against a KV cache (`ar_kv_cache`, same logits up to summation
+    order), or -- `ar_kv_cache = False` -- runs a fixed full-length causal
+    forward whose row i is the prefix re-encode."""
     guidance = self.config.get('guidance')
     method = None if guidance is None else guidance.method
     if method not in (None, 'cfg'):
@@ -515,7 +520,7 @@ class Diffusion:
     x[:, 0] = self.tokenizer.bos_token_id
     two = method == 'cfg' and guidance.gamma not in (0.0, 1.0)
     n_fwd = 2 if two else 1
-    buf = self.backbone.alloc_logits(n_fwd * B * L)
+    buf = None if self.ar_kv_cache else self.backbone.alloc_logits(n_fwd * B * L)
     y = torch.empty(B, dtype=torch.int64, device=self.device)
     labels = None
     if method == 'cfg':
@@ -523,15 +528,29 @@ class Diffusion:
       labels = (torch.cat([cond, mask_cond]) if two
                 else (mask_cond if guidance.gamma == 0.0 else cond))
     mod = ModSpec(n_mod=n_fwd * B, seqs_per_mod=1, labels=labels)
+    kv = step_logits = None
+    if self.ar_kv_cache:
+      kv = self.backbone.alloc_kv_cache(n_fwd * B, L)
+      step_logits = self.backbone.alloc_logits(n_fwd * B)
     for i in range(L - 1):
-      self.backbone.run(x, n_fwd * B, L, mod, buf, ids_period=B * L)
+      if kv is not None:
+        # only token i goes through the network; rows 0..i-1 of the cache hold
+        # the keys / values of the prefix
+        xi = x[:, i].contiguous()
+        self.backbone.run_decode(xi, n_fwd * B, L, i, mod, kv, step_logits,
+                                 ids_period=B)
+        la, lda = step_logits.data_ptr(), ld
+        lb, ldb = step_logits.data_ptr() + B * ld * 2, ld
+      else:
+        self.backbone.run(x, n_fwd * B, L, mod, buf, ids_period=B * L)
+        la, lda = buf.data_ptr() + i * ld * 2, L * ld
+        lb, ldb = buf.data_ptr() + (B * L + i) * ld * 2, L * ld
       noise = None
       if self.noise_fn is not None:
         noise = self.noise_fn(i).to(self.device, torch.float32).contiguous()
       self._launch_sampler(
-        logits_a=buf.data_ptr() + i * ld * 2, ld_a=L * ld,
-        logits_b=(buf.data_ptr() + (B * L + i) * ld * 2) if two else None,
-        ld_b=L * ld if two else 0, noise=noise, xt=y, xs=y, rows=B, seq_len=1,
+        logits_a=la, ld_a=lda, logits_b=lb if two else None,
+        ld_b=ldb if two else 0, noise=noise, xt=y, xs=y, rows=B, seq_len=1,
         guidance=_lib.GUIDE_CFG if two else _lib.GUIDE_NONE,
         gamma=guidance.gamma if two else 1.0, diffusion=_lib.AR,
         select=_lib.SELECT_GUMBEL, step=i,

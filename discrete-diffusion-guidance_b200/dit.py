@@ -330,6 +330,86 @@ class DIT:
          self.vocab_ld, self.vocab_size, h, _lib.EPI_STORE, hcode,
          bias=ptr(self.b_vocab), stats=st, stats_ld=st_ld)
 
+  # ------------------------------------------------------------------ AR decode
+  def alloc_kv_cache(self, n_seqs: int, L: int):
+    """Per block, the (n_seqs * L, 3 * hidden) tensor the QKV GEMM fills one token
+    row at a time (row b * L + t = token t of sequence b, rotary already applied)."""
+    return [torch.zeros(n_seqs * L, 3 * self.hidden, dtype=self.block_dtype,
+                        device=self.device) for _ in range(self.n_blocks)]
+
+  def run_decode(self, ids_t: torch.Tensor, n_seqs: int, L: int, pos: int,
+                 mod: ModSpec, kv_cache, logits_out: torch.Tensor,
+                 ids_period: typing.Optional[int] = None):
+    """One incremental step of the causal forward (AR sampling with a KV cache
+    instead of the reference's prefix re-encode, diffusion.py:1132): the token
+    at position `pos` of every sequence (`ids_t`, reused cyclically with period
+    `ids_period`) -> logits (n_seqs, vocab_ld) of the next position.  Keys and
+    values of positions 0..pos-1 come from `kv_cache`."""
+    assert self._loaded and self.causal and not self.classifier
+    n, h, nb = n_seqs, self.hidden, self.n_blocks
+    period = n if ids_period is None else ids_period
+    ws = self._workspace(max(n, 1), mod.n_mod)
+    s = stream_ptr()
+    bcode = _lib.DTYPE_CODE[self.block_dtype]
+    hcode = _lib.DTYPE_CODE[self.head_dtype]
+    mod_stride = nb * 6 * h
+    rpm = mod.seqs_per_mod            # one token row per sequence
+    ada = self.use_adaln
+    if ada:
+      check(lib.ddg_cond_embed(
+        0, 0, 0, 0, ptr(mod.labels), mod.n_mod, self.cond_dim, _FREQ_DIM, 0, 0, 0, 0,
+        ptr(self.label_table), ptr(ws['c']), s))
+      check(lib.ddg_adaln(ptr(ws['c']), mod.n_mod, self.cond_dim, ptr(self.ada_w),
+                          ptr(self.ada_b), nb * 6 * h, bcode, h, 0b010010, 6,
+                          ptr(ws['mod_blk']), mod_stride, s))
+      if self.final_adaln:
+        check(lib.ddg_adaln(ptr(ws['c']), mod.n_mod, self.cond_dim,
+                            ptr(self.ada_f_w), ptr(self.ada_f_b), 2 * h, hcode, h,
+                            0b10, 2, ptr(ws['mod_fin']), 2 * h, s))
+    cos, sin = self._rope_tables(L)
+    x, a16, h4 = ptr(ws['x']), ptr(ws['a16']), ptr(ws['h4'])
+    modb = ptr(ws['mod_blk'])
+
+    def gemm(a, lda, w, ldw, out, ld_out, N, K, epi, dtype, bias=0, gate=0,
+             gate_stride=0, rope_pos0=0):
+      g = _lib.GemmArgs(
+        a=a, w=w, out=out, bias=bias, gate=gate, rope_cos=ptr(cos),
+        rope_sin=ptr(sin), lda=lda, ldw=ldw, ld_out=ld_out,
+        gate_stride=gate_stride, rows_per_mod=rpm, M=n, N=N, K=K, dtype=dtype,
+        epilogue=epi, seq_len=1, head_dim=self.head_dim, rope_cols=2 * h,
+        stats=0, stats_ld=0, stats_mask_col=-1, rope_pos0=rope_pos0)
+      check(lib.ddg_gemm(g, s))
+
+    for i in range(nb):
+      mb = modb + i * 6 * h * 2
+      check(lib.ddg_ln_modulate(
+        x, n, h, ptr(ids_t) if i == 0 else 0, period, ptr(self.embedding),
+        ptr(self.ln1[i]), mb if ada else 0, mb + h * 2 if ada else 0,
+        mod_stride, rpm, bcode, a16, s))
+      # this token's q, k, v go straight into row b * L + pos of the cache
+      gemm(a16, h, ptr(self.w_qkv[i]), h, ptr(kv_cache[i]) + pos * 3 * h * 2,
+           L * 3 * h, 3 * h, h, _lib.EPI_QKV_ROPE, bcode, rope_pos0=pos)
+      check(lib.ddg_attention_decode(ptr(kv_cache[i]), a16, n, L, pos, self.n_heads,
+                                     self.head_dim, bcode, s))
+      gemm(a16, h, ptr(self.w_out[i]), h, x, h, h, h, _lib.EPI_GATE_RESIDUAL,
+           bcode, gate=mb + 2 * h * 2 if ada else 0, gate_stride=mod_stride)
+      check(lib.ddg_ln_modulate(
+        x, n, h, 0, period, 0, ptr(self.ln2[i]), mb + 3 * h * 2 if ada else 0,
+        mb + 4 * h * 2 if ada else 0, mod_stride, rpm, bcode, a16, s))
+      gemm(a16, h, ptr(self.w_fc1[i]), h, h4, 4 * h, 4 * h, h,
+           _lib.EPI_BIAS_GELU, bcode, bias=ptr(self.b_fc1[i]))
+      gemm(h4, 4 * h, ptr(self.w_fc2[i]), 4 * h, x, h, h, 4 * h,
+           _lib.EPI_GATE_RESIDUAL, bcode, bias=ptr(self.b_fc2[i]),
+           gate=mb + 5 * h * 2 if ada else 0, gate_stride=mod_stride)
+    fin = ada and self.final_adaln
+    mf = ptr(ws['mod_fin'])
+    check(lib.ddg_ln_modulate(
+      x, n, h, 0, period, 0, ptr(self.ln_f), mf if fin else 0,
+      mf + h * 2 if fin else 0, 2 * h, rpm, hcode, a16, s))
+    gemm(a16, h, ptr(self.w_vocab), h, ptr(logits_out), self.vocab_ld,
+         self.vocab_size, h, _lib.EPI_STORE, hcode, bias=ptr(self.b_vocab))
+    return logits_out
+
   # ------------------------------------------------------------------ API
   def forward(self, indices, sigma, cond=None, x_emb=None,
               return_hidden_states=False, stats_out=None, stats_mask_col=-1):

@@ -251,6 +251,9 @@ typedef struct ddg_gemm_args {
   int64_t stats_ld;
   int32_t stats_mask_col;
   int32_t accumulate;   /* ACCUM_F32: 1 = add to the existing output         */
+  int32_t rope_pos0;    /* QKV_ROPE: position = rope_pos0 + m % seq_len (the
+                           incremental AR decode passes the current position) */
+  int32_t reserved;
 } ddg_gemm_args;
 
 /* tcgen05 / TMEM / TMA GEMM: out = epilogue(a @ w^T). */
@@ -263,6 +266,15 @@ DDG_API int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream);
 DDG_API int ddg_attention(const void* qkv, void* out, int32_t batch, int32_t seq_len,
                   int32_t n_heads, int32_t head_dim, int32_t causal,
                   int32_t dtype, ddg_stream_t stream);
+
+/* One decode step of causal attention with a KV cache (AR sampler,
+ * diffusion.py:1085-1186: the reference re-encodes the whole prefix for the DiT
+ * backbone, :1132).  qkv_cache is the (batch*cache_len, 3*H*D) tensor ddg_gemm
+ * QKV_ROPE fills row by row (row b*cache_len + t = token t of sequence b);
+ * the query is row `pos`, the keys/values rows 0..pos.  out (batch, H*D). */
+DDG_API int ddg_attention_decode(const void* qkv_cache, void* out, int32_t batch, int32_t cache_len,
+                         int32_t pos, int32_t n_heads, int32_t head_dim, int32_t dtype,
+                         ddg_stream_t stream);
 
 /* fp32 -> 16-bit cast of a weight tensor (what autocast does per call;
  * done once at load time here). */

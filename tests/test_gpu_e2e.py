@@ -221,3 +221,35 @@ def test_production_shapes_graph_equals_eager(B, guidance):
   model.use_cuda_graph = True
   c = model.sample()
   assert not torch.equal(a, c)
+
+
+@pytest.mark.parametrize('guidance', [None, 'cfg'])
+def test_ar_kv_cache_equals_prefix_reencode(guidance):
+  """AR sampling with the KV cache (one token per step through the network) against the
+  reference's scheme (re-encode the prefix, here a full-length causal forward): the same
+  injected Gumbel noise must give the same ids; the incremental logits differ from the
+  re-encoded ones only by summation order (decode attention vs the prefill kernel), so at
+  most an isolated near-tie may flip -- and would then change the suffix, hence the
+  comparison position by position on the SAME prefix."""
+  import dataclasses
+  case = dataclasses.replace(cases.CASE_BY_NAME['ar_null'], name='ar_kv', guidance=guidance,
+                             gamma=2.0 if guidance else 1.0, length=48, batch=3)
+  model, cfg, tok = _diffusion(case)
+  G = cases.ar_gumbel(case)
+  model.noise_fn = lambda i: G[:, i]
+  model.ar_kv_cache = True
+  a = model.sample()
+  model._call_count -= 1
+  model.ar_kv_cache = False
+  b = model.sample()
+  torch.cuda.synchronize()
+  assert a[:, 0].eq(tok.bos_token_id).all() and tuple(a.shape) == (3, 48)
+  assert int(a.min()) >= 0 and int(a.max()) < tok.vocab_size
+  same = (a == b).all(dim=1)
+  assert int(same.sum()) >= 2, (a, b)          # at most one sequence may hit a near-tie
+  if guidance is None:
+    # every id of the KV-cache run follows the (re-encoded) log-probs of its own prefix
+    lp = model.forward(a, None).cpu()
+    ok = sum(int((ref_sampler.ar_select(lp[:, i], G[:, i]) == a[:, i + 1].cpu()).sum())
+             for i in range(case.length - 1))
+    assert ok >= 3 * (case.length - 1) - 2
