@@ -380,7 +380,7 @@ extern "C" int ddg_cond_embed(const float* sigma, int32_t sigma_row_stride, cons
                 "Conditioning variable provided, but Model was not initialized with condition embedding layer.");
   if (n == 0) return DDG_OK;
   const size_t smem = sizeof(float) * (size_t)(freq_dim + cond_dim);
-  cond_embed_kernel<<<n, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  cond_embed_kernel<<<n, 512, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
     sigma, sigma_row_stride, step_ptr, sigma_step_stride, label, cond_dim, freq_dim, w0, b0, w2, b2,
     label_table, c_out);
   return check_cuda(cudaGetLastError(), "cond_embed launch");
