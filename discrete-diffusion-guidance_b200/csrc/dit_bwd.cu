@@ -10,6 +10,9 @@
 #include "ddg_common.cuh"
 
 namespace ddg {
+// attention_bwd.cu: tensor-core path for seq_len <= 128
+int launch_attention_bwd_mma(const void* qkv, const void* g_o, const void* rope_cos, const void* rope_sin, int batch,
+                             int seq_len, int n_heads, int causal, int dtype, void* g_qkv, cudaStream_t s);
 namespace {
 
 // ---------------------------------------------------------------- head backward
@@ -164,7 +167,8 @@ ln_modulate_bwd_kernel(const float* __restrict__ x, const T* __restrict__ g_a, i
     }
 }
 
-// ---------------------------------------------------------------- attention backward
+// ---------------------------------------------------------------- attention backward (seq_len > 128)
+// CUDA-core fallback for long sequences; seq_len <= 128 runs attention_bwd.cu's tensor-core kernel.
 // One CTA per (sequence, head); q, k (post-rotary), v and dO of the head in shared
 // memory (row stride 66 elements: conflict-free column walks).  Pass A: one warp per
 // query row -> softmax stats, D_i = dO_i . o_i, dq_i.  Pass B: one warp per key row ->
@@ -409,6 +413,10 @@ extern "C" int ddg_attention_backward(const void* qkv, const void* g_out, const 
   DDG_REQUIRE(head_dim == 64 && seq_len >= 1 && seq_len <= 256, DDG_ERR_UNSUPPORTED,
               "attention_backward: head_dim must be 64 and seq_len <= 256");
   if (batch == 0) return DDG_OK;
+  DDG_REQUIRE(dtype == DDG_F16 || dtype == DDG_BF16, DDG_ERR_INVALID, "attention_backward: dtype must be f16 or bf16");
+  if (seq_len <= 128)
+    return launch_attention_bwd_mma(qkv, g_out, rope_cos, rope_sin, batch, seq_len, n_heads, causal, dtype, g_qkv,
+                                    reinterpret_cast<cudaStream_t>(stream));
   const size_t smem = (size_t)4 * seq_len * kRowPad * 2 + (size_t)3 * seq_len * 4 + (size_t)8 * 2 * seq_len * 4;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   static bool attr_done[64][2] = {{false}};

@@ -167,6 +167,51 @@ def test_attention(L, dtype, causal):
                              rtol=rtol, atol=atol)
 
 
+@pytest.mark.parametrize('L', [16, 24, 32, 48, 64, 100, 128, 160])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('causal', [False, True])
+def test_attention_backward(L, dtype, causal):
+  """d loss / d (QKV GEMM output) from d loss / d (attention output), through
+  softmax(q k^T / 8) v and the rotary (models/dit.py:284-307), against fp64
+  autograd on the same post-rotary q, k, v.  L <= 128 runs the tensor-core
+  kernel (P, dS rounded to the 16-bit type like the reference's flash backward),
+  longer sequences the CUDA-core one; ragged L covers the padded tiles."""
+  B, H = 3, 2
+  g = torch.Generator().manual_seed(100 + L)
+  qkv = (torch.randn(B, L, 3, H, 64, generator=g) * 1.2).to(dtype)     # post-rotary q, k and v
+  go = torch.randn(B, L, H, 64, generator=g).to(dtype)
+  cos, sin = ref_dit.rotary_tables(L, 64)
+  cos, sin = cos.to(dtype), sin.to(dtype)
+  out = torch.empty(B * L, 3 * H * 64, dtype=dtype, device=DEV)
+  qd, gd = qkv.to(DEV).contiguous(), go.to(DEV).contiguous()
+  cd, sd = cos.to(DEV).contiguous(), sin.to(DEV).contiguous()
+  _lib.check(_lib.lib.ddg_attention_backward(
+    qd.data_ptr(), gd.data_ptr(), cd.data_ptr(), sd.data_ptr(), B, L, H, 64, int(causal),
+    _lib.DTYPE_CODE[dtype], out.data_ptr(), _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  x = qkv.double().requires_grad_(True)
+  sc = torch.einsum('blhd,bmhd->bhlm', x[:, :, 0], x[:, :, 1]) / 8.0
+  if causal:
+    sc = sc.masked_fill(torch.triu(torch.ones(L, L, dtype=torch.bool), 1), float('-inf'))
+  o = torch.einsum('bhlm,bmhd->blhd', sc.softmax(-1), x[:, :, 2])
+  gpost, = torch.autograd.grad(o, x, grad_outputs=go.double())
+  # back through the rotation (linear): the transpose of ref_dit._rope's map
+  pre = torch.zeros(B, L, H, 64, dtype=torch.float64, requires_grad=True)
+  c, s_ = cos.double()[None, :, None, :], sin.double()[None, :, None, :]
+  rot = torch.cat([pre[..., :32] * c - pre[..., 32:] * s_, pre[..., :32] * s_ + pre[..., 32:] * c], dim=-1)
+  ref = torch.stack([torch.autograd.grad(rot, pre, grad_outputs=gpost[:, :, 0], retain_graph=True)[0],
+                     torch.autograd.grad(rot, pre, grad_outputs=gpost[:, :, 1])[0],
+                     gpost[:, :, 2]], dim=2).float()
+  got = out.float().cpu().view(B, L, 3, H, 64)
+  tol = 6e-3 if dtype == torch.float16 else 3e-2
+  for i, nm in enumerate('qkv'):
+    scale = ref[:, :, i].abs().max().item()
+    err = (got[:, :, i] - ref[:, :, i]).abs().max().item()
+    assert err <= tol * scale, (nm, err, scale)
+    rms = ((got[:, :, i] - ref[:, :, i]).pow(2).mean() / ref[:, :, i].pow(2).mean()).sqrt().item()
+    assert rms <= tol / 3, (nm, rms)
+
+
 @pytest.mark.parametrize('hidden', [128, 512, 768, 1024])
 @pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
 def test_ln_modulate(hidden, dtype):
