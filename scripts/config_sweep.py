@@ -56,9 +56,38 @@ def cbg_main(dev):
     torch.cuda.empty_cache()
 
 
+class Text8Tok:
+  vocab_size, mask_token_id, bos_token_id, eos_token_id, pad_token_id = 35, 4, 0, 1, 3
+  mask_token = '[MASK]'
+
+
+def c1_main(dev):
+  """C1: text8 UDLM DiT-tiny, L=256, V=35, 128 steps, batch 4, guidance=null (the
+  reference's CPU-runnable case), full sample() wall time."""
+  over = ['parameterization=d3pm', 'diffusion=uniform', 'time_conditioning=True', 'T=0',
+          'model=tiny', 'model.length=256', 'training.guidance=null']
+  for B in (4, 512):
+    cfg = ddg_b200.compose(over + [f'sampling.batch_size={B}', 'sampling.steps=128'])
+    tok = Text8Tok()
+    sd = ddg_b200.weights.random_state_dict(cfg, tok.vocab_size, seed=1)
+    model = ddg_b200.Diffusion(cfg, tok, device=dev).load_state_dict(sd)
+    model.sample()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = model.sample()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert int(out.min()) >= 0 and int(out.max()) < tok.vocab_size
+    print(f'{"C1 text8 UDLM tiny null B=%d" % B:32s} {dt / 128 * 1e3:8.3f} ms/step  -> {B / dt:7.2f} seq/s at 128 steps',
+          flush=True)
+    del model
+    torch.cuda.empty_cache()
+
+
 def main():
   dev = torch.device('cuda', 0)
   steps = 40
+  c1_main(dev)
   for name, (over, B) in CONFIGS.items():
     cfg = ddg_b200.compose(list(over) + [f'sampling.batch_size={B}', f'sampling.steps={steps}'])
     sd = ddg_b200.weights.random_state_dict(cfg, bench.V, seed=1)
