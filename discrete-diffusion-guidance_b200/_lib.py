@@ -48,7 +48,8 @@ class SampleStepArgs(C.Structure):
     ('select', C.c_int32), ('fast_math', C.c_int32), ('gamma', C.c_float),
     ('seed', C.c_uint64), ('step', C.c_int32), ('stats_chunks', C.c_int32),
     ('stats_a', C.c_void_p), ('stats_b', C.c_void_p), ('stats_ld', C.c_int64),
-    ('race_group', C.c_int32), ('compute_f64', C.c_int32)]
+    ('race_group', C.c_int32), ('compute_f64', C.c_int32),
+    ('clf_round_bf16', C.c_int32), ('reserved0', C.c_int32)]   # ABI v3
 
 
 class GemmArgs(C.Structure):

@@ -173,9 +173,16 @@ __device__ __forceinline__ float g_value(const ddg_sample_step_args& a, const Ro
     if (rnd) mix = bf16_round(mix);
     return mix;   // caller adds mix_shift / ln_keep (needs the lse of mix)
   }
+  // gamma * classifier_log_prob is a bf16 product in the reference when the exact
+  // classifier term (a bf16 tensor on a GPU) is used (diffusion.py:1607, 1612)
+  float gc = 0.f;
+  if (mode_clf(MODE)) {
+    gc = F::mul(a.gamma, clf);
+    if (a.clf_round_bf16) gc = bf16_round(gc);
+  }
   if (MODE == ABS_CBG) {
     const float lq = (j == a.mask_index) ? rc.ln_mask : F::add(lpa, rc.ln_keep);
-    return F::add(F::mul(a.gamma, clf), lq);
+    return F::add(gc, lq);
   }
   // uniform: q_j = (d_alpha x_j + c0 + [j = z] zc) / den     diffusion.py:383-392
   float xa = F::exp(lpa);
@@ -184,7 +191,7 @@ __device__ __forceinline__ float g_value(const ddg_sample_step_args& a, const Ro
                          : F::add(F::mul(rc.d_alpha, xa), rc.c0);
   const float lqa = F::log(F::div(na, rc.den_a));
   if (MODE == UNI_NONE) return lqa;
-  if (MODE == UNI_CBG) return F::add(F::mul(a.gamma, clf), lqa);
+  if (MODE == UNI_CBG) return F::add(gc, lqa);
   float xb = F::exp(lpb);
   if (rnd) xb = bf16_round(xb);
   float nb = (j == rc.z) ? F::add(F::add(rc.zc_b, F::mul(rc.d_alpha, xb)), rc.c0)

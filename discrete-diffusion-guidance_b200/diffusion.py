@@ -222,7 +222,8 @@ class Diffusion:
                       mc_seq_stride=0, mc_step_stride=0, step_ptr=None, step=0,
                       guidance=_lib.GUIDE_NONE, gamma=1.0, q_out=None,
                       select=None, diffusion=None, logits_dtype=_lib.BF16,
-                      seed_ptr=None, stats=None, compute_f64=False):
+                      seed_ptr=None, stats=None, compute_f64=False,
+                      clf_round_bf16=False):
     V = self.vocab_size
     # log-softmax partials of these logits, if our own vocab GEMM made them:
     # stats = (tensor (chunks, rows_total, 2), row offset of a, row offset of b)
@@ -253,7 +254,8 @@ class Diffusion:
       gamma=float(gamma), seed=self.seed + 7919 * self._call_count,
       step=int(step), stats_chunks=st_chunks, stats_a=st_a,
       stats_b=st_b if logits_b else 0, stats_ld=st_ld,
-      race_group=int(self.race_group), compute_f64=1 if compute_f64 else 0)
+      race_group=int(self.race_group), compute_f64=1 if compute_f64 else 0,
+      clf_round_bf16=1 if clf_round_bf16 else 0)
     check(lib.ddg_sample_step(a, stream_ptr()))
 
   def _mc(self, mc):
@@ -416,7 +418,9 @@ class Diffusion:
       clf=term if term.stride(-1) == 1 else term.contiguous(),
       xt=xt, xs=xs, mc_t=mct, mc_s=mcs, rows=B * L, seq_len=L,
       mc_seq_stride=1 if mct.numel() > 1 else 0, noise=noise,
-      q_out=q, guidance=_lib.GUIDE_CBG, gamma=gamma, step=self._step_index)
+      q_out=q, guidance=_lib.GUIDE_CBG, gamma=gamma, step=self._step_index,
+      # exact term: bf16 tensor in the reference, so gamma * term rounds to bf16
+      clf_round_bf16=self.round_bf16 and not use_approx)
     if self._low_confidence:
       self._low_confidence_draw(q, xt, xs, noise,
                                 carry=self.diffusion == 'absorbing_state')

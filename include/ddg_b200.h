@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DDG_ABI_VERSION 2
+#define DDG_ABI_VERSION 3
 #define DDG_API __attribute__((visibility("default")))
 
 typedef void* ddg_stream_t; /* cudaStream_t */
@@ -135,6 +135,13 @@ typedef struct ddg_sample_step_args {
    * double.  Like the reference only without guidance (absorbing / uniform /
    * AR); with guidance -> DDG_ERR_UNSUPPORTED ("not implemented").            */
   int32_t compute_f64;
+  /* ABI v3.  D-CBG with the EXACT classifier term on a GPU: get_log_probs returns
+   * a bf16 tensor (classifier.py:325-327), so `gamma * classifier_log_prob`
+   * (python float x bf16 tensor, diffusion.py:1607, 1612) is rounded to bf16 before
+   * the fp32 posterior is added.  1 = apply that rounding to gamma * clf; 0 = the
+   * first-order term (fp32 in the reference, :1540-1547) or fp32 parity runs.  */
+  int32_t clf_round_bf16;
+  int32_t reserved0;
 } ddg_sample_step_args;
 
 DDG_API int ddg_sample_step(const ddg_sample_step_args* args, ddg_stream_t stream);

@@ -198,19 +198,26 @@ def cfg_update(lp_cond, lp_uncond, gamma, xt, mc_t, mc_s, U, *, diffusion,
 
 def cbg_update(lp, clf_log_prob, gamma, xt, mc_t, mc_s, U, *, diffusion,
                mask_index, lp_dtype=None, argmax_sampling=False,
-               low_confidence=None):
+               low_confidence=None, clf_dtype=None):
   """`_cbg_denoise` after the forward and classifier term
-  (diffusion.py:1587-1621).  clf_log_prob (B,L,V) fp32."""
+  (diffusion.py:1587-1621).  clf_log_prob (B,L,V) fp32 values.  `clf_dtype`:
+  dtype the classifier term HAS in the reference -- bf16 for the exact term on a
+  GPU (classifier.py:325-327 returns the bf16 log_softmax), so that
+  `gamma * classifier_log_prob` (python float x bf16 tensor, :1607, :1612) is
+  itself rounded to bf16; the first-order term is fp32 (:1540-1547) -> None."""
+  gc = gamma * clf_log_prob
+  if clf_dtype is not None:
+    gc = gc.to(clf_dtype).float()
   if diffusion == 'absorbing_state':
     lq = lp + torch.log(1. - (mc_s / mc_t))
     lq[..., mask_index] = torch.log(mc_s / mc_t)[:, :, 0]
-    g = gamma * clf_log_prob + lq
+    g = gc + lq
     copy_flag = xt != mask_index
     g[copy_flag] = NEG_INF
     g[copy_flag, xt[copy_flag]] = 0.0
   elif diffusion == 'uniform':
     lq = posterior_uniform(_exp(lp, lp_dtype), xt, 1 - mc_s, 1 - mc_t).log()
-    g = gamma * clf_log_prob + lq
+    g = gc + lq
   else:
     raise NotImplementedError(diffusion)
   p = g.softmax(dim=-1)
@@ -347,7 +354,8 @@ class OracleSampler:
       else:
         term = cbg_classifier_term_exact(
           self.clf_log_probs, xt, sigma_t, self.V, condition)
-      xs, q = cbg_update(lp, term, gamma, xt, mc_t, mc_s, U, **kw)
+      xs, q = cbg_update(lp, term, gamma, xt, mc_t, mc_s, U,
+                         clf_dtype=None if use_approx else self.lp_dtype, **kw)
       return xs, q, {'log_x_theta': lp, 'classifier_log_prob': term}
     raise NotImplementedError(
       f'Guidance method {guidance} not implemented.')

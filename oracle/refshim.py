@@ -185,11 +185,14 @@ def load_reference():
 
     def _rotary_qkv_(qkv, cos, sin, *a, **k):
       # reference models/dit.py:116-121 calls the Triton kernel; on CPU use
-      # the same package's pure-torch form on q and k (v untouched).
+      # the same package's pure-torch form on q and k (v untouched).  Like the
+      # Triton kernel (flash_attn/ops/triton/rotary.py:73-88) the math runs in
+      # fp32 on the 16-bit q, k, cos, sin values and is rounded once.
       if qkv.is_cuda:
         return _orig(qkv, cos, sin, *a, **k)
-      qkv[:, :, 0] = far.apply_rotary_emb_torch(qkv[:, :, 0], cos, sin)
-      qkv[:, :, 1] = far.apply_rotary_emb_torch(qkv[:, :, 1], cos, sin)
+      for i in (0, 1):
+        qkv[:, :, i] = far.apply_rotary_emb_torch(
+          qkv[:, :, i].float(), cos.float(), sin.float()).to(qkv.dtype)
       return qkv
     far.apply_rotary_emb_qkv_ = _rotary_qkv_
     far._ddg_cpu_shim = True
@@ -202,6 +205,47 @@ def load_reference():
     diffusion=diffusion, classifier=classifier, dataloader=dataloader,
     noise_schedule=noise_schedule, models=models)
   return _REF
+
+
+class _CpuAutocast:
+  """Stand-in for `torch.cuda.amp.autocast` that applies the SAME dtype policy
+  with CPU autocast, so that the unmodified reference rounds on the CPU where it
+  rounds on a GPU: fp16 / bf16 requests become `torch.autocast('cpu', dtype)`;
+  any other dtype (the reference asks for float32, diffusion.py:353,
+  classifier.py:312,325) disables autocast, which is what CUDA autocast does with
+  an unsupported dtype (torch/amp/autocast_mode.py)."""
+
+  def __init__(self, enabled=True, dtype=None, cache_enabled=True):
+    import torch
+    dtype = torch.float16 if dtype is None else dtype
+    if dtype not in (torch.float16, torch.bfloat16):
+      enabled, dtype = False, torch.bfloat16
+    self._ctx = torch.autocast('cpu', dtype=dtype, enabled=enabled,
+                               cache_enabled=cache_enabled)
+
+  def __enter__(self):
+    return self._ctx.__enter__()
+
+  def __exit__(self, *exc):
+    return self._ctx.__exit__(*exc)
+
+
+class cuda_autocast_on_cpu:
+  """Context manager: while active, the reference's `torch.cuda.amp.autocast`
+  blocks take effect on CPU tensors (see _CpuAutocast).  This is how the GPU
+  rounding points of the path (fp16 blocks, bf16 final layer, bf16 log-softmax /
+  exp; SURVEY.md 8a') are pinned without a GPU run of the reference."""
+
+  def __enter__(self):
+    import torch
+    self._saved = torch.cuda.amp.autocast
+    torch.cuda.amp.autocast = _CpuAutocast
+    return self
+
+  def __exit__(self, *exc):
+    import torch
+    torch.cuda.amp.autocast = self._saved
+    return False
 
 
 class SurrogateTokenizer:

@@ -83,6 +83,11 @@ CASES = [
        time_conditioning=False, length=16, steps=0),
 ]
 CASE_BY_NAME = {c.name: c for c in CASES}
+# cases also run with the reference's GPU autocast policy emulated on the CPU
+# (make_golden.py --amp -> <name>_amp.npz): they pin the rounding points
+AMP_CASES = ['udlm_null', 'mdlm_null', 'udlm_cfg_g2', 'mdlm_cfg_g2', 'udlm_cbg',
+             'mdlm_cbg', 'bert_udlm_cfg_g2', 'bert_mdlm_null', 'udlm_cbg_approx',
+             'mdlm_cbg_approx']
 
 
 class Tok:

@@ -6,6 +6,15 @@ prior and noise.  Run in the build container only:
 
 The reference is on CPU, where every autocast in it is disabled, so these
 vectors pin the fp32 math of the path (SURVEY.md 8a' item 7).
+
+    python tests/golden/make_golden.py --amp [case ...]
+
+writes `<case>_amp.npz` instead: the same unmodified reference code, but with
+`torch.cuda.amp.autocast` mapped onto CPU autocast of the same dtype
+(oracle/refshim.cuda_autocast_on_cpu), so every tensor is rounded where the
+reference rounds it on a GPU (fp16 blocks, bf16 final layer, bf16 log-softmax
+and exp).  These vectors pin the ROUNDING POINTS of the path; `*_dtype`
+entries record the dtype each traced tensor had.
 """
 from __future__ import annotations
 
@@ -115,6 +124,8 @@ def run_case(ref, case):
       xt = k['xt']
       xs, q, cache = orig(*a, **k)
       rec = {'xt': xt.clone(), 'xs': xs.clone(), 'q_xs': q.clone(),
+             'dtypes': {'q_xs': str(q.dtype), **{
+               ck: str(cv.dtype) for ck, cv in cache.items() if cv is not None}},
              'mc_t': k['move_chance_t'].reshape(-1)[0].clone(),
              'mc_s': k['move_chance_s'].reshape(-1)[0].clone(),
              'sigma_t': k['time_conditioning'].reshape(-1)[0].clone()}
@@ -148,16 +159,24 @@ def run_case(ref, case):
               'classifier_log_prob'):
       if k in rec:
         summarise(f's{i}_{k}', rec[k], out, big)
+  for k, v in trace[0]['dtypes'].items():
+    out[f'{k}_dtype'] = np.array(v)
   return out
 
 
 def main(argv):
   ref = refshim.load_reference()
-  names = argv or [c.name for c in cases.CASES]
+  amp = '--amp' in argv
+  argv = [a for a in argv if a != '--amp']
+  names = argv or (cases.AMP_CASES if amp else [c.name for c in cases.CASES])
   for name in names:
     case = cases.CASE_BY_NAME[name]
-    out = run_case(ref, case)
-    path = os.path.join(HERE, f'{name}.npz')
+    if amp:
+      with refshim.cuda_autocast_on_cpu():
+        out = run_case(ref, case)
+    else:
+      out = run_case(ref, case)
+    path = os.path.join(HERE, f'{name}_amp.npz' if amp else f'{name}.npz')
     np.savez_compressed(path, **out)
     print(f'{name}: {len(out)} arrays, {os.path.getsize(path) / 1024:.1f} KiB')
 

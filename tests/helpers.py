@@ -105,7 +105,8 @@ def sampler_kernel(*, logits_a, xt, mc_t, mc_s, vocab, seq_len, diffusion,
                    gamma=1.0, subs=False, mask_logit=False, mask_index=0,
                    round_bf16=False, select='race', fast_math=False, seed=0,
                    step=0, want_q=False, stats_a=0, stats_b=0, stats_ld=0,
-                   stats_chunks=0, race_group=0, compute_f64=False):
+                   stats_chunks=0, race_group=0, compute_f64=False,
+                   clf_round_bf16=False):
   """Direct call of ddg_sample_step through the C ABI on torch CUDA tensors.
   logits (rows, ld) f32 or bf16; xt (rows,) int64; mc_* scalars or (n_seq,)."""
   from ddg_b200 import _lib
@@ -136,7 +137,8 @@ def sampler_kernel(*, logits_a, xt, mc_t, mc_s, vocab, seq_len, diffusion,
     mask_index=mask_index, round_bf16=int(round_bf16), select=scode,
     fast_math=int(fast_math), gamma=float(gamma), seed=int(seed),
     step=int(step), stats_chunks=stats_chunks, stats_a=stats_a, stats_b=stats_b,
-    stats_ld=stats_ld, race_group=race_group, compute_f64=int(compute_f64))
+    stats_ld=stats_ld, race_group=race_group, compute_f64=int(compute_f64),
+    clf_round_bf16=int(clf_round_bf16))
   _lib.check(_lib.lib.ddg_sample_step(a, _lib.stream_ptr()))
   torch.cuda.synchronize()
   return xs, q

@@ -151,13 +151,17 @@ def test_kernel_vs_oracle_bf16_logits(diffusion, guidance, V, ld, round_bf16):
   elif guidance == 'cfg':
     xs_ref, q_ref = ref_sampler.cfg_update(lps(la), lps(lb), 2.0, xt, mct3, mcs3, U, **kw)
   else:
-    xs_ref, q_ref = ref_sampler.cbg_update(lps(la), clf, 1.5, xt, mct3, mcs3, U, **kw)
+    # round_bf16 runs take the exact classifier term: a bf16 tensor in the reference,
+    # so gamma * term is itself rounded to bf16 (diffusion.py:1607, 1612)
+    xs_ref, q_ref = ref_sampler.cbg_update(lps(la), clf, 1.5, xt, mct3, mcs3, U,
+                                           clf_dtype=lp_dtype, **kw)
   xs, q = helpers.sampler_kernel(
     logits_a=la.to(dev), logits_b=lb.to(dev) if guidance == 'cfg' else None,
     clf=clf if guidance == 'cbg' else None, noise=U, xt=xt, mc_t=mc_t,
     mc_s=mc_s, vocab=V, seq_len=L, diffusion=diffusion, guidance=guidance,
     gamma=2.0 if guidance == 'cfg' else 1.5, subs=subs, mask_logit=subs,
-    mask_index=mask, round_bf16=round_bf16, fast_math=False, want_q=True)
+    mask_index=mask, round_bf16=round_bf16, fast_math=False, want_q=True,
+    clf_round_bf16=round_bf16 and guidance == 'cbg')
   q = q.view(B, L, V).cpu()
   # with the bf16 roundings on, an fp32 last-ulp difference can flip a bf16
   # rounding (0.4 % of that element): allow <= 0.1 % of entries to move 1 bf16 ulp
