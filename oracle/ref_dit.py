@@ -7,7 +7,9 @@ path; the product package never imports it.
 
 Parity status: pinned against the unmodified reference imported in the build
 container (tests/golden/make_golden.py writes fixtures, tests/test_oracle_pins.py
-replays them).  The reference itself ships no tests or golden vectors.
+replays them; the `*_amp` fixtures pin `Rounding.gpu_*` against the reference run
+under an emulation of its cuda autocast policy).  The reference itself ships no
+tests or golden vectors.
 
 `Rounding` reproduces where the reference rounds on a GPU (SURVEY.md 8a'):
 blocks under autocast(fp16) (models/dit.py:454), final layer under

@@ -7,7 +7,10 @@ drawn.  It exists to check the CUDA path (tests/, smoke(), bench.py's CPU
 baseline legs); the product package never imports it.
 
 Parity status: pinned against the unmodified reference imported in the build
-container -- see tests/golden/make_golden.py and tests/test_oracle_pins.py.
+container -- see tests/golden/make_golden.py and tests/test_oracle_pins.py:
+22 fixtures of the reference on CPU (fp32 math; ids exact, probabilities 2e-4)
+and 10 `*_amp` fixtures of the reference with its cuda autocast policy emulated
+on the CPU (the GPU rounding points, `lp_dtype` / `clf_dtype` here).
 The reference ships no tests or golden vectors of its own.
 """
 from __future__ import annotations
