@@ -53,19 +53,21 @@ class Classifier:
     # classifier.py:484-490
     if sigma.ndim > 1:
       sigma = sigma.squeeze(-1)
-    if not self.time_conditioning:
-      sigma = torch.zeros_like(sigma)
+    if not self.time_conditioning:   # one shared zero (stride 0): a single conditioning row
+      sigma = torch.zeros(1, dtype=sigma.dtype, device=sigma.device).expand(sigma.shape[0])
     assert sigma.ndim == 1, sigma.shape
     return sigma
 
-  def get_log_probs(self, x, sigma, x_emb=None):
-    """classifier.py:316-327 for token ids (n, L) -> (n, classes) fp32."""
+  def get_log_probs(self, x, sigma, x_emb=None, seqs_per_mod=1):
+    """classifier.py:316-327 for token ids (n, L) -> (n, classes) fp32.
+    `seqs_per_mod` > 1: sigma holds one value per that many consecutive sequences."""
     if x_emb is not None or x.ndim != 2:
       raise NotImplementedError(
         'one-hot / x_emb classifier inputs (first-order CBG, NOS) are not '
         'implemented yet')
     return self.classifier_model.classify(x, self._process_sigma(sigma),
-                                          round_bf16=self.round_bf16)
+                                          round_bf16=self.round_bf16,
+                                          seqs_per_mod=seqs_per_mod)
 
   def first_order_term(self, xt, sigma, conditioning_class):
     """The `use_approx` branch of `_cbg_denoise` (diffusion.py:1532-1548):

@@ -105,8 +105,8 @@ class Diffusion:
       return sigma
     if sigma.ndim > 1:
       sigma = sigma.squeeze(-1)
-    if not self.time_conditioning:
-      sigma = torch.zeros_like(sigma)
+    if not self.time_conditioning:   # one shared zero (stride 0): a single conditioning row
+      sigma = torch.zeros(1, dtype=sigma.dtype, device=sigma.device).expand(sigma.shape[0])
     assert sigma.ndim == 1, sigma.shape
     return sigma
 
@@ -391,9 +391,11 @@ class Diffusion:
       n = min(chunk, total - c0)
       ids = torch.empty(n, L, dtype=torch.int64, device=self.device)
       check(lib.ddg_cbg_candidates(ptr(xt), L, V, c0, n, ptr(ids), stream_ptr()))
+      # whole sequences per chunk: the L * V edits of a sequence share its sigma, so the
+      # classifier gets one conditioning row per sequence (or one in all when every
+      # sequence shares t), not one per candidate (diffusion.py:1584 repeats sigma instead)
       b0, b1 = c0 // (L * V), (c0 + n) // (L * V)
-      sig = sigma[b0:b1].repeat_interleave(L * V)
-      lp = classifier_model.get_log_probs(ids, sig)
+      lp = classifier_model.get_log_probs(ids, sigma[b0:b1], seqs_per_mod=L * V)
       term[c0:c0 + n] = lp[:, conditioning_class]
     return term.view(B, L, V)
 

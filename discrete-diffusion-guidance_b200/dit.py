@@ -411,6 +411,25 @@ class DIT:
     return logits_out
 
   # ------------------------------------------------------------------ API
+  def _mod_spec(self, sigma, n: int, labels=None, seqs_per_mod: int = 1) -> ModSpec:
+    """Conditioning rows of a forward over n sequences: one per `seqs_per_mod`
+    consecutive sequences.  Every sequence of a sampling step shares t
+    (diffusion.py:1304-1310 builds `t * ones(B)`), so an expanded scalar sigma
+    (stride 0) without labels collapses to ONE row -- the conditioning MLP and the
+    adaLN linears then run once instead of once per sequence (same values)."""
+    mod = ModSpec(n_mod=n // seqs_per_mod, seqs_per_mod=seqs_per_mod)
+    if not self.causal:
+      sig = sigma.to(self.device, torch.float32).reshape(-1)
+      if labels is None and (sig.numel() == 1 or sig.stride(0) == 0):
+        mod.n_mod, mod.seqs_per_mod = 1, n
+        sig = sig[:1]
+      assert sig.numel() == mod.n_mod, (sig.numel(), mod.n_mod)
+      mod.sigma = sig.contiguous()
+      mod.sigma_row_stride = 1 if mod.n_mod > 1 else 0
+    if labels is not None:
+      mod.labels = labels.to(self.device, torch.int64).contiguous()
+    return mod
+
   def forward(self, indices, sigma, cond=None, x_emb=None,
               return_hidden_states=False, stats_out=None, stats_mask_col=-1):
     """`DIT.forward(indices, sigma, cond)` (models/dit.py:426-468): logits
@@ -420,12 +439,7 @@ class DIT:
                                 'are outside the sampling hot path')
     B, L = indices.shape
     ids = indices.to(self.device, torch.int64).contiguous()
-    mod = ModSpec(n_mod=B, seqs_per_mod=1)
-    if not self.causal:
-      mod.sigma = sigma.to(self.device, torch.float32).reshape(-1).contiguous()
-      mod.sigma_row_stride = 1
-    if cond is not None:
-      mod.labels = cond.to(self.device, torch.int64).contiguous()
+    mod = self._mod_spec(sigma, B, labels=cond)
     logits = self.alloc_logits(B * L)
     self.run(ids, B, L, mod, logits, stats_out=stats_out,
              stats_mask_col=stats_mask_col)
@@ -433,18 +447,15 @@ class DIT:
 
   __call__ = forward
 
-  def classify(self, indices, sigma, round_bf16=True):
+  def classify(self, indices, sigma, round_bf16=True, seqs_per_mod: int = 1):
     """`Classifier.get_log_probs` for token ids (classifier.py:316-327 over
-    models/dit.py:516-556): (n, L) ids -> (n, num_classes) fp32 log-probs."""
+    models/dit.py:516-556): (n, L) ids -> (n, num_classes) fp32 log-probs.
+    `sigma` holds one value per `seqs_per_mod` consecutive sequences (exact D-CBG:
+    the L * V single-token edits of one sequence share its sigma)."""
     assert self.classifier
     n, L = indices.shape
     ids = indices.to(self.device, torch.int64).contiguous()
-    mod = ModSpec(n_mod=n, seqs_per_mod=1)
-    if not self.causal:
-      mod.sigma = sigma.to(self.device, torch.float32).reshape(-1).contiguous()
-      mod.sigma_row_stride = 1 if mod.sigma.numel() > 1 else 0
-      if mod.sigma.numel() == 1:
-        mod.n_mod, mod.seqs_per_mod = 1, n
+    mod = self._mod_spec(sigma, n, seqs_per_mod=seqs_per_mod)
     x = self.run(ids, n, L, mod)
     out = torch.empty(n, self.num_classes, dtype=torch.float32,
                       device=self.device)
@@ -467,12 +478,7 @@ class DIT:
     dev, s = self.device, stream_ptr()
     bcode = _lib.DTYPE_CODE[self.block_dtype]
     ids = indices.to(dev, torch.int64).contiguous()
-    mod = ModSpec(n_mod=n, seqs_per_mod=1)
-    if not self.causal:
-      mod.sigma = sigma.to(dev, torch.float32).reshape(-1).contiguous()
-      mod.sigma_row_stride = 1 if mod.sigma.numel() > 1 else 0
-      if mod.sigma.numel() == 1:
-        mod.n_mod, mod.seqs_per_mod = 1, n
+    mod = self._mod_spec(sigma, n)
     saved = []
     x = self.run(ids, n, L, mod, save_for_backward=saved)
     ws = self._ws

@@ -1,5 +1,5 @@
-"""Kernel-time breakdown of one QM9-shaped first-order D-CBG step (torch profiler / CUPTI).
-`python scripts/profile_cbg.py [B]`"""
+"""Kernel-time breakdown of one QM9-shaped D-CBG step (torch profiler / CUPTI).
+`python scripts/profile_cbg.py [B] [exact]`  (default: first-order, B = 4096)"""
 import os
 import sys
 
@@ -14,7 +14,9 @@ import ddg_b200
 def main():
   B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
   dev = torch.device('cuda', 0)
-  over, _, steps = config_sweep.CBG_CONFIGS['C4 QM9 cbg first-order B=4096']
+  exact = len(sys.argv) > 2 and sys.argv[2] == 'exact'
+  over, _, steps = config_sweep.CBG_CONFIGS[
+    'C4 QM9 cbg exact B=64' if exact else 'C4 QM9 cbg first-order B=4096']
   cfg = ddg_b200.compose(list(over) + [f'sampling.batch_size={B}', f'sampling.steps={steps}'])
   tok = config_sweep.Qm9Tok()
   model = ddg_b200.Diffusion(cfg, tok, device=dev).load_state_dict(
