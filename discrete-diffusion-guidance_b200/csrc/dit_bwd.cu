@@ -92,22 +92,90 @@ __global__ void gate_mul_kernel(const float* __restrict__ g, const T* __restrict
   }
 }
 
+// 16-bit pairs <-> fp32
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t w);
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t w) {
+  return __half22float2(*reinterpret_cast<__half2*>(&w));
+}
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 8 columns per thread (hidden % 8 == 0, 16-byte aligned rows): two 128-bit loads of g, one
+// of the gate row, one 128-bit store; one row division per 8 elements.  Same per-element
+// arithmetic as the scalar kernel above.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gate_mul_vec_kernel(const float* __restrict__ g, const T* __restrict__ gate, int64_t gate_stride,
+                    int64_t rows_per_mod, int64_t rows, int hidden, T* __restrict__ out) {
+  const int vec_per_row = hidden >> 3;
+  const int64_t n8 = rows * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / vec_per_row;
+    const int col = (int)(i - row * vec_per_row) << 3;
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(g + row * hidden + col));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(g + row * hidden + col) + 1);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (gate) {
+      const uint4 gw = __ldg(reinterpret_cast<const uint4*>(gate + (row / rows_per_mod) * gate_stride + col));
+      const uint32_t w[4] = {gw.x, gw.y, gw.z, gw.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack2<T>(w[k]);
+        v[2 * k] *= f.x;
+        v[2 * k + 1] *= f.y;
+      }
+    }
+    uint4 o;
+    o.x = pack2<T>(v[0], v[1]); o.y = pack2<T>(v[2], v[3]); o.z = pack2<T>(v[4], v[5]); o.w = pack2<T>(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + row * hidden + col) = o;
+  }
+}
+
 // ---------------------------------------------------------------- GELU'(pre) * g
+// d/dv [0.5 v (1 + tanh u)],  u = sqrt(2/pi) (v + 0.044715 v^3)   (models/dit.py:243)
+__device__ __forceinline__ float gelu_tanh_grad(float v) {
+  const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+  const float t = tanhf(u);
+  const float du = 0.7978845608028654f * (1.f + 3.f * 0.044715f * v * v);
+  return 0.5f * (1.f + t) + 0.5f * v * (1.f - t * t) * du;
+}
 template <typename T>
 __global__ void gelu_bwd_kernel(const T* __restrict__ g_h, const T* __restrict__ pre, T* __restrict__ out, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float v = Cvt<T>::to_f32(pre[i]);
-    const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
-    const float t = tanhf(u);
-    const float du = 0.7978845608028654f * (1.f + 3.f * 0.044715f * v * v);
-    const float d = 0.5f * (1.f + t) + 0.5f * v * (1.f - t * t) * du;
-    out[i] = Cvt<T>::from_f32(Cvt<T>::to_f32(g_h[i]) * d);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = Cvt<T>::from_f32(Cvt<T>::to_f32(g_h[i]) * gelu_tanh_grad(Cvt<T>::to_f32(pre[i])));
+}
+// 8 elements per thread, 128-bit loads / stores (n % 8 == 0, 16-byte aligned pointers)
+template <typename T>
+__global__ void __launch_bounds__(256)
+gelu_bwd_vec_kernel(const T* __restrict__ g_h, const T* __restrict__ pre, T* __restrict__ out, int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 gw = __ldcs(reinterpret_cast<const uint4*>(g_h) + i);
+    const uint4 pw = __ldcs(reinterpret_cast<const uint4*>(pre) + i);
+    const uint32_t a[4] = {gw.x, gw.y, gw.z, gw.w}, b[4] = {pw.x, pw.y, pw.z, pw.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 gg = unpack2<T>(a[k]), pp = unpack2<T>(b[k]);
+      o[k] = pack2<T>(gg.x * gelu_tanh_grad(pp.x), gg.y * gelu_tanh_grad(pp.y));
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
 // ---------------------------------------------------------------- LayerNorm + modulate backward
 // a = LN(x) * w * ops + shift  (models/dit.py:131-139, 47-50);  g_resid += d a / d x ^T g_a.
-template <typename T, int MAXV>
+// EXACT: hidden == 128 * MAXV (the loops unroll fully and no register is held for unused slots)
+template <typename T, int MAXV, bool EXACT = false>
 __global__ void __launch_bounds__(256)
 ln_modulate_bwd_kernel(const float* __restrict__ x, const T* __restrict__ g_a, int64_t rows, int hidden,
                        const float* __restrict__ ln_w, const T* __restrict__ ops, int64_t mod_stride,
@@ -115,7 +183,7 @@ ln_modulate_bwd_kernel(const float* __restrict__ x, const T* __restrict__ g_a, i
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const int nv = hidden >> 7;
+  const int nv = EXACT ? MAXV : hidden >> 7;
   float4 v[MAXV], gh[MAXV];
   float sum = 0.f;
 #pragma unroll
@@ -140,12 +208,13 @@ ln_modulate_bwd_kernel(const float* __restrict__ x, const T* __restrict__ g_a, i
     if (i < nv) {
       const int col = (i * 32 + lane) * 4;
       const float4 w4 = *reinterpret_cast<const float4*>(ln_w + col);
-      const T* gp = g_a + row * (int64_t)hidden + col;
-      float gv[4] = {Cvt<T>::to_f32(gp[0]) * w4.x, Cvt<T>::to_f32(gp[1]) * w4.y, Cvt<T>::to_f32(gp[2]) * w4.z,
-                     Cvt<T>::to_f32(gp[3]) * w4.w};
+      const uint2 gw = *reinterpret_cast<const uint2*>(g_a + row * (int64_t)hidden + col);   // 4 x 16-bit
+      const float2 g01 = unpack2<T>(gw.x), g23 = unpack2<T>(gw.y);
+      float gv[4] = {g01.x * w4.x, g01.y * w4.y, g23.x * w4.z, g23.y * w4.w};
       if (sc) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) gv[e] *= Cvt<T>::to_f32(sc[col + e]);
+        const uint2 sw = *reinterpret_cast<const uint2*>(sc + col);
+        const float2 s01 = unpack2<T>(sw.x), s23 = unpack2<T>(sw.y);
+        gv[0] *= s01.x; gv[1] *= s01.y; gv[2] *= s23.x; gv[3] *= s23.y;
       }
       v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;      // nhat
       gh[i] = make_float4(gv[0], gv[1], gv[2], gv[3]);
@@ -348,6 +417,19 @@ extern "C" int ddg_gate_mul(const float* g, const void* gate, int64_t gate_strid
   DDG_REQUIRE(g && out && rows >= 0 && hidden > 0 && (!gate || rows_per_mod > 0), DDG_ERR_INVALID, "gate_mul: bad args");
   if (rows == 0) return DDG_OK;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool vec = hidden % 8 == 0 && gate_stride % 8 == 0 && reinterpret_cast<uintptr_t>(g) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(gate) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  if (vec && (dtype == DDG_F16 || dtype == DDG_BF16)) {
+    const unsigned vgrid = (unsigned)grid_for(rows * (hidden / 8));
+    if (dtype == DDG_F16)
+      gate_mul_vec_kernel<__half><<<vgrid, 256, 0, s>>>(g, reinterpret_cast<const __half*>(gate), gate_stride,
+                                                        rows_per_mod, rows, hidden, reinterpret_cast<__half*>(out));
+    else
+      gate_mul_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, s>>>(g, reinterpret_cast<const __nv_bfloat16*>(gate),
+                                                               gate_stride, rows_per_mod, rows, hidden,
+                                                               reinterpret_cast<__nv_bfloat16*>(out));
+    return check_cuda(cudaGetLastError(), "gate_mul launch");
+  }
   const unsigned grid = (unsigned)grid_for(rows * hidden);
   if (dtype == DDG_F16)
     gate_mul_kernel<__half><<<grid, 256, 0, s>>>(g, reinterpret_cast<const __half*>(gate), gate_stride, rows_per_mod,
@@ -367,6 +449,20 @@ extern "C" int ddg_gelu_backward(const void* g_h, const void* pre, void* out, in
   DDG_REQUIRE(g_h && pre && out && n >= 0, DDG_ERR_INVALID, "gelu_backward: bad args");
   if (n == 0) return DDG_OK;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool vec = n % 8 == 0 && reinterpret_cast<uintptr_t>(g_h) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(pre) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  if (vec && (dtype == DDG_F16 || dtype == DDG_BF16)) {
+    const unsigned vgrid = (unsigned)grid_for(n / 8);
+    if (dtype == DDG_F16)
+      gelu_bwd_vec_kernel<__half><<<vgrid, 256, 0, s>>>(reinterpret_cast<const __half*>(g_h),
+                                                        reinterpret_cast<const __half*>(pre),
+                                                        reinterpret_cast<__half*>(out), n / 8);
+    else
+      gelu_bwd_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(g_h),
+                                                               reinterpret_cast<const __nv_bfloat16*>(pre),
+                                                               reinterpret_cast<__nv_bfloat16*>(out), n / 8);
+    return check_cuda(cudaGetLastError(), "gelu_backward launch");
+  }
   const unsigned grid = (unsigned)grid_for(n);
   if (dtype == DDG_F16)
     gelu_bwd_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(g_h),
@@ -387,6 +483,9 @@ extern "C" int ddg_ln_modulate_backward(const float* x, const void* g_a, int64_t
   DDG_REQUIRE(x && g_a && ln_weight && g_resid && rows >= 0, DDG_ERR_INVALID, "ln_modulate_backward: bad args");
   DDG_REQUIRE(hidden % 128 == 0 && hidden >= 128 && hidden <= 2048, DDG_ERR_UNSUPPORTED,
               "ln_modulate_backward: hidden=%d must be a multiple of 128 in [128, 2048]", hidden);
+  DDG_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(g_resid) % 16 == 0 &&
+              reinterpret_cast<uintptr_t>(g_a) % 8 == 0 && reinterpret_cast<uintptr_t>(one_plus_scale) % 8 == 0 &&
+              mod_stride % 4 == 0, DDG_ERR_INVALID, "ln_modulate_backward: pointer alignment / mod_stride");
   if (rows == 0) return DDG_OK;
   const unsigned grid = (unsigned)((rows + 7) / 8);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -394,12 +493,21 @@ extern "C" int ddg_ln_modulate_backward(const float* x, const void* g_a, int64_t
   ln_modulate_bwd_kernel<T, MAXV><<<grid, 256, 0, s>>>(x, reinterpret_cast<const T*>(g_a), rows, hidden,     \
                                                        ln_weight, reinterpret_cast<const T*>(one_plus_scale), \
                                                        mod_stride, rows_per_mod, g_resid)
+#define DDG_LNB_EXACT(T, NV)                                                                                  \
+  ln_modulate_bwd_kernel<T, NV, true><<<grid, 256, 0, s>>>(x, reinterpret_cast<const T*>(g_a), rows, hidden,   \
+                                                           ln_weight, reinterpret_cast<const T*>(one_plus_scale), \
+                                                           mod_stride, rows_per_mod, g_resid)
   if (dtype == DDG_F16) {
-    if (hidden <= 1024) DDG_LNB_LAUNCH(__half, 8); else DDG_LNB_LAUNCH(__half, 16);
+    if (hidden == 512) DDG_LNB_EXACT(__half, 4);
+    else if (hidden == 768) DDG_LNB_EXACT(__half, 6);
+    else if (hidden <= 1024) DDG_LNB_LAUNCH(__half, 8); else DDG_LNB_LAUNCH(__half, 16);
   } else if (dtype == DDG_BF16) {
-    if (hidden <= 1024) DDG_LNB_LAUNCH(__nv_bfloat16, 8); else DDG_LNB_LAUNCH(__nv_bfloat16, 16);
+    if (hidden == 512) DDG_LNB_EXACT(__nv_bfloat16, 4);
+    else if (hidden == 768) DDG_LNB_EXACT(__nv_bfloat16, 6);
+    else if (hidden <= 1024) DDG_LNB_LAUNCH(__nv_bfloat16, 8); else DDG_LNB_LAUNCH(__nv_bfloat16, 16);
   } else { set_error("ln_modulate_backward: dtype must be f16 or bf16"); return DDG_ERR_INVALID; }
 #undef DDG_LNB_LAUNCH
+#undef DDG_LNB_EXACT
   return check_cuda(cudaGetLastError(), "ln_modulate_backward launch");
 }
 

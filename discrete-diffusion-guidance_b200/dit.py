@@ -297,12 +297,15 @@ class DIT:
         x, n, h, ids_p if i == 0 else 0, period, ptr(self.embedding),
         ptr(self.ln1[i]), mb if ada else 0, mb + h * 2 if ada else 0,
         mod_stride, rpm, bcode, a16, s))
-      gemm(a16, h, ptr(self.w_qkv[i]), h, qkv, 3 * h, 3 * h, h,
+      qkv_i = qkv
+      if saved is not None:   # block input (set by the gather above for i == 0); the rotated
+        # QKV of this block is written straight into its own buffer (kept for the backward)
+        keep = torch.empty(n, 3 * h, dtype=self.block_dtype, device=self.device)
+        saved.append([ws['x'][:n].clone(), None, keep])
+        qkv_i = ptr(keep)
+      gemm(a16, h, ptr(self.w_qkv[i]), h, qkv_i, 3 * h, 3 * h, h,
            _lib.EPI_QKV_ROPE, bcode)
-      if saved is not None:   # block input (set by the gather above for i == 0) and rotated QKV
-        saved.append([ws['x'][:n].clone(), None,
-                      ws['qkv'][:n].view(self.block_dtype).clone()])
-      check(lib.ddg_attention(qkv, a16, n // L, L, self.n_heads, self.head_dim,
+      check(lib.ddg_attention(qkv_i, a16, n // L, L, self.n_heads, self.head_dim,
                               1 if self.causal else 0, bcode, s))
       gemm(a16, h, ptr(self.w_out[i]), h, x, h, h, h, _lib.EPI_GATE_RESIDUAL,
            bcode, gate=mb + 2 * h * 2 if ada else 0, gate_stride=mod_stride)

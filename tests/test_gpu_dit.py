@@ -499,3 +499,69 @@ def test_gemm_vocab_softmax_partials(mask_col):
   if mask_col >= 0:
     v[:, mask_col] = float('-inf')
   torch.testing.assert_close(lse, torch.logsumexp(v, -1), rtol=1e-5, atol=1e-4)
+
+
+# ---------------------------------------------------------------- first-order D-CBG: elementwise backward pieces
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('rows,hidden', [(4100, 512), (333, 768), (50, 132)])
+def test_gate_mul(dtype, rows, hidden):
+  """g (fp32) x adaLN gate row -> 16-bit (models/dit.py:20-35 backwards); the 8-wide
+  vector kernel (hidden % 8 == 0) and the scalar fallback (hidden = 132)."""
+  rpm = 100
+  g = torch.Generator().manual_seed(rows)
+  gr = torch.randn(rows, hidden, generator=g).to(DEV)
+  gate = torch.randn((rows + rpm - 1) // rpm, 2 * hidden + 8, generator=g).to(dtype).to(DEV)
+  out = torch.empty(rows, hidden, dtype=dtype, device=DEV)
+  gv = gate[:, 8:8 + hidden] if hidden % 8 == 0 else gate[:, 1:1 + hidden]
+  _lib.check(_lib.lib.ddg_gate_mul(gr.data_ptr(), gv.data_ptr(), gate.stride(0), rpm, rows, hidden,
+                                   _lib.DTYPE_CODE[dtype], out.data_ptr(), _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  ref = (gr * gv.float()[torch.arange(rows, device=DEV) // rpm]).to(dtype)
+  assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
+  _lib.check(_lib.lib.ddg_gate_mul(gr.data_ptr(), 0, 0, 0, rows, hidden, _lib.DTYPE_CODE[dtype],
+                                   out.data_ptr(), _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  assert torch.equal(out.view(torch.int16), gr.to(dtype).view(torch.int16))
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('n', [8 * 70001, 12345])
+def test_gelu_backward(dtype, n):
+  """g_h * GELU_tanh'(pre) against autograd in fp32 (vector kernel and scalar fallback)."""
+  g = torch.Generator().manual_seed(n)
+  pre = (torch.randn(n, generator=g) * 2).to(dtype).to(DEV)
+  gh = torch.randn(n, generator=g).to(dtype).to(DEV)
+  out = torch.empty(n, dtype=dtype, device=DEV)
+  _lib.check(_lib.lib.ddg_gelu_backward(gh.data_ptr(), pre.data_ptr(), out.data_ptr(), n,
+                                        _lib.DTYPE_CODE[dtype], _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  p32 = pre.float().requires_grad_(True)
+  torch.nn.functional.gelu(p32, approximate='tanh').backward(gh.float())
+  rtol, atol = _tol(dtype)
+  torch.testing.assert_close(out.float(), p32.grad.to(dtype).float(), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('hidden', [512, 768])
+@pytest.mark.parametrize('ada', [True, False])
+def test_ln_modulate_backward(dtype, hidden, ada):
+  """g_resid += d[LN(x) * w * (1 + scale) + shift]/dx^T g_a against autograd in fp32."""
+  rows, rpm = 777, 100
+  g = torch.Generator().manual_seed(hidden)
+  x = (torch.randn(rows, hidden, generator=g) * 1.5 + 0.2).to(DEV)
+  ga = torch.randn(rows, hidden, generator=g).to(dtype).to(DEV)
+  lnw = (1 + 0.1 * torch.randn(hidden, generator=g)).to(DEV)
+  ops = (1 + 0.3 * torch.randn((rows + rpm - 1) // rpm, 2 * hidden, generator=g)).to(dtype).to(DEV)
+  opv = ops[:, hidden:]
+  g0 = torch.randn(rows, hidden, generator=g).to(DEV)
+  gres = g0.clone()
+  _lib.check(_lib.lib.ddg_ln_modulate_backward(
+    x.data_ptr(), ga.data_ptr(), rows, hidden, lnw.data_ptr(), opv.data_ptr() if ada else 0,
+    ops.stride(0), rpm, _lib.DTYPE_CODE[dtype], gres.data_ptr(), _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  x32 = x.clone().requires_grad_(True)
+  y = torch.nn.functional.layer_norm(x32, [hidden]) * lnw
+  if ada:
+    y = y * opv.float()[torch.arange(rows, device=DEV) // rpm]
+  y.backward(ga.float())
+  torch.testing.assert_close(gres, g0 + x32.grad, rtol=2e-4, atol=2e-4)
