@@ -374,9 +374,17 @@ template <typename T> __device__ __forceinline__ constexpr uint32_t idesc(int n,
          ((uint32_t)(128 >> 4) << 24);
 }
 
-template <typename T>
+// LSEQ = 128: one item = one (sequence, head).  LSEQ = 32 / 64 (packed short sequences):
+// one item = 128 consecutive token rows = 128 / LSEQ whole sequences of one head.  The
+// tensor core still forms the full 128 x 128 score tile, but a query row only keeps the
+// LSEQ keys of its own sequence: thread = row reads just those 32-column chunks of S out
+// of tensor memory, the other chunks of P are written as zeros, and O = P V is then the
+// per-sequence attention.  The extra MMA work is free (the kernel is HBM-bound) and the
+// HBM traffic per token is that of the 128-long case.  total_rows bounds a ragged last item.
+template <typename T, int LSEQ>
 __global__ void __launch_bounds__(160, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__ out, int H, int n_items) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__ out, int H, int n_items,
+                    int64_t total_rows) {
   extern __shared__ uint8_t sm_raw[];
   const uint32_t sm_base = (static_cast<uint32_t>(__cvta_generic_to_shared(sm_raw)) + 1023u) & ~1023u;
   uint8_t* sm_gen = sm_raw + (sm_base - static_cast<uint32_t>(__cvta_generic_to_shared(sm_raw)));
@@ -459,9 +467,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
       const int bb = item / H, hh = item % H;
       mbar_wait(b_s, ph);
       tc_fence_after();
+      // key chunks (32 columns each) of this warp's rows: all 4, or those of its own sequence
+      constexpr int CPS = LSEQ / 32;                    // chunks per sequence
+      const int c_lo = (warp / CPS) * CPS, c_hi = c_lo + CPS;
       float m = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = c_lo; c < c_hi; ++c) {
         uint32_t r[32];
         tmem_ld32_sync(tm_s + lane_addr + (uint32_t)(c * 32), r);
 #pragma unroll
@@ -472,15 +483,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
       if (it > 0) mbar_wait(b_o, ph ^ 1);               // P of the previous item has been consumed
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32_sync(tm_s + lane_addr + (uint32_t)(c * 32), r);
         uint32_t w[16];
+        if (c >= c_lo && c < c_hi) {                      // warp-uniform
+          uint32_t r[32];
+          tmem_ld32_sync(tm_s + lane_addr + (uint32_t)(c * 32), r);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), kScale2, -msc));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), kScale2, -msc));
-          l += p0 + p1;
-          w[i] = Mma<T>::pack(p0, p1);
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), kScale2, -msc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), kScale2, -msc));
+            l += p0 + p1;
+            w[i] = Mma<T>::pack(p0, p1);
+          }
+        } else {                                          // keys of the other sequences of the item
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[i] = 0u;
         }
         // keys 32c .. 32c+31 of row `row`: tile c / 2, 16-byte chunks 4 (c & 1) .. + 3, swizzled
         const uint32_t tile = sp + (uint32_t)(c >> 1) * TILE + (uint32_t)row * 128u;
@@ -523,7 +539,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
         uint4 v;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                      : "r"(so + (uint32_t)(warp * 32 + r) * 128u + ((uint32_t)(ch ^ (r & 7)) << 4)) : "memory");
-        *reinterpret_cast<uint4*>(obase + (int64_t)r * H * 64 + ch * 8) = v;
+        if (LSEQ == L_TC || (int64_t)bb * L_TC + warp * 32 + r < total_rows)
+          *reinterpret_cast<uint4*>(obase + (int64_t)r * H * 64 + ch * 8) = v;
       }
       __syncwarp();
     }
@@ -564,22 +581,30 @@ int launch_attention_k(const void* qkv, void* out, int batch, int L, int H, int 
 
 template <typename T, bool CAUSAL>
 int launch_attention(const void* qkv, void* out, int batch, int L, int H, int dtype, cudaStream_t s) {
-  if (!CAUSAL && L == tc::L_TC) {     // tensor-memory kernel for the benchmark shape
-    static bool attr_done[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-      DDG_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TC));
-      attr_done[dev] = true;
-    }
+  if (!CAUSAL && (L == tc::L_TC || L == 64 || L == 32) && (int64_t)batch * L >= tc::L_TC) {
+    // tensor-memory kernel: the benchmark shape, and short sequences packed 128 rows per item
     CUtensorMap map;
     const int64_t cols = (int64_t)3 * H * 64;
-    int rc = make_tma_rows64(&map, qkv, (int64_t)batch * L, cols, cols, L, dtype);
+    const int64_t rows = (int64_t)batch * L;
+    int rc = make_tma_rows64(&map, qkv, rows, cols, cols, tc::L_TC, dtype);
     if (rc) return rc;
-    const int n_items = batch * H;
+    const int n_items = (int)((rows + tc::L_TC - 1) / tc::L_TC) * H;
     int grid = sm_count() * 2;
     if (grid > n_items) grid = n_items;
-    tc::attention_tc_kernel<T><<<grid, 160, tc::SMEM_TC, s>>>(map, reinterpret_cast<T*>(out), H, n_items);
+    int dev = 0;
+    cudaGetDevice(&dev);
+#define DDG_TC_LAUNCH(LSEQ)                                                                                   \
+  {                                                                                                           \
+    static bool attr_done[64] = {false};                                                                      \
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {                                                            \
+      DDG_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<T, LSEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    tc::SMEM_TC));                                                            \
+      attr_done[dev] = true;                                                                                  \
+    }                                                                                                         \
+    tc::attention_tc_kernel<T, LSEQ><<<grid, 160, tc::SMEM_TC, s>>>(map, reinterpret_cast<T*>(out), H, n_items, rows); \
+  }
+    if (L == tc::L_TC) DDG_TC_LAUNCH(128) else if (L == 64) DDG_TC_LAUNCH(64) else DDG_TC_LAUNCH(32)
+#undef DDG_TC_LAUNCH
     return check_cuda(cudaGetLastError(), "attention_tc launch");
   }
   if (!CAUSAL && L % 64 == 0) return launch_attention_k<T, false, true>(qkv, out, batch, L, H, dtype, s);

@@ -167,6 +167,27 @@ def test_attention(L, dtype, causal):
                              rtol=rtol, atol=atol)
 
 
+@pytest.mark.parametrize('L,B', [(32, 9), (32, 64), (64, 5), (64, 32), (128, 7)])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+def test_attention_tensor_memory_kernel_packed_sequences(L, B, dtype):
+  """Non-causal L in {32, 64, 128} with >= 128 token rows runs the tcgen05 kernel; short
+  sequences are packed 128 rows per item and each query keeps only the keys of its own
+  sequence.  Ragged last items (B * L not a multiple of 128) and many items per CTA."""
+  H = 8
+  g = torch.Generator().manual_seed(L * 1000 + B)
+  qkv = (torch.randn(B * L, 3 * H * 64, generator=g) * 1.5).to(dtype)
+  out = torch.full((B * L + 64, H * 64), 9.0, dtype=dtype, device=DEV)   # guard rows behind the end
+  qd = qkv.to(DEV)
+  _lib.check(_lib.lib.ddg_attention(qd.data_ptr(), out.data_ptr(), B, L, H, 64, 0,
+                                    _lib.DTYPE_CODE[dtype], _lib.stream_ptr()))
+  torch.cuda.synchronize()
+  v = qkv.float().view(B, L, 3, H, 64)
+  ref = ref_dit._attention(v[:, :, 0], v[:, :, 1], v[:, :, 2], False, dtype)
+  rtol, atol = _tol(dtype)
+  torch.testing.assert_close(out[:B * L].float().cpu().view(B, L, H, 64), ref, rtol=rtol, atol=atol)
+  assert bool((out[B * L:] == 9.0).all()), 'rows past the last sequence must stay untouched'
+
+
 @pytest.mark.parametrize('L', [16, 24, 32, 48, 64, 100, 128, 160])
 @pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize('causal', [False, True])
