@@ -325,7 +325,8 @@ namespace tc {
 
 constexpr int L_TC = 128;
 constexpr int TILE = L_TC * 128;                  // one 128 x 64 16-bit tile
-constexpr int SMEM_TC = 6 * TILE + 1024 + 128;     // q k v p0 p1 out + align slack + barriers
+// q, NK x k, NK x v, 2 NK x p, out tiles + align slack + barriers (NK = 128-key tiles per sequence)
+constexpr int smem_tc(int nk) { return (2 + 4 * nk) * TILE + 1024 + 128; }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -381,18 +382,23 @@ template <typename T> __device__ __forceinline__ constexpr uint32_t idesc(int n,
 // of tensor memory, the other chunks of P are written as zeros, and O = P V is then the
 // per-sequence attention.  The extra MMA work is free (the kernel is HBM-bound) and the
 // HBM traffic per token is that of the 128-long case.  total_rows bounds a ragged last item.
+// LSEQ = 256: one item = one 128-query tile of a (sequence, head) against all 256 keys
+// (NK = 2 key tiles: S is 128 x 256 in tensor memory, P four 64-column tiles, one CTA per SM).
 template <typename T, int LSEQ>
-__global__ void __launch_bounds__(160, 2)
+__global__ void __launch_bounds__(160, LSEQ > 128 ? 1 : 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__ out, int H, int n_items,
                     int64_t total_rows) {
+  constexpr int NK = LSEQ > L_TC ? LSEQ / L_TC : 1;      // 128-key tiles
+  constexpr int NKEY = NK * L_TC;
+  constexpr uint32_t TMEM_COLS = NK == 1 ? 256u : 512u;  // S (NKEY) + O (64), power of two
   extern __shared__ uint8_t sm_raw[];
   const uint32_t sm_base = (static_cast<uint32_t>(__cvta_generic_to_shared(sm_raw)) + 1023u) & ~1023u;
   uint8_t* sm_gen = sm_raw + (sm_base - static_cast<uint32_t>(__cvta_generic_to_shared(sm_raw)));
-  const uint32_t sq = sm_base, sk = sq + TILE, sv = sk + TILE, sp = sv + TILE, so = sp + 2 * TILE;
+  const uint32_t sq = sm_base, sk = sq + TILE, sv = sk + NK * TILE, sp = sv + NK * TILE, so = sp + 2 * NK * TILE;
   const uint32_t bars = so + TILE;
   // barriers (8 B each): 0 qk_full, 1 v_full, 2 s_full, 3 p_ready (128), 4 o_full, 5 o_read (128)
   const uint32_t b_qk = bars, b_v = bars + 8, b_s = bars + 16, b_p = bars + 24, b_o = bars + 32, b_r = bars + 40;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm_gen + 6 * TILE + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm_gen + (2 + 4 * NK) * TILE + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -403,28 +409,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                   static_cast<uint32_t>(__cvta_generic_to_shared(tmem_slot))), "r"(256u) : "memory");
+                   static_cast<uint32_t>(__cvta_generic_to_shared(tmem_slot))), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_s = tmem_base, tm_o = tmem_base + 128;
+  const uint32_t tm_s = tmem_base, tm_o = tmem_base + NKEY;
+  // item -> (first query row, first key row, head).  NK == 1: 128 consecutive rows are both.
+  auto item_rows = [&](int item, int& q0, int& k0, int& hh) {
+    hh = item % H;
+    const int t = item / H;
+    if (NK == 1) { q0 = k0 = t * L_TC; }
+    else { q0 = t * L_TC; k0 = (t / NK) * NKEY; }
+  };
 
   if (warp == 4) {
     if (lane == 0) {
-      constexpr uint32_t id_s = idesc<T>(128, 0), id_o = idesc<T>(64, 1);
+      constexpr uint32_t id_s = idesc<T>(NKEY, 0), id_o = idesc<T>(64, 1);
       auto load_qk = [&](int item) {
-        const int bb = item / H, hh = item % H;
-        mbar_expect_tx(b_qk, 2 * TILE);
-        tma_load_2d(&tma_qkv, b_qk, sq, hh * 64, bb * L_TC);
-        tma_load_2d(&tma_qkv, b_qk, sk, (H + hh) * 64, bb * L_TC);
+        int q0, k0, hh;
+        item_rows(item, q0, k0, hh);
+        mbar_expect_tx(b_qk, (1 + NK) * TILE);
+        tma_load_2d(&tma_qkv, b_qk, sq, hh * 64, q0);
+#pragma unroll
+        for (int t = 0; t < NK; ++t) tma_load_2d(&tma_qkv, b_qk, sk + t * TILE, (H + hh) * 64, k0 + t * L_TC);
       };
       auto load_v = [&](int item) {
-        const int bb = item / H, hh = item % H;
-        mbar_expect_tx(b_v, TILE);
-        tma_load_2d(&tma_qkv, b_v, sv, (2 * H + hh) * 64, bb * L_TC);
+        int q0, k0, hh;
+        item_rows(item, q0, k0, hh);
+        mbar_expect_tx(b_v, NK * TILE);
+#pragma unroll
+        for (int t = 0; t < NK; ++t) tma_load_2d(&tma_qkv, b_v, sv + t * TILE, (2 * H + hh) * 64, k0 + t * L_TC);
       };
       if ((int)blockIdx.x < n_items) { load_qk(blockIdx.x); load_v(blockIdx.x); }
       int it = 0;
@@ -447,7 +464,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
         if (it > 0) mbar_wait(b_r, ph ^ 1);           // previous O has been read out of tensor memory
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < 8 * NK; ++k)
           umma_f16(tm_o, smem_desc(sp + (k >> 2) * TILE) + (uint64_t)(2 * (k & 3)),
                    smem_desc(sv) + (uint64_t)(k * 128), id_o, (uint32_t)(k != 0));
         umma_commit(b_o);
@@ -464,10 +481,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
-      const int bb = item / H, hh = item % H;
+      int q0, k0_unused, hh;
+      item_rows(item, q0, k0_unused, hh);
       mbar_wait(b_s, ph);
       tc_fence_after();
-      // key chunks (32 columns each) of this warp's rows: all 4, or those of its own sequence
+      // key chunks (32 columns each) of this warp's rows: all of them, or those of its own sequence
+      constexpr int NCH = 4 * NK;                       // chunks of the score tile
       constexpr int CPS = LSEQ / 32;                    // chunks per sequence
       const int c_lo = (warp / CPS) * CPS, c_hi = c_lo + CPS;
       float m = -INFINITY;
@@ -482,7 +501,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
       float l = 0.f;
       if (it > 0) mbar_wait(b_o, ph ^ 1);               // P of the previous item has been consumed
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NCH; ++c) {
         uint32_t w[16];
         if (c >= c_lo && c < c_hi) {                      // warp-uniform
           uint32_t r[32];
@@ -531,7 +550,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
                      "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
       }
       __syncwarp();
-      T* obase = out + ((int64_t)bb * L_TC + warp * 32) * ((int64_t)H * 64) + (int64_t)hh * 64;
+      T* obase = out + ((int64_t)q0 + warp * 32) * ((int64_t)H * 64) + (int64_t)hh * 64;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int cidx = i * 32 + lane;                  // 256 chunks: 32 rows x 8
@@ -539,7 +558,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
         uint4 v;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                      : "r"(so + (uint32_t)(warp * 32 + r) * 128u + ((uint32_t)(ch ^ (r & 7)) << 4)) : "memory");
-        if (LSEQ == L_TC || (int64_t)bb * L_TC + warp * 32 + r < total_rows)
+        if (LSEQ >= L_TC || (int64_t)q0 + warp * 32 + r < total_rows)
           *reinterpret_cast<uint4*>(obase + (int64_t)r * H * 64 + ch * 8) = v;
       }
       __syncwarp();
@@ -549,7 +568,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -581,15 +600,16 @@ int launch_attention_k(const void* qkv, void* out, int batch, int L, int H, int 
 
 template <typename T, bool CAUSAL>
 int launch_attention(const void* qkv, void* out, int batch, int L, int H, int dtype, cudaStream_t s) {
-  if (!CAUSAL && (L == tc::L_TC || L == 64 || L == 32) && (int64_t)batch * L >= tc::L_TC) {
-    // tensor-memory kernel: the benchmark shape, and short sequences packed 128 rows per item
+  if (!CAUSAL && (L == 256 || L == tc::L_TC || L == 64 || L == 32) && (int64_t)batch * L >= tc::L_TC) {
+    // tensor-memory kernel: the benchmark shape, short sequences packed 128 rows per item,
+    // and 256-token sequences as two query tiles against 256 keys
     CUtensorMap map;
     const int64_t cols = (int64_t)3 * H * 64;
     const int64_t rows = (int64_t)batch * L;
     int rc = make_tma_rows64(&map, qkv, rows, cols, cols, tc::L_TC, dtype);
     if (rc) return rc;
     const int n_items = (int)((rows + tc::L_TC - 1) / tc::L_TC) * H;
-    int grid = sm_count() * 2;
+    int grid = sm_count() * (L > tc::L_TC ? 1 : 2);
     if (grid > n_items) grid = n_items;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -598,12 +618,14 @@ int launch_attention(const void* qkv, void* out, int batch, int L, int H, int dt
     static bool attr_done[64] = {false};                                                                      \
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {                                                            \
       DDG_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<T, LSEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    tc::SMEM_TC));                                                            \
+                                    tc::smem_tc(LSEQ > 128 ? LSEQ / 128 : 1)));                               \
       attr_done[dev] = true;                                                                                  \
     }                                                                                                         \
-    tc::attention_tc_kernel<T, LSEQ><<<grid, 160, tc::SMEM_TC, s>>>(map, reinterpret_cast<T*>(out), H, n_items, rows); \
+    tc::attention_tc_kernel<T, LSEQ><<<grid, 160, tc::smem_tc(LSEQ > 128 ? LSEQ / 128 : 1), s>>>(               \
+      map, reinterpret_cast<T*>(out), H, n_items, rows);                                                      \
   }
-    if (L == tc::L_TC) DDG_TC_LAUNCH(128) else if (L == 64) DDG_TC_LAUNCH(64) else DDG_TC_LAUNCH(32)
+    if (L == 256) DDG_TC_LAUNCH(256) else if (L == tc::L_TC) DDG_TC_LAUNCH(128)
+    else if (L == 64) DDG_TC_LAUNCH(64) else DDG_TC_LAUNCH(32)
 #undef DDG_TC_LAUNCH
     return check_cuda(cudaGetLastError(), "attention_tc launch");
   }

@@ -167,12 +167,13 @@ def test_attention(L, dtype, causal):
                              rtol=rtol, atol=atol)
 
 
-@pytest.mark.parametrize('L,B', [(32, 9), (32, 64), (64, 5), (64, 32), (128, 7)])
+@pytest.mark.parametrize('L,B', [(32, 9), (32, 64), (64, 5), (64, 32), (128, 7), (256, 5), (256, 80)])
 @pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
 def test_attention_tensor_memory_kernel_packed_sequences(L, B, dtype):
-  """Non-causal L in {32, 64, 128} with >= 128 token rows runs the tcgen05 kernel; short
+  """Non-causal L in {32, 64, 128, 256} with >= 128 token rows runs the tcgen05 kernel; short
   sequences are packed 128 rows per item and each query keeps only the keys of its own
-  sequence.  Ragged last items (B * L not a multiple of 128) and many items per CTA."""
+  sequence; 256-token sequences are two query tiles against 256 keys.  Ragged last items
+  (B * L not a multiple of 128) and many items per CTA."""
   H = 8
   g = torch.Generator().manual_seed(L * 1000 + B)
   qkv = (torch.randn(B * L, 3 * H * 64, generator=g) * 1.5).to(dtype)
