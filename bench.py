@@ -166,6 +166,8 @@ def build_model(batch, device, seed):
   sd = ddg_b200.weights.random_state_dict(cfg, V, seed=1)
   model = ddg_b200.Diffusion(cfg, BertTok(), device=device).load_state_dict(sd)
   model.seed = seed
+  if os.environ.get('DDG_RACE_GROUP'):             # sampler A/B knob (0 | 8 | 64)
+    model.race_group = int(os.environ['DDG_RACE_GROUP'])
   seg = int(os.environ.get('DDG_SEG_SEQS', '0'))   # micro-batch experiment knob
   if seg > 0:
     model.backbone.seg_seqs = seg

@@ -305,8 +305,8 @@ int launch_sample_group(int mode, const ddg_sample_step_args& a, cudaStream_t s)
 // Returns 1 if the fused single-pass kernel took the call, 0 if the generic
 // kernel must, negative on error.
 int try_sample_fused(const ddg_sample_step_args& a, cudaStream_t s) {
-  if (a.race_group != 0 && a.race_group != 8) {
-    set_error("sample_step: race_group must be 0 or 8 (got %d)", a.race_group);
+  if (a.race_group != 0 && a.race_group != 8 && a.race_group != 64) {
+    set_error("sample_step: race_group must be 0, 8 or 64 (got %d)", a.race_group);
     return DDG_ERR_INVALID;
   }
   if (!a.stats_a || a.stats_chunks <= 0 || a.logits_dtype != DDG_BF16 || a.q_out || a.clf) return 0;
@@ -325,7 +325,7 @@ int try_sample_fused(const ddg_sample_step_args& a, cudaStream_t s) {
   } else if (a.diffusion == DDG_ABSORBING && a.guidance == DDG_GUIDE_NONE && a.subs && a.mask_logit)
     mode = F_ABS_NONE;   // stats must have been built with stats_mask_col = mask_index
   else return 0;
-  if (a.race_group == 8 && !a.noise) {
+  if (a.race_group != 0 && !a.noise) {
     const int rcg = launch_sample_group(mode, a, s);   // hierarchical race (Philox only)
     return rcg ? rcg : 1;
   }

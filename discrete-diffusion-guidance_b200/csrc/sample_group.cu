@@ -36,6 +36,18 @@
 //                      word (G >> 8) & 3,  U = (word >> 8) * 2^-24,
 //                      E = 1e-10 - ln(U + 1e-10)
 //   in-group pick:     counter = (G, row_lo, row_hi | 0x80000000, step), word 0
+//
+// race_group = 64 (WIDE): a group is any SET of columns, it need not be contiguous.  Here
+// it is the 8 vectors one thread touches in one sweep of its unrolled loop: with vector
+// index v = j / 8, slot t = v % 128, kk = v / 128, sweep k8 = kk / 8, the group is
+// G = k8 * 128 + t and holds columns 8 (t + 128 (8 k8 + s)) + e, s, e = 0..7 (64 columns,
+// pick order (s, e)).  Memory access is unchanged; the per-group work (Philox, the two lg2
+// of the exponential, the lg2 of the sum, the compare) is paid once per 64 columns instead
+// of once per 8, which removes a third of the kernel's instructions.  The in-group pick is
+// done by 64 threads (one column each) with a shuffle scan.
+//   group exponential: counter = (t | ((k8 >> 2) << 8), row_lo, row_hi | 0x40000000, step),
+//                      word k8 & 3
+//   in-group pick:     counter = (G, row_lo, row_hi | 0x80000000, step), word 0
 #include "ddg_common.cuh"
 
 namespace ddg {
@@ -315,7 +327,90 @@ __device__ __forceinline__ void row_pass(const RowConst& c, const uint4* va, con
   }
 }
 
+// ---- WIDE (race_group = 64): linear / log2 sum of the 8 ordinary columns of one vector
 template <int MODE, bool ROUND>
+__device__ __forceinline__ float vec_sum_lin(const RowConst& c, const uint4& ra, const uint4& rb, const float* A,
+                                             const float* B, uint32_t neg_base2) {
+  float2 va[4];
+  lut_gather(ra, c.Ka, A, neg_base2, va);
+  float2 acc;
+  if (MODE == G_UNI_CFG) {
+    float2 vb[4];
+    lut_gather(rb, c.Kb, B, neg_base2, vb);
+    acc = make_float2(va[0].x * vb[0].x, va[0].y * vb[0].y);
+#pragma unroll
+    for (int p = 1; p < 4; ++p) acc = fma2(va[p], vb[p], acc);
+  } else {
+    acc = add2(add2(va[0], va[1]), add2(va[2], va[3]));
+  }
+  return acc.x + acc.y;
+}
+
+// log2-domain accumulator (max, sum of 2^(v - max)) for the non-linear paths
+struct LogAcc {
+  float m = -INFINITY, s = 0.f;
+  __device__ __forceinline__ void add(float v) {        // v = log2 of a non-negative term (may be -inf)
+    if (!(v > -INFINITY)) return;
+    const float nm = fmaxf(m, v);
+    s = s * ex2a(m - nm) + ex2a(v - nm);                // m = -inf: s = 0 * 0 + 1
+    m = nm;
+  }
+  __device__ __forceinline__ float value() const { return m + lg2a(s); }   // -inf + lg2(0) = NaN never wins
+};
+
+__device__ __forceinline__ uint4 wide_noise_words(int t, int quad, int64_t row, int step, uint2 key) {
+  return philox4x32_10(make_uint4((uint32_t)(t | (quad << 8)), (uint32_t)row,
+                                  (uint32_t)((uint64_t)row >> 32) | 0x40000000u, (uint32_t)step), key);
+}
+
+// One pass over the row, one score per 64-column group (see the header).  extra0 / extra1:
+// contribution of the careful vectors this thread owns (z / mask vector, ragged tail) to its
+// sweep ek0 / ek1 -- linear units (LIN) or log2 (otherwise); neutral on the other threads.
+template <int MODE, bool ROUND, bool LIN>
+__device__ __forceinline__ void row_pass_wide(const RowConst& c, const uint4* va, const uint4* vb, uint4 ra0,
+                                              uint4 rb0, uint4 ra1, uint4 rb1, const float* A, const float* B,
+                                              uint32_t neg_base2, int n_full, int n_vec, int special_vec,
+                                              int64_t row, int step, uint2 key, float extra0, int ek0, float extra1,
+                                              int ek1, float& best, int& bgrp) {
+  const int tid = threadIdx.x;
+  uint4 ra[2] = {ra0, ra1}, rb[2] = {rb0, rb1};
+  uint4 nw = make_uint4(0, 0, 0, 0);
+  for (int k8 = 0; tid + k8 * (8 * kThreads) < n_vec; ++k8) {
+    if ((k8 & 3) == 0) nw = wide_noise_words(tid, k8 >> 2, row, step, key);
+    float lin_sum = 0.f;
+    LogAcc lacc;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int vi = tid + (k8 * 8 + s) * kThreads;
+      if (vi >= n_full) break;
+      float v;
+      if (LIN) v = vec_sum_lin<MODE, ROUND>(c, ra[s & 1], rb[s & 1], A, B, neg_base2);
+      else v = group_hot<MODE, ROUND, false>(c, ra[s & 1], rb[s & 1], A, B, neg_base2);
+      {                                               // reload this buffer for two vectors ahead (clamped)
+        const uint32_t off = (uint32_t)min(vi + 2 * kThreads, n_full - 1) << 4;
+        ra[s & 1] = ldg_stream(reinterpret_cast<const char*>(va) + off);
+        if (MODE == G_UNI_CFG) rb[s & 1] = ldg_stream(reinterpret_cast<const char*>(vb) + off);
+      }
+      if (vi != special_vec) {
+        if (LIN) lin_sum += v; else lacc.add(v);
+      }
+    }
+    float lsum;
+    if (LIN) {
+      lin_sum += (k8 == ek0 ? extra0 : 0.f) + (k8 == ek1 ? extra1 : 0.f);
+      lsum = lg2a(lin_sum);                           // lg2(0) = -inf: an empty group never wins
+    } else {
+      if (k8 == ek0) lacc.add(extra0);
+      if (k8 == ek1) lacc.add(extra1);
+      lsum = lacc.value();
+    }
+    const uint32_t w = (k8 & 3) == 0 ? nw.x : (k8 & 3) == 1 ? nw.y : (k8 & 3) == 2 ? nw.z : nw.w;
+    const float sc = lsum + neg_log2_E(u01_from_bits(w));
+    if (sc > best) { best = sc; bgrp = k8 * kThreads + tid; }
+  }
+}
+
+template <int MODE, bool ROUND, bool WIDE>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 sample_group_kernel(const ddg_sample_step_args a) {
   constexpr int NT = MODE == G_UNI_CFG ? 2 : 1;        // logits tensors
@@ -326,6 +421,8 @@ sample_group_kernel(const ddg_sample_step_args a) {
   __shared__ float s_red[kWarps];
   __shared__ int s_idx[kWarps];
   __shared__ int s_win;
+  __shared__ float s_pick_f[4];
+  __shared__ int s_pick_i[4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = a.vocab;
   const int step = a.step_ptr ? *a.step_ptr : a.step;
@@ -337,7 +434,7 @@ sample_group_kernel(const ddg_sample_step_args a) {
   const bool stage = a.stats_chunks <= kMaxChunks;
   // a value the compiler cannot fold (race_group == 8 on this path), so the constant
   // lives in one register instead of being re-materialised in front of every VIADDMNMX
-  const uint32_t neg_base2 = kNegBase2 ^ (uint32_t)(a.race_group ^ 8);
+  const uint32_t neg_base2 = kNegBase2 ^ (uint32_t)(a.race_group ^ (WIDE ? 64 : 8));
   float tab_mct = -1.f, tab_mcs = -1.f;     // schedule scalars the table was built for
   bool tab_ready = false, lin = true;
   float goff = 0.f;                          // row-constant offset of the linear tables (log2)
@@ -481,11 +578,43 @@ sample_group_kernel(const ddg_sample_step_args a) {
     }
     const int special_grp = special >> 3;
 
+    float best = -INFINITY;
+    int bgrp = 0x7fffffff;
+    if (WIDE) {
+      // ---- careful vectors (the one holding z / the mask column, the ragged tail) are left
+      // out of the hot sums and added to their owner thread's group here
+      const int n_vec = n_groups;
+      const int special_vec = special_grp;
+      float extra[2];
+      int ek[2];
+      const bool use_lin = ROUND && lin;
+#pragma unroll
+      for (int sp = 0; sp < 2; ++sp) {
+        const int vec = sp == 0 ? special_vec : n_full;
+        const bool exists = sp == 0 || (n_full != n_groups && special_vec != n_full);
+        extra[sp] = use_lin ? 0.f : -INFINITY;
+        ek[sp] = -1;
+        if (exists && tid == (vec & (kThreads - 1))) {
+          const uint4 ca = __ldg(va + (vec - tid));
+          const uint4 cb = MODE == G_UNI_CFG ? __ldg(vb + (vec - tid)) : ca;
+          float g[8];
+          group_careful<MODE, ROUND>(c, ca, cb, vec * 8, g);
+          const float gm = max8(g);
+          if (gm > -INFINITY) {
+            const float lg = (gm - goff) + lg2a(sum_ex2_8(g, gm));
+            extra[sp] = use_lin ? ex2a(lg) : lg;
+            ek[sp] = (vec / kThreads) >> 3;
+          }
+        }
+      }
+      if (use_lin)
+        row_pass_wide<MODE, ROUND, true>(c, reinterpret_cast<const uint4*>(pa), reinterpret_cast<const uint4*>(pb), ra0, rb0, ra1, rb1, s_A, s_B, neg_base2, n_full, n_vec, special_vec, row, step, key, extra[0], ek[0], extra[1], ek[1], best, bgrp);
+      else
+        row_pass_wide<MODE, ROUND, false>(c, reinterpret_cast<const uint4*>(pa), reinterpret_cast<const uint4*>(pb), ra0, rb0, ra1, rb1, s_A, s_B, neg_base2, n_full, n_vec, special_vec, row, step, key, extra[0], ek[0], extra[1], ek[1], best, bgrp);
+    } else {
     // ---- one pass over the row: per full group of 8 columns, log2(sum q~) - log2(E).
     // The group holding z / the mask column is evaluated too (branch-free) but its
     // score is discarded there and redone on the careful path below.
-    float best = -INFINITY;
-    int bgrp = 0x7fffffff;
     if (ROUND && lin)
       row_pass<MODE, ROUND, true>(c, reinterpret_cast<const uint4*>(pa), reinterpret_cast<const uint4*>(pb), ra0, rb0, ra1, rb1, s_A, s_B, neg_base2, n_full, special_grp, row, step, key, best, bgrp);
     else
@@ -508,6 +637,7 @@ sample_group_kernel(const ddg_sample_step_args a) {
           if (sc > best || (sc == best && G < bgrp)) { best = sc; bgrp = G; }
         }
       }
+    }
     }
     // ---- block argmax over groups, lowest group index wins ties
 #pragma unroll
@@ -533,6 +663,58 @@ sample_group_kernel(const ddg_sample_step_args a) {
     const int win = s_win;
     if (win == 0x7fffffff) {
       if (tid == 0) a.xs[row] = 0;                      // all-zero row: cannot happen with finite logits
+      if (WIDE) { __syncthreads(); __syncthreads(); }   // keep the barrier count of the pick below
+    } else if (WIDE) {
+      // ---- inverse-CDF pick inside the winning 64-column group: thread i < 64 takes column
+      // (s, e) = (i / 8, i % 8); shuffle scan inside each of the two warps, offsets through smem
+      const int wt = win & (kThreads - 1), wk8 = win / kThreads;
+      float g = -INFINITY;
+      int j = 0;
+      if (tid < 64) {
+        const int vi = wt + kThreads * (8 * wk8 + (tid >> 3));
+        j = vi * 8 + (tid & 7);
+        if (j < V) {
+          const float la = __bfloat162float(pa[j]);
+          const float lb = MODE == G_UNI_CFG ? __bfloat162float(pb[j]) : 0.f;
+          g = g_elem<MODE, ROUND>(c, la, lb, j);
+        }
+      }
+      const float wm = warp_max(g);
+      if (lane == 0 && warp < 2) s_pick_f[warp] = wm;
+      __syncthreads();                                   // P1
+      const float gm = fmaxf(s_pick_f[0], s_pick_f[1]);
+      const float pr = (tid < 64 && g > -INFINITY) ? ex2a(g - gm) : 0.f;
+      float cum = pr;                                    // inclusive scan inside the warp
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float up = __shfl_up_sync(0xffffffffu, cum, o);
+        if (lane >= o) cum += up;
+      }
+      if (lane == 31 && warp < 2) s_pick_f[2 + warp] = cum;
+      __syncthreads();                                   // P2
+      if (tid < 64) {
+        const float S = s_pick_f[2] + s_pick_f[3];
+        if (warp == 1) cum += s_pick_f[2];
+        const uint4 r2 = philox4x32_10(
+          make_uint4((uint32_t)win, (uint32_t)row, (uint32_t)((uint64_t)row >> 32) | 0x80000000u, (uint32_t)step), key);
+        const float target = u01_from_bits(r2.x) * S;
+        const uint32_t hit = __ballot_sync(0xffffffffu, cum > target);
+        const uint32_t pos = __ballot_sync(0xffffffffu, pr > 0.f);
+        // first column whose running sum passes the target, else (rounding) the last positive one
+        if (lane == 0) {
+          s_pick_i[warp] = hit ? __ffs(hit) - 1 : -1;
+          s_pick_i[2 + warp] = pos ? 31 - __clz(pos) : -1;
+        }
+      }
+      __syncthreads();                                   // P3
+      if (tid == 0) {
+        int i;
+        if (s_pick_i[0] >= 0) i = s_pick_i[0];
+        else if (s_pick_i[1] >= 0) i = 32 + s_pick_i[1];
+        else if (s_pick_i[3] >= 0) i = 32 + s_pick_i[3];
+        else i = s_pick_i[2] >= 0 ? s_pick_i[2] : 0;
+        a.xs[row] = (int64_t)(wt + kThreads * (8 * wk8 + (i >> 3))) * 8 + (i & 7);
+      }
     } else if (tid == (win & (kThreads - 1))) {
       // ---- inverse-CDF pick inside the winning group
       const uint4 ca = __ldg(va + (win - tid));
@@ -567,13 +749,16 @@ template <int MODE, bool ROUND>
 int launch(const ddg_sample_step_args& a, cudaStream_t s) {
   int64_t grid = (int64_t)sm_count() * kCtasPerSm * 2;     // two waves of resident CTAs
   if (grid > a.rows) grid = a.rows;
-  sample_group_kernel<MODE, ROUND><<<(unsigned)grid, kThreads, 0, s>>>(a);
+  if (a.race_group == 64)
+    sample_group_kernel<MODE, ROUND, true><<<(unsigned)grid, kThreads, 0, s>>>(a);
+  else
+    sample_group_kernel<MODE, ROUND, false><<<(unsigned)grid, kThreads, 0, s>>>(a);
   return check_cuda(cudaGetLastError(), "sample_group launch");
 }
 
 }  // namespace
 
-// Called by try_sample_fused once alignment / stats have been validated.
+// Called by try_sample_fused once alignment / stats have been validated (race_group 8 or 64).
 int launch_sample_group(int mode, const ddg_sample_step_args& a, cudaStream_t s) {
   switch (mode * 2 + (a.round_bf16 ? 1 : 0)) {
     case 0: return launch<G_UNI_NONE, false>(a, s);

@@ -61,9 +61,10 @@ class Diffusion:
     self.ar_kv_cache = True     # AR sampler: incremental decode against a KV
                                 # cache; False = re-encode the prefix per
                                 # token like the reference (diffusion.py:1132)
-    self.race_group = 8         # Philox path: hierarchical race over 8-column
-                                # groups (same distribution, 8x less noise
-                                # work); 0 = one exponential per vocab entry
+    self.race_group = 64        # Philox path: hierarchical race over 64-column
+                                # groups (same distribution, 64x less noise
+                                # work); 8 = 8-column groups; 0 = one
+                                # exponential per vocab entry
     self.return_q_xs = False    # materialise q_xs (B, L, V) fp32 per step
     self.use_cuda_graph = True
     self.noise_fn = None        # i -> injected U (B, L, V); None -> Philox

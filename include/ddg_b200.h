@@ -128,7 +128,12 @@ typedef struct ddg_sample_step_args {
    *      columns, argmax over groups of (sum_G q) / E_G, then an inverse-CDF
    *      pick inside the winning group.  Identical distribution (min of
    *      independent exponentials), 8x less noise work; needs the stats_*
-   *      partials, bf16 logits and fast_math.  Other values: DDG_ERR_INVALID. */
+   *      partials, bf16 logits and fast_math.
+   *  64  the same with 64-column groups made of the 8 vectors (of 8 columns)
+   *      one thread of the kernel visits in a sweep: columns
+   *      8 (t + 128 (8 k + s)) + e, s, e = 0..7, for group k * 128 + t.  Same
+   *      distribution again (a group may be any set of columns); the per-group
+   *      work is paid once per 64 columns.  Other values: DDG_ERR_INVALID.    */
   int32_t race_group;
   /* 1: sampling.use_float64 (diffusion.py:1393-1394, 1110-1111, 1134-1135): the
    * log-probs keep the forward's precision, everything after them runs in

@@ -416,11 +416,17 @@ def group_race_select(probs, seed, step, group=8, threads=256):
   q_j over a group is Exp(sum q_j), and the arg-min inside the group is
   q_j / sum q_j independent of the minimum.
 
+  group=8: groups of 8 consecutive columns.  group=64: the kernel's strided
+  64-column groups (`group_race_select_wide`).
+
   probs: (rows, V) non-negative, any common scale per row.  Returns a dict:
   ids (rows,), group scores (rows, n_groups) in log2 units, and for the winning
   group the in-group cumulative sums / target so that a test can tell a real
-  mismatch from a near-tie."""
+  mismatch from a near-tie; `cols` (rows, group) = the columns of the winning
+  group in pick order (-1 = past the vocabulary)."""
   import numpy as np
+  if group == 64:
+    return group_race_select_wide(probs, seed, step)
   p = probs.detach().double().cpu().numpy()
   rows, V = p.shape
   nG = (V + group - 1) // group
@@ -451,5 +457,65 @@ def group_race_select(probs, seed, step, group=8, threads=256):
   cum = np.cumsum(pw, -1)
   target = u2 * cum[:, -1]
   pick = (cum > target[:, None]).argmax(-1)
+  cols = win[:, None] * group + np.arange(group)[None, :]
+  cols = np.where(cols < V, cols, -1)
   return dict(ids=torch.from_numpy(win * group + pick), score=score, win=win, cum=cum,
-              target=target, u2=u2)
+              target=target, u2=u2, cols=cols)
+
+
+def wide_group_columns(V, threads=128):
+  """Column map of the kernel's 64-column groups (race_group = 64): with vector index
+  v = j // 8, slot t = v % threads, kk = v // threads, sweep k8 = kk // 8, group
+  G = k8 * threads + t holds columns 8 (t + threads (8 k8 + s)) + e in pick order
+  (s, e).  Returns (n_groups, 64) int64 with -1 past the vocabulary."""
+  import numpy as np
+  n_vec = (V + 7) // 8
+  n_k8 = (n_vec + 8 * threads - 1) // (8 * threads)
+  G = np.arange(n_k8 * threads, dtype=np.int64)
+  t, k8 = G % threads, G // threads
+  s = np.arange(8, dtype=np.int64)
+  e = np.arange(8, dtype=np.int64)
+  v = t[:, None] + threads * (8 * k8[:, None] + s[None, :])           # (nG, 8)
+  cols = (8 * v[:, :, None] + e[None, None, :]).reshape(len(G), 64)
+  return np.where(cols < V, cols, -1)
+
+
+def group_race_select_wide(probs, seed, step, threads=128):
+  """`group_race_select` for the strided 64-column groups of race_group = 64
+  (csrc/sample_group.cu, WIDE): group exponential from Philox counter
+  (t | ((k8 >> 2) << 8), row_lo, row_hi | 0x40000000, step), word k8 & 3; in-group
+  pick from counter (G, row_lo, row_hi | 0x80000000, step), word 0."""
+  import numpy as np
+  p = probs.detach().double().cpu().numpy()
+  rows, V = p.shape
+  cols = wide_group_columns(V, threads)                              # (nG, 64)
+  nG = cols.shape[0]
+  pg = np.where(cols[None] >= 0, p[:, np.maximum(cols, 0)], 0.0)     # (rows, nG, 64)
+  S = pg.sum(-1)
+  G = np.arange(nG, dtype=np.int64)[None, :]
+  t, k8 = G % threads, G // threads
+  r = np.arange(rows, dtype=np.uint64)[:, None]
+  row_lo = (r & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+  row_hi = (r >> np.uint64(32)).astype(np.uint32)
+  k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+  ctr0 = (t | ((k8 >> 2) << 8)).astype(np.uint32)
+  words = np.stack(philox4x32_10(ctr0, row_lo, row_hi | np.uint32(0x40000000),
+                                 np.uint32(step & 0xFFFFFFFF), k0, k1), -1)
+  sel = (k8 & 3).astype(np.int64)
+  w = np.take_along_axis(words, np.broadcast_to(sel[..., None], (rows, nG, 1)), -1)[..., 0]
+  U = (w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+  E = 1e-10 - np.log(U.astype(np.float64) + 1e-10)
+  with np.errstate(divide='ignore'):
+    score = np.log2(S) - np.log2(E)
+  win = score.argmax(-1)
+  pw = pg[np.arange(rows), win]                                      # (rows, 64)
+  w2 = philox4x32_10(win.astype(np.uint32), row_lo[:, 0],
+                     row_hi[:, 0] | np.uint32(0x80000000), np.uint32(step & 0xFFFFFFFF), k0, k1)[0]
+  u2 = (w2 >> np.uint32(8)).astype(np.float32).astype(np.float64) * 2.0 ** -24
+  cum = np.cumsum(pw, -1)
+  target = u2 * cum[:, -1]
+  pick = (cum > target[:, None]).argmax(-1)
+  wcols = cols[win]                                                  # (rows, 64)
+  ids = wcols[np.arange(rows), pick]
+  return dict(ids=torch.from_numpy(ids), score=score, win=win, cum=cum, target=target,
+              u2=u2, cols=wcols)

@@ -29,7 +29,10 @@ def main():
   mct = torch.tensor([0.5], device=dev)
   mcs = torch.tensor([0.499], device=dev)
   bytes_cfg = rows * (2 * V * 2 + 16)
-  for name, kw in (('group cfg round', dict(race_group=8, guidance=_lib.GUIDE_CFG, round_bf16=1)),
+  for name, kw in (('wide cfg round', dict(race_group=64, guidance=_lib.GUIDE_CFG, round_bf16=1)),
+                   ('wide cfg exact', dict(race_group=64, guidance=_lib.GUIDE_CFG, round_bf16=0)),
+                   ('wide null round', dict(race_group=64, guidance=_lib.GUIDE_NONE, round_bf16=1)),
+                   ('group cfg round', dict(race_group=8, guidance=_lib.GUIDE_CFG, round_bf16=1)),
                    ('group cfg exact', dict(race_group=8, guidance=_lib.GUIDE_CFG, round_bf16=0)),
                    ('group null round', dict(race_group=8, guidance=_lib.GUIDE_NONE, round_bf16=1)),
                    ('column cfg round', dict(race_group=0, guidance=_lib.GUIDE_CFG, round_bf16=1))):

@@ -433,7 +433,8 @@ def _oracle_probs(la, lb, xt, mc_t, mc_s, V, diffusion, guidance, gamma, round_b
 
 @pytest.mark.parametrize('diffusion,guidance', FUSED_MODES)
 @pytest.mark.parametrize('round_bf16', [True, False])
-def test_group_race_matches_cpu_restatement(diffusion, guidance, round_bf16):
+@pytest.mark.parametrize('race_group', [8, 64])
+def test_group_race_matches_cpu_restatement(diffusion, guidance, round_bf16, race_group):
   """Production kernel (hierarchical race, in-kernel Philox) against the CPU
   restatement fed with the oracle's posterior and the regenerated Philox
   stream: ids bit-equal except near-ties -- a different group only if the two
@@ -454,10 +455,10 @@ def test_group_race_matches_cpu_restatement(diffusion, guidance, round_bf16):
     gamma=2.0, subs=subs, mask_logit=subs, mask_index=103, round_bf16=round_bf16,
     fast_math=True, seed=seed, step=step, stats_a=st_a.data_ptr(),
     stats_b=st_b.data_ptr() if guidance == 'cfg' else 0, stats_ld=rows,
-    stats_chunks=st_a.shape[0], race_group=8)
+    stats_chunks=st_a.shape[0], race_group=race_group)
   xs = xs.cpu()
   q = _oracle_probs(la, lb, xt, mc_t, mc_s, V, diffusion, guidance, 2.0, round_bf16)
-  ref = ref_sampler.group_race_select(q.view(rows, V), seed, step)
+  ref = ref_sampler.group_race_select(q.view(rows, V), seed, step, group=race_group)
   ids_ref = ref['ids']
   xt_flat = xt.view(-1)
   if subs:     # carry-over rows keep their token (diffusion.py:1414-1418)
@@ -466,14 +467,20 @@ def test_group_race_matches_cpu_restatement(diffusion, guidance, round_bf16):
     ids_ref = torch.where(keep, xt_flat, ids_ref)
   tol = 3e-2 if round_bf16 else 2e-3
   bad = (xs != ids_ref).nonzero().flatten().tolist()
+  def group_of(j):      # group index of column j
+    if race_group == 8:
+      return j // 8
+    v = j // 8
+    return ((v // 128) // 8) * 128 + v % 128
   for r in bad:
-    gg, gr = int(xs[r]) // 8, int(ids_ref[r]) // 8
+    gg, gr = group_of(int(xs[r])), group_of(int(ids_ref[r]))
     if gg != gr:
       gap = abs(ref['score'][r, gg] - ref['score'][r, gr])
       assert gap <= tol, f'row {r}: groups {gg} vs {gr}, score gap {gap:.3e}'
     else:
       cum, tgt = ref['cum'][r], ref['target'][r]
-      lo, hi = sorted((int(xs[r]) % 8, int(ids_ref[r]) % 8))
+      cols = ref['cols'][r].tolist()
+      lo, hi = sorted((cols.index(int(xs[r])), cols.index(int(ids_ref[r]))))
       edge = cum[lo:hi]
       assert (abs(edge - tgt) <= tol * cum[-1]).all(), f'row {r}: in-group pick not a near-tie'
   assert len(bad) <= max(2, rows // 16), f'{len(bad)} near-ties of {rows}'
@@ -506,12 +513,13 @@ def test_group_race_statistics(diffusion, guidance, round_bf16):
     step=3, stats_a=st_a.data_ptr(), stats_b=st_b.data_ptr() if guidance == 'cfg' else 0,
     stats_ld=n, stats_chunks=st_a.shape[0])
   xs_grp, _ = helpers.sampler_kernel(race_group=8, **common)
+  xs_wide, _ = helpers.sampler_kernel(race_group=64, **common)
   xs_col, _ = helpers.sampler_kernel(race_group=0, **common)
   q = _oracle_probs(ra[None], rb[None], xt[:1, None], torch.tensor([0.8]), torch.tensor([0.3]),
                     V, diffusion, guidance, 2.0, round_bf16)[0, 0].double()
   q = q / q.sum()
   top = q.topk(60).indices
-  for xs, what in ((xs_grp, 'group'), (xs_col, 'column')):
+  for xs, what in ((xs_grp, 'group'), (xs_wide, 'wide group'), (xs_col, 'column')):
     counts = torch.bincount(xs.cpu(), minlength=V).double()
     exp = q[top] * n
     zs = (counts[top] - exp) / (exp * (1 - q[top])).clamp_min(1).sqrt()
@@ -520,7 +528,8 @@ def test_group_race_statistics(diffusion, guidance, round_bf16):
     assert abs(rest - rest_exp) < 5 * max(rest_exp, 1) ** 0.5, (what, rest, rest_exp)
 
 
-def test_group_race_full_size_properties():
+@pytest.mark.parametrize('race_group', [8, 64])
+def test_group_race_full_size_properties(race_group):
   """Config-3 sized launch (64 x 128 rows of 30522) through the production
   kernel: ids in range, absorbing carry-over exact, deterministic for a fixed
   Philox key and different for another key."""
@@ -534,7 +543,7 @@ def test_group_race_full_size_properties():
   common = dict(logits_a=la, logits_b=lb, xt=xt, mc_t=0.5, mc_s=0.499, vocab=V, seq_len=128,
                 diffusion='uniform', guidance='cfg', gamma=2.0, round_bf16=True, fast_math=True,
                 stats_a=st_a.data_ptr(), stats_b=st_b.data_ptr(), stats_ld=rows,
-                stats_chunks=st_a.shape[0], race_group=8)
+                stats_chunks=st_a.shape[0], race_group=race_group)
   a1, _ = helpers.sampler_kernel(seed=1, step=5, **common)
   a2, _ = helpers.sampler_kernel(seed=1, step=5, **common)
   a3, _ = helpers.sampler_kernel(seed=2, step=5, **common)

@@ -111,19 +111,34 @@ def test_oracle_mdlm_resolves_all_masks():
   assert (out == cases.Tok(case.vocab).mask_token_id).float().mean().item() < 0.05
 
 
-def test_group_race_restatement_is_a_categorical_draw():
+def test_wide_group_columns_partition_the_vocabulary():
+  """race_group = 64: the strided 64-column groups cover every column exactly once."""
+  import numpy as np
+  from oracle import ref_sampler
+  for V in (30522, 4096, 2051, 40):
+    cols = ref_sampler.wide_group_columns(V)
+    live = cols[cols >= 0]
+    assert live.size == V and np.array_equal(np.sort(live), np.arange(V))
+    assert cols.shape[1] == 64
+  c = ref_sampler.wide_group_columns(30522)
+  assert c[0, :9].tolist() == [0, 1, 2, 3, 4, 5, 6, 7, 1024]      # (s, e) order, 128 vectors apart
+  assert c[129, 0] == 8 * (1 + 128 * 8)                            # t = 1, sweep 1
+
+
+@pytest.mark.parametrize('group', [8, 64])
+def test_group_race_restatement_is_a_categorical_draw(group):
   """oracle.group_race_select (the CPU restatement of the production
   sampler's hierarchical exponential race) reproduces the categorical
   distribution it is given, and is a pure function of (seed, step, row)."""
   import torch
   from oracle import ref_sampler
-  V, n = 83, 30000            # ragged last group (83 = 10 * 8 + 3)
+  V, n = (83, 30000) if group == 8 else (2051, 30000)   # ragged last group / vector
   g = torch.Generator().manual_seed(0)
   q = torch.softmax(torch.randn(V, generator=g) * 2, 0)
   q[5] = 0.0
-  r1 = ref_sampler.group_race_select(q[None].repeat(n, 1), 12345, 7)
-  r2 = ref_sampler.group_race_select(q[None].repeat(n, 1), 12345, 7)
-  r3 = ref_sampler.group_race_select(q[None].repeat(n, 1), 12345, 8)
+  r1 = ref_sampler.group_race_select(q[None].repeat(n, 1), 12345, 7, group=group)
+  r2 = ref_sampler.group_race_select(q[None].repeat(n, 1), 12345, 7, group=group)
+  r3 = ref_sampler.group_race_select(q[None].repeat(n, 1), 12345, 8, group=group)
   assert torch.equal(r1['ids'], r2['ids']) and not torch.equal(r1['ids'], r3['ids'])
   assert int(r1['ids'].max()) < V
   c = torch.bincount(r1['ids'], minlength=V).double()
