@@ -58,6 +58,9 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 constexpr int kCtasPerSm = 6;
+// resident CTAs per SM of the 64-column-group kernels (measured: 72 registers / 7 CTAs is the
+// best point for the two-forward D-CFG kernel, 64 / 8 for the one-forward ones)
+__host__ __device__ constexpr int wide_ctas(int mode) { return mode == 1 /* G_UNI_CFG */ ? 7 : 8; }
 constexpr int kLut = 2048;          // bf16 magnitudes 0x3B00 .. 0x42FF: |lp| in [2^-9, 128)
 constexpr int kLutBase = 0x3B00;
 constexpr int kMaxChunks = 256;     // softmax partials staged in smem (V <= 32768); else read from global
@@ -185,6 +188,18 @@ __device__ __forceinline__ float2 fma2(float2 x, float2 y, float2 z) {
   return r;
 }
 
+__device__ __forceinline__ float2 mul2(float2 x, float2 y) {
+  float2 r;
+  asm("{\n\t"
+      ".reg .b64 a, b, d;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "mul.f32x2 d, a, b;\n\t"
+      "mov.b64 {%0, %1}, d;\n\t"
+      "}" : "=f"(r.x), "=f"(r.y) : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y));
+  return r;
+}
+
 // Table byte offsets of a pair of differences d = lse - l >= 0: bf16 round,
 // (magnitude bits - 0x3B00) clamped to [0, 2047] with one DPX instruction for
 // the pair, times 4 (both halves at once: 4 * 2047 still fits 16 bits).
@@ -198,12 +213,13 @@ __device__ __forceinline__ uint32_t lut_offsets2(float d0, float d1, uint32_t ne
 __device__ __forceinline__ float lut_at(const float* T, uint32_t byte_off) {
   return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(T) + byte_off);
 }
-// table values of the four column pairs of one 16-byte vector
+// table values of the first NP column pairs of one 16-byte vector
+template <int NP = 4>
 __device__ __forceinline__ void lut_gather(const uint4& r, float K, const float* T, uint32_t neg_base2,
                                            float2 (&v)[4]) {
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
+  for (int p = 0; p < NP; ++p) {
     const float2 d = sub2(K, bf16_lo(w[p]), bf16_hi(w[p]));
     const uint32_t t = lut_offsets2(d.x, d.y, neg_base2);
     v[p] = make_float2(lut_at(T, t & 0xffffu), lut_at(T, t >> 16));
@@ -327,12 +343,44 @@ __device__ __forceinline__ void row_pass(const RowConst& c, const uint4* va, con
   }
 }
 
+// The first forward's factor of the linear tables by arithmetic instead of a lookup:
+// x = bf16(2^(-d log2 e)) exactly as the table builder forms it, d = bf16(lse - l); then
+// (dA x + c0)^2 (D-CFG with gamma == 2), dA x + c0 (UDLM without guidance) or x itself
+// (MDLM: dA = 1, c0 = 0).  The data-dependent shared-memory lookups are the pipe this kernel
+// is bound by: this moves half of them (all of them without guidance) to the XU / FMA pipes.
+// dA2 / c02 carry the table's scale (2^(-mA / 2) when squared, 2^-mA otherwise).
+template <bool SQUARE, int P0>
+__device__ __forceinline__ void cond_factor(const uint4& r, float K, float2 dA2, float2 c02, float2 (&v)[4]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  const float2 nl2e = make_float2(-kLog2e, -kLog2e);
+#pragma unroll
+  for (int p = P0; p < 4; ++p) {                      // column pairs P0 .. 3 (the others come from the table)
+    const float2 d = sub2(K, bf16_lo(w[p]), bf16_hi(w[p]));
+    const __nv_bfloat162 h = __floats2bfloat162_rn(d.x, d.y);      // d >= 0: lse >= every logit
+    const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 t = mul2(make_float2(bf16_lo(hw), bf16_hi(hw)), nl2e);
+    const __nv_bfloat162 xh = __floats2bfloat162_rn(ex2a(t.x), ex2a(t.y));
+    const uint32_t xw = *reinterpret_cast<const uint32_t*>(&xh);
+    const float2 a = fma2(make_float2(bf16_lo(xw), bf16_hi(xw)), dA2, c02);
+    v[p] = SQUARE ? mul2(a, a) : a;
+  }
+}
+
 // ---- WIDE (race_group = 64): linear / log2 sum of the 8 ordinary columns of one vector
-template <int MODE, bool ROUND>
+template <int MODE, bool ROUND, bool A2 = false>
 __device__ __forceinline__ float vec_sum_lin(const RowConst& c, const uint4& ra, const uint4& rb, const float* A,
-                                             const float* B, uint32_t neg_base2) {
+                                             const float* B, uint32_t neg_base2, float2 dA2 = make_float2(0.f, 0.f),
+                                             float2 c02 = make_float2(0.f, 0.f)) {
   float2 va[4];
-  lut_gather(ra, c.Ka, A, neg_base2, va);
+  if (A2) {
+    // D-CFG: all four pairs by arithmetic (the second forward keeps the LSU busy); one forward
+    // only: two pairs from the table, two by arithmetic, so that LSU and XU share the row
+    constexpr int P0 = MODE == G_UNI_CFG ? 0 : 2;
+    if (P0 > 0) lut_gather<P0>(ra, c.Ka, A, neg_base2, va);
+    cond_factor<MODE == G_UNI_CFG, P0>(ra, c.Ka, dA2, c02, va);
+  } else {
+    lut_gather(ra, c.Ka, A, neg_base2, va);
+  }
   float2 acc;
   if (MODE == G_UNI_CFG) {
     float2 vb[4];
@@ -366,12 +414,13 @@ __device__ __forceinline__ uint4 wide_noise_words(int t, int quad, int64_t row, 
 // One pass over the row, one score per 64-column group (see the header).  extra0 / extra1:
 // contribution of the careful vectors this thread owns (z / mask vector, ragged tail) to its
 // sweep ek0 / ek1 -- linear units (LIN) or log2 (otherwise); neutral on the other threads.
-template <int MODE, bool ROUND, bool LIN>
+template <int MODE, bool ROUND, bool LIN, bool A2 = false>
 __device__ __forceinline__ void row_pass_wide(const RowConst& c, const uint4* va, const uint4* vb, uint4 ra0,
                                               uint4 rb0, uint4 ra1, uint4 rb1, const float* A, const float* B,
                                               uint32_t neg_base2, int n_full, int n_vec, int special_vec,
                                               int64_t row, int step, uint2 key, float extra0, int ek0, float extra1,
-                                              int ek1, float& best, int& bgrp) {
+                                              int ek1, float& best, int& bgrp, float dA2s = 0.f, float c02s = 0.f) {
+  const float2 dA2 = make_float2(dA2s, dA2s), c02 = make_float2(c02s, c02s);
   const int tid = threadIdx.x;
   uint4 ra[2] = {ra0, ra1}, rb[2] = {rb0, rb1};
   uint4 nw = make_uint4(0, 0, 0, 0);
@@ -384,7 +433,7 @@ __device__ __forceinline__ void row_pass_wide(const RowConst& c, const uint4* va
       const int vi = tid + (k8 * 8 + s) * kThreads;
       if (vi >= n_full) break;
       float v;
-      if (LIN) v = vec_sum_lin<MODE, ROUND>(c, ra[s & 1], rb[s & 1], A, B, neg_base2);
+      if (LIN) v = vec_sum_lin<MODE, ROUND, A2>(c, ra[s & 1], rb[s & 1], A, B, neg_base2, dA2, c02);
       else v = group_hot<MODE, ROUND, false>(c, ra[s & 1], rb[s & 1], A, B, neg_base2);
       {                                               // reload this buffer for two vectors ahead (clamped)
         const uint32_t off = (uint32_t)min(vi + 2 * kThreads, n_full - 1) << 4;
@@ -411,7 +460,7 @@ __device__ __forceinline__ void row_pass_wide(const RowConst& c, const uint4* va
 }
 
 template <int MODE, bool ROUND, bool WIDE>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+__global__ void __launch_bounds__(kThreads, WIDE ? wide_ctas(MODE) : kCtasPerSm)
 sample_group_kernel(const ddg_sample_step_args a) {
   constexpr int NT = MODE == G_UNI_CFG ? 2 : 1;        // logits tensors
   __shared__ __align__(16) float s_A[ROUND ? kLut : 4];
@@ -421,7 +470,7 @@ sample_group_kernel(const ddg_sample_step_args a) {
   __shared__ float s_red[kWarps];
   __shared__ int s_idx[kWarps];
   __shared__ int s_win;
-  __shared__ float s_pick_f[4];
+  __shared__ float s_pick_f[5];
   __shared__ int s_pick_i[4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = a.vocab;
@@ -438,6 +487,7 @@ sample_group_kernel(const ddg_sample_step_args a) {
   float tab_mct = -1.f, tab_mcs = -1.f;     // schedule scalars the table was built for
   bool tab_ready = false, lin = true;
   float goff = 0.f;                          // row-constant offset of the linear tables (log2)
+  float tab_mA = 0.f;                        // log2 scale of the conditional table
 
   // warp w < NT stages tensor w's partials of `row` into buffer `buf` (each lane copies what it reads later)
   auto prefetch_stats = [&](int64_t r, int b) {
@@ -510,7 +560,8 @@ sample_group_kernel(const ddg_sample_step_args a) {
     RowConst c;
     c.z = z; c.mask_index = a.mask_index; c.V = V;
     c.gam = a.gamma; c.omg = 1.f - a.gamma;
-    const int64_t mc_off = (row / a.seq_len) * a.mc_seq_stride + (int64_t)step * a.mc_step_stride;
+    const int64_t seq = a.rows <= 0x7fffffff ? (int64_t)((uint32_t)row / (uint32_t)a.seq_len) : row / a.seq_len;
+    const int64_t mc_off = seq * a.mc_seq_stride + (int64_t)step * a.mc_step_stride;
     const float mc_t = a.mc_t[mc_off], mc_s = a.mc_s[mc_off];
     float atV = 0.f, zoff = 0.f;
     if (MODE == G_ABS_NONE) {
@@ -543,6 +594,7 @@ sample_group_kernel(const ddg_sample_step_args a) {
             mB = fmaxf(__fmul_rn(c.omg, lq_hi), __fmul_rn(c.omg, lq_lo));
           }
           goff = lin ? mA + mB : 0.f;
+          tab_mA = mA;
         }
         for (int i = tid; i < kLut; i += kThreads) {
           const float mag = __uint_as_float((uint32_t)(kLutBase + i) << 16);
@@ -594,20 +646,31 @@ sample_group_kernel(const ddg_sample_step_args a) {
         const bool exists = sp == 0 || (n_full != n_groups && special_vec != n_full);
         extra[sp] = use_lin ? 0.f : -INFINITY;
         ek[sp] = -1;
-        if (exists && tid == (vec & (kThreads - 1))) {
-          const uint4 ca = __ldg(va + (vec - tid));
-          const uint4 cb = MODE == G_UNI_CFG ? __ldg(vb + (vec - tid)) : ca;
-          float g[8];
-          group_careful<MODE, ROUND>(c, ca, cb, vec * 8, g);
-          const float gm = max8(g);
-          if (gm > -INFINITY) {
-            const float lg = (gm - goff) + lg2a(sum_ex2_8(g, gm));
+        const int owner = vec & (kThreads - 1);
+        if (exists && warp == (owner >> 5)) {             // warp-uniform: the owner's warp, lane e % 8 = column e
+          const int j = vec * 8 + (lane & 7);             // rows are padded to whole vectors: in bounds
+          const float la = __bfloat162float(pa[j]);
+          const float lb = MODE == G_UNI_CFG ? __bfloat162float(pb[j]) : 0.f;
+          const float g = g_elem<MODE, ROUND>(c, la, lb, j);
+          float gm = g;
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+          float sm = gm > -INFINITY ? ex2a(g - gm) : 0.f;
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+          if (lane == (owner & 31) && gm > -INFINITY) {
+            const float lg = (gm - goff) + lg2a(sm);
             extra[sp] = use_lin ? ex2a(lg) : lg;
             ek[sp] = (vec / kThreads) >> 3;
           }
         }
       }
-      if (use_lin)
+      if (use_lin && (MODE != G_UNI_CFG || c.gam == 2.f)) {
+        // table scale: (dA x + c0)^2 / 2^mA = ((dA x + c0) 2^(-mA / 2))^2;  (dA x + c0) / 2^mA;  x
+        const float sc2 = MODE == G_UNI_CFG ? ex2a(-0.5f * tab_mA) : ex2a(-tab_mA);
+        const float dAs = MODE == G_ABS_NONE ? 1.f : c.dA * sc2, c0s = MODE == G_ABS_NONE ? 0.f : c.c0 * sc2;
+        row_pass_wide<MODE, ROUND, true, true>(c, reinterpret_cast<const uint4*>(pa), reinterpret_cast<const uint4*>(pb), ra0, rb0, ra1, rb1, s_A, s_B, neg_base2, n_full, n_vec, special_vec, row, step, key, extra[0], ek[0], extra[1], ek[1], best, bgrp, dAs, c0s);
+      } else if (use_lin)
         row_pass_wide<MODE, ROUND, true>(c, reinterpret_cast<const uint4*>(pa), reinterpret_cast<const uint4*>(pb), ra0, rb0, ra1, rb1, s_A, s_B, neg_base2, n_full, n_vec, special_vec, row, step, key, extra[0], ek[0], extra[1], ek[1], best, bgrp);
       else
         row_pass_wide<MODE, ROUND, false>(c, reinterpret_cast<const uint4*>(pa), reinterpret_cast<const uint4*>(pb), ra0, rb0, ra1, rb1, s_A, s_B, neg_base2, n_full, n_vec, special_vec, row, step, key, extra[0], ek[0], extra[1], ek[1], best, bgrp);
@@ -681,6 +744,11 @@ sample_group_kernel(const ddg_sample_step_args a) {
       }
       const float wm = warp_max(g);
       if (lane == 0 && warp < 2) s_pick_f[warp] = wm;
+      if (warp == 2) {                                   // idle in the pick: draws its uniform
+        const uint4 r2 = philox4x32_10(
+          make_uint4((uint32_t)win, (uint32_t)row, (uint32_t)((uint64_t)row >> 32) | 0x80000000u, (uint32_t)step), key);
+        if (lane == 0) s_pick_f[4] = u01_from_bits(r2.x);
+      }
       __syncthreads();                                   // P1
       const float gm = fmaxf(s_pick_f[0], s_pick_f[1]);
       const float pr = (tid < 64 && g > -INFINITY) ? ex2a(g - gm) : 0.f;
@@ -695,9 +763,7 @@ sample_group_kernel(const ddg_sample_step_args a) {
       if (tid < 64) {
         const float S = s_pick_f[2] + s_pick_f[3];
         if (warp == 1) cum += s_pick_f[2];
-        const uint4 r2 = philox4x32_10(
-          make_uint4((uint32_t)win, (uint32_t)row, (uint32_t)((uint64_t)row >> 32) | 0x80000000u, (uint32_t)step), key);
-        const float target = u01_from_bits(r2.x) * S;
+        const float target = s_pick_f[4] * S;
         const uint32_t hit = __ballot_sync(0xffffffffu, cum > target);
         const uint32_t pos = __ballot_sync(0xffffffffu, pr > 0.f);
         // first column whose running sum passes the target, else (rounding) the last positive one
@@ -747,7 +813,7 @@ sample_group_kernel(const ddg_sample_step_args a) {
 
 template <int MODE, bool ROUND>
 int launch(const ddg_sample_step_args& a, cudaStream_t s) {
-  int64_t grid = (int64_t)sm_count() * kCtasPerSm * 2;     // two waves of resident CTAs
+  int64_t grid = (int64_t)sm_count() * (a.race_group == 64 ? wide_ctas(MODE) : kCtasPerSm) * 2;   // two waves of resident CTAs
   if (grid > a.rows) grid = a.rows;
   if (a.race_group == 64)
     sample_group_kernel<MODE, ROUND, true><<<(unsigned)grid, kThreads, 0, s>>>(a);
