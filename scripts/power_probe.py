@@ -138,7 +138,7 @@ def main():
     mc_seq_stride=0, mc_step_stride=0, logits_dtype=_lib.BF16, diffusion=_lib.UNIFORM,
     guidance=_lib.GUIDE_CFG, subs=0, mask_logit=0, mask_index=103, round_bf16=1,
     select=_lib.SELECT_RACE, fast_math=1, gamma=2.0, seed=1, step=3, stats_chunks=st_a.shape[0],
-    stats_a=st_a.data_ptr(), stats_b=st_b.data_ptr(), stats_ld=R, race_group=8)
+    stats_a=st_a.data_ptr(), stats_b=st_b.data_ptr(), stats_ld=R, race_group=64)
   ms, p, c = sustained(lambda: _lib.check(_lib.lib.ddg_sample_step(a, sp)), h)
   rows.append(('sampler (x4 rows)', 4, ms, p, c, None))
 
