@@ -55,6 +55,8 @@ def main():
     ('fc1 store', 131072, 3072, 768, _lib.EPI_STORE, torch.float16),
     ('fc1 gelu', 131072, 3072, 768, _lib.EPI_BIAS_GELU, torch.float16),
     ('attn_out res', 131072, 768, 768, _lib.EPI_GATE_RESIDUAL, torch.float16),
+    ('attn_out store16', 131072, 768, 768, _lib.EPI_STORE, torch.float16),
+    ('attn_out accf32', 131072, 768, 768, _lib.EPI_ACCUM_F32, torch.float16),
     ('fc2 res', 131072, 768, 3072, _lib.EPI_GATE_RESIDUAL, torch.float16),
     ('vocab', 131072, 30522, 768, _lib.EPI_STORE, torch.bfloat16),
   ]
@@ -65,7 +67,7 @@ def main():
     a = (torch.randn(M, K, device=DEV) * 0.7).to(dt)
     w = (torch.randn(N, K, device=DEV) * 0.03).to(dt)
     bias = (torch.randn((N + 255) // 256 * 256, device=DEV) * 0.1).to(dt)
-    res = epi == _lib.EPI_GATE_RESIDUAL
+    res = epi in (_lib.EPI_GATE_RESIDUAL, _lib.EPI_ACCUM_F32)
     ldo = (N + 7) // 8 * 8
     out = torch.zeros(M, ldo, dtype=torch.float32 if res else dt, device=DEV)
     gate = (torch.randn(2, N, device=DEV) * 0.1).to(dt)
@@ -73,11 +75,12 @@ def main():
     sin = torch.randn(L, 32, device=DEV).to(dt)
     stats = torch.empty((N + 127) // 128, M, 2, dtype=torch.float32, device=DEV) if name == 'vocab' else None
     g = _lib.GemmArgs(a=a.data_ptr(), w=w.data_ptr(), out=out.data_ptr(), bias=bias.data_ptr(),
-                      gate=gate.data_ptr() if res else None, rope_cos=cos.data_ptr(), rope_sin=sin.data_ptr(),
+                      gate=gate.data_ptr() if epi == _lib.EPI_GATE_RESIDUAL else None, rope_cos=cos.data_ptr(), rope_sin=sin.data_ptr(),
                       lda=K, ldw=K, ld_out=ldo, gate_stride=N, rows_per_mod=M // 2, M=M, N=N, K=K,
                       dtype=_lib.DTYPE_CODE[dt], epilogue=epi, seq_len=L, head_dim=64,
                       rope_cols=2 * N // 3 if epi == _lib.EPI_QKV_ROPE else 0,
-                      stats=stats.data_ptr() if stats is not None else None, stats_ld=M, stats_mask_col=-1)
+                      stats=stats.data_ptr() if stats is not None else None, stats_ld=M, stats_mask_col=-1,
+                      accumulate=1 if 'accf32' in name else 0)
     sp = _lib.stream_ptr()
 
     def fn():

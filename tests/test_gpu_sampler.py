@@ -433,14 +433,19 @@ def _oracle_probs(la, lb, xt, mc_t, mc_s, V, diffusion, guidance, gamma, round_b
 
 @pytest.mark.parametrize('diffusion,guidance', FUSED_MODES)
 @pytest.mark.parametrize('round_bf16', [True, False])
-@pytest.mark.parametrize('race_group', [8, 64])
-def test_group_race_matches_cpu_restatement(diffusion, guidance, round_bf16, race_group):
+@pytest.mark.parametrize('race_group,V', [(8, 30522), (64, 30522), (64, 2051), (64, 4100),
+                                          (64, 33001), (8, 33001)])
+def test_group_race_matches_cpu_restatement(diffusion, guidance, round_bf16, race_group, V):
   """Production kernel (hierarchical race, in-kernel Philox) against the CPU
   restatement fed with the oracle's posterior and the regenerated Philox
   stream: ids bit-equal except near-ties -- a different group only if the two
   group scores agree to `tol` (log2 units), a different column of the same
-  group only if the inverse-CDF target sits within `tol` of the boundary."""
-  B, L, V, ld = 4, 16, 30522, 30528
+  group only if the inverse-CDF target sits within `tol` of the boundary.
+  Vocabulary sizes: the benchmark's, a ragged one just above the kernel's minimum, one
+  whose last 64-column sweep is nearly empty, and one past 32768 (more than four sweeps
+  per thread -> a second Philox call; softmax partials read from global memory)."""
+  B, L = 4, 16
+  ld = (V + 7) // 8 * 8
   rows = B * L
   dev = torch.device('cuda')
   la, lb, xt, subs = _group_inputs(diffusion, guidance, B, L, V, ld, 41)
