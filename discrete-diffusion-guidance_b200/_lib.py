@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DDG_B200_LIB: developer knob for same-box A/B runs of two builds of the library
 LIB_PATH = os.environ.get('DDG_B200_LIB') or os.path.join(_HERE, 'libddg_b200.so')
 
+ABI_VERSION = 3   # DDG_ABI_VERSION of include/ddg_b200.h these bindings were written for
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 F32, F16, BF16 = 0, 1, 2
 ABSORBING, UNIFORM, AR = 0, 1, 2
@@ -77,6 +78,9 @@ def _load():
     if not hasattr(lib, name):
       raise ImportError(f'{LIB_PATH} does not export {name}')
   lib.ddg_last_error.restype = C.c_char_p
+  if lib.ddg_abi_version() != ABI_VERSION:
+    raise ImportError(f'{LIB_PATH} has ABI version {lib.ddg_abi_version()}, these bindings need '
+                      f'{ABI_VERSION}: rebuild it (python -c "import __graft_entry__ as g; g.build()")')
   i32, i64, vp, u32, u64 = C.c_int32, C.c_int64, C.c_void_p, C.c_uint32, C.c_uint64
   lib.ddg_sample_step.argtypes = [C.POINTER(SampleStepArgs), vp]
   lib.ddg_low_confidence_select.argtypes = [vp, i64, i64, i32, C.c_float, vp, i64, i32, u64, vp,
