@@ -373,15 +373,30 @@ __global__ void split16_kernel(const float* __restrict__ src, T* __restrict__ hi
 
 // ---------------------------------------------------------------- first-order term
 // term[row, v] = grad[row, v] - grad[row, xt[row]] + log p(y | xt)[row / L]   (diffusion.py:1541-1548)
-__global__ void cbg_first_order_kernel(const float* grad, int64_t ld_grad, const int64_t* __restrict__ xt,
-                                       const float* __restrict__ log_probs, int n_classes, int target, int seq_len,
-                                       int vocab, int64_t rows, float* term, int64_t ld_term) {
-  const int64_t row = blockIdx.x;
-  if (row >= rows) return;
-  const float* g = grad + row * ld_grad;
-  const float base = log_probs[(row / seq_len) * n_classes + target] - g[xt[row]];
-  __syncthreads();                                 // term may alias grad: everyone has read g[xt] by now
-  for (int v = threadIdx.x; v < vocab; v += blockDim.x) term[row * ld_term + v] = g[v] + base;
+__global__ void __launch_bounds__(256)
+cbg_first_order_kernel(const float* grad, int64_t ld_grad, const int64_t* __restrict__ xt,
+                       const float* __restrict__ log_probs, int n_classes, int target, int seq_len,
+                       int vocab, int64_t rows, float* term, int64_t ld_term) {
+  const bool vec = ((ld_grad | ld_term) & 3) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(term) & 15) == 0;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float* g = grad + row * ld_grad;
+    float* t = term + row * ld_term;
+    const float base = log_probs[(row / seq_len) * n_classes + target] - g[xt[row]];
+    __syncthreads();                               // term may alias grad: everyone has read g[xt] by now
+    if (vec) {                                     // 128-bit loads / stores; the tail (vocab % 4) scalar
+      const int n4 = vocab >> 2;
+      for (int v = threadIdx.x; v < n4; v += blockDim.x) {
+        float4 x = __ldcs(reinterpret_cast<const float4*>(g) + v);
+        x.x += base; x.y += base; x.z += base; x.w += base;
+        reinterpret_cast<float4*>(t)[v] = x;
+      }
+      for (int v = (n4 << 2) + threadIdx.x; v < vocab; v += blockDim.x) t[v] = g[v] + base;
+    } else {
+      for (int v = threadIdx.x; v < vocab; v += blockDim.x) t[v] = g[v] + base;
+    }
+    __syncthreads();                               // the next row's g[xt] is read after this row's stores
+  }
 }
 
 int64_t grid_for(int64_t n) {
@@ -578,7 +593,8 @@ extern "C" int ddg_cbg_first_order(const float* grad, int64_t ld_grad, const int
   DDG_REQUIRE(grad && xt && log_probs && term && rows >= 0 && vocab > 0 && seq_len > 0 && ld_grad >= vocab &&
               ld_term >= vocab && target >= 0 && target < n_classes, DDG_ERR_INVALID, "cbg_first_order: bad args");
   if (rows == 0) return DDG_OK;
-  cbg_first_order_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  const int64_t cap = (int64_t)ddg::sm_count() * 8;
+  cbg_first_order_kernel<<<(unsigned)(rows < cap ? rows : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
     grad, ld_grad, xt, log_probs, n_classes, target, seq_len, vocab, rows, term, ld_term);
   return check_cuda(cudaGetLastError(), "cbg_first_order launch");
 }

@@ -146,10 +146,13 @@ class DIT:
       self.w_out_t = [tcast(f'blocks.{i}.attn_out.weight') for i in range(self.n_blocks)]
       self.w_fc1_t = [tcast(f'blocks.{i}.mlp.0.weight') for i in range(self.n_blocks)]
       self.w_fc2_t = [tcast(f'blocks.{i}.mlp.2.weight') for i in range(self.n_blocks)]
-      self.emb_hi = torch.empty(V * h, dtype=bd, device=self.device)
-      self.emb_lo = torch.empty(V * h, dtype=bd, device=self.device)
-      check(lib.ddg_split16(ptr(self.embedding), ptr(self.emb_hi), ptr(self.emb_lo),
+      emb_hi = torch.empty(V, h, dtype=bd, device=self.device)
+      emb_lo = torch.empty(V, h, dtype=bd, device=self.device)
+      check(lib.ddg_split16(ptr(self.embedding), ptr(emb_hi), ptr(emb_lo),
                             V * h, _lib.DTYPE_CODE[bd], stream_ptr()))
+      # G @ E^T ~ G_hi E_hi^T + G_lo E_hi^T + G_hi E_lo^T as ONE GEMM over the concatenated
+      # reduction dimension: [G_hi | G_lo | G_hi] @ [E_hi | E_hi | E_lo]^T, K = 3 h
+      self.emb_cat = torch.cat([emb_hi, emb_hi, emb_lo], dim=1).contiguous()
       torch.cuda.current_stream().synchronize()
     else:
       self.ln_f = f32('output_layer.norm_final.weight')
@@ -537,17 +540,16 @@ class DIT:
       check(lib.ddg_ln_modulate_backward(
         ptr(x_in), ptr(g_a), M, h, ptr(self.ln1[i]), mb + 1 * h * 2 if ada else 0,
         mod_stride, rpm, bcode, ptr(g), s))
-    # ---- d / d one-hot = G @ E^T in (almost) fp32: hi*hi + lo*hi + hi*lo
+    # ---- d / d one-hot = G @ E^T in (almost) fp32: hi*hi + lo*hi + hi*lo, accumulated in ONE
+    # pass over the (M, V) fp32 output by concatenating the three products along K
     g_lo = g16
     g_hi = g_a
     check(lib.ddg_split16(ptr(g), ptr(g_hi), ptr(g_lo), M * h, bcode, s))
+    g_cat = torch.cat([g_hi, g_lo, g_hi], dim=1)
     ldv = _pad_to(V, 4)
     term = torch.empty(M, ldv, dtype=torch.float32, device=dev)
-    gemm(ptr(g_hi), h, ptr(self.emb_hi), h, ptr(term), ldv, V, h, epi=_lib.EPI_ACCUM_F32)
-    gemm(ptr(g_lo), h, ptr(self.emb_hi), h, ptr(term), ldv, V, h, epi=_lib.EPI_ACCUM_F32,
-         accumulate=1)
-    gemm(ptr(g_hi), h, ptr(self.emb_lo), h, ptr(term), ldv, V, h, epi=_lib.EPI_ACCUM_F32,
-         accumulate=1)
+    gemm(ptr(g_cat), 3 * h, ptr(self.emb_cat), 3 * h, ptr(term), ldv, V, 3 * h,
+         epi=_lib.EPI_ACCUM_F32)
     check(lib.ddg_cbg_first_order(
       ptr(term), ldv, ptr(ids), ptr(lp), self.num_classes, int(target), L, V, M,
       ptr(term), ldv, s))
