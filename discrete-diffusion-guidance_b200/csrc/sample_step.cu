@@ -250,7 +250,27 @@ sample_step_kernel(const ddg_sample_step_args a) {
     RowConst rc;
     rc.z = z;
     // ---------------- pass 1: log-softmax normalisers
-    {
+    // Throughput mode with the vocab GEMM's per-128-column (max, sum exp(v - max)) partials
+    // at hand (ddg_gemm_args.stats): combine those instead of walking the row -- the D-CBG
+    // and other guided modes this generic kernel serves then read each logit once.
+    const bool have_stats = FAST && a.stats_a != nullptr && a.stats_chunks == (V + 127) / 128 &&
+                            (!mode_two(MODE) || a.stats_b != nullptr);
+    if (have_stats) {
+      LseAcc<FAST> acc_a, acc_b;
+      const float2* sa = reinterpret_cast<const float2*>(a.stats_a) + row;
+      const float2* sb = mode_two(MODE) ? reinterpret_cast<const float2*>(a.stats_b) + row : nullptr;
+      for (int ch = lane_in_group; ch < a.stats_chunks; ch += GROUP) {
+        const float2 pa2 = sa[(int64_t)ch * a.stats_ld];
+        if (pa2.x > -INFINITY) { acc_a.push_max(pa2.x); acc_a.s += pa2.y * F::exp(pa2.x - acc_a.m); }
+        if (mode_two(MODE)) {
+          const float2 pb2 = sb[(int64_t)ch * a.stats_ld];
+          if (pb2.x > -INFINITY) { acc_b.push_max(pb2.x); acc_b.s += pb2.y * F::exp(pb2.x - acc_b.m); }
+        }
+      }
+      lse_finish<GROUP, FAST>(acc_a.m, acc_a.s, sm, rc.Ma, rc.lnSa);
+      if (mode_two(MODE)) lse_finish<GROUP, FAST>(acc_b.m, acc_b.s, sm, rc.Mb, rc.lnSb);
+      else { rc.Mb = 0.f; rc.lnSb = 0.f; }
+    } else {
       LseAcc<FAST> acc_a, acc_b;
       for (int j0 = lane_in_group * VEC; j0 < V; j0 += GROUP * VEC) {
         float va[VEC], vb[VEC];

@@ -592,3 +592,39 @@ def test_float64_kernel_vs_oracle(diffusion, round_bf16):
   helpers.assert_close_frac(q.view(B, L, V), q_ref, rtol=3e-4, atol=1e-7,
                             loose_frac=1e-3 if round_bf16 else 0.0, loose_rtol=2e-2)
   helpers.assert_ids_match(xs.view(B, L), xs_ref, q_ref.float(), U, f'f64 {diffusion}', tol=2e-5)
+
+
+@pytest.mark.parametrize('diffusion,guidance', [('uniform', 'cbg'), ('absorbing_state', 'cbg'),
+                                                ('absorbing_state', 'cfg')])
+def test_generic_kernel_with_gemm_partials_equals_two_pass(diffusion, guidance):
+  """Guided modes served by the generic kernel (D-CBG, MDLM D-CFG) in throughput mode
+  (Philox noise, fast math): with the vocab GEMM's log-softmax partials the normaliser
+  pass over the row is skipped; posterior and ids must equal the two-pass run."""
+  B, L, V, ld = 3, 8, 30522, 30528
+  rows = B * L
+  dev = torch.device('cuda')
+  subs = diffusion == 'absorbing_state'
+  la = _rand_logits(rows, V, ld, torch.bfloat16, 21, 2.0).to(dev)
+  lb = _rand_logits(rows, V, ld, torch.bfloat16, 22, 2.0).to(dev)
+  g = torch.Generator().manual_seed(23)
+  clf = torch.randn(B, L, V, generator=g) * 0.5 - 1.0
+  if subs:
+    xt = torch.full((B, L), 103, dtype=torch.long)
+    xt[1, :3] = torch.tensor([5, 6, 7])
+  else:
+    xt = torch.randint(0, V, (B, L), generator=g)
+  st_a = helpers.make_stats(la, V, 103 if subs else -1)
+  st_b = helpers.make_stats(lb, V, 103 if subs else -1)
+  common = dict(logits_a=la, logits_b=lb if guidance == 'cfg' else None,
+                clf=clf if guidance == 'cbg' else None, xt=xt, mc_t=0.6, mc_s=0.55, vocab=V,
+                seq_len=L, diffusion=diffusion, guidance=guidance, gamma=1.5, subs=subs,
+                mask_logit=subs, mask_index=103, round_bf16=True, fast_math=True, seed=77, step=2,
+                want_q=True, clf_round_bf16=guidance == 'cbg')
+  xs0, q0 = helpers.sampler_kernel(**common)
+  xs1, q1 = helpers.sampler_kernel(stats_a=st_a.data_ptr(),
+                                   stats_b=st_b.data_ptr() if guidance == 'cfg' else 0,
+                                   stats_ld=rows, stats_chunks=st_a.shape[0], **common)
+  helpers.assert_close_frac(q1.cpu(), q0.cpu(), rtol=3e-4, atol=1e-7, loose_frac=2e-3, loose_rtol=2e-2)
+  assert (xs0 != xs1).float().mean().item() <= 0.05
+  if subs:
+    assert xs1.view(B, L)[1, :3].tolist() == [5, 6, 7]
