@@ -243,6 +243,38 @@ def kernel_breakdown(model, cfg, batch):
   return out
 
 
+def sampler_alone_ms(model, loop, reps=10):
+  """The step's fused-sampler launch (same buffers, same arguments) repeated on its own:
+  what the kernel does when the SM clock is not held down by the GEMMs of the step."""
+  from ddg_b200 import _lib
+  B, L = loop.B, loop.L
+  _, mct, mcs = loop.tables
+  ld = model.backbone.vocab_ld
+  xs = torch.empty_like(loop.xt)
+
+  def launch():
+    model._launch_sampler(
+      logits_a=loop.logits.data_ptr(), ld_a=ld,
+      logits_b=(loop.logits.data_ptr() + B * L * ld * 2) if loop.two else None,
+      ld_b=ld if loop.two else 0, xt=loop.xt, xs=xs, mc_t=mct, mc_s=mcs, rows=B * L, seq_len=L,
+      mc_seq_stride=0, mc_step_stride=1, step_ptr=loop.step, seed_ptr=loop.seed_dev,
+      stats=(loop.stats, 0, B * L if loop.two else 0),
+      guidance=_lib.GUIDE_CFG if loop.two else _lib.GUIDE_NONE,
+      gamma=loop.gamma if loop.two else 1.0)
+  loop.step.zero_()
+  torch.cuda.synchronize()
+  time.sleep(0.5)
+  for _ in range(3):
+    launch()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(reps):
+    launch()
+  e1.record()
+  torch.cuda.synchronize()
+  return e0.elapsed_time(e1) / reps
+
+
 def run_gpu_arm(args, rank, world, local_rank):
   import ddg_b200
   from ddg_b200 import dist as ddist
@@ -344,6 +376,8 @@ def run_gpu_arm(args, rank, world, local_rank):
   samp_bytes = rows * (2 * V * 2 + 16)
   samp_ms = kb['sample_step']['ms']
   samp_gbs = samp_bytes / (samp_ms * 1e-3) / 1e9
+  samp_alone_ms = sampler_alone_ms(model, loop)
+  samp_alone_gbs = samp_bytes / (samp_alone_ms * 1e-3) / 1e9
   gemm_tf = gemm_total_flops / (gemm_ms * 1e-3) / 1e12
   n_launch = sum(d['launches'] for d in kb.values())
   traffic = ncu_traffic(B)
@@ -376,7 +410,11 @@ def run_gpu_arm(args, rank, world, local_rank):
       'achieved': round(samp_gbs, 1), 'peak': pk['hbm'], 'unit': 'GB/s',
       'frac': round(samp_gbs / pk['hbm'], 4), 'traffic': samp_traffic,
       'algorithmic_bytes': samp_bytes, 'peak_source': pk['src'],
-      'share_of_step': round(samp_ms / step_kernel_ms, 4)},
+      'share_of_step': round(samp_ms / step_kernel_ms, 4),
+      'note': 'timed inside the power-capped step (SM clocks held at ~1.2-1.3 GHz by the GEMMs)',
+      'alone': {'ms_per_launch': round(samp_alone_ms, 4), 'achieved': round(samp_alone_gbs, 1),
+                'frac': round(samp_alone_gbs / pk['hbm'], 4),
+                'note': 'the same launch on the same buffers repeated 10x on its own after the step timing'}},
     'step_roofline': {
       'flops_per_step': total_flops,
       'tensor_bound_ms': round(total_flops / (pk['tf_sustained'] * 1e12) * 1e3, 3),
