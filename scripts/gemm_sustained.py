@@ -57,6 +57,7 @@ def main():
     ('attn_out res', 131072, 768, 768, _lib.EPI_GATE_RESIDUAL, torch.float16),
     ('attn_out store16', 131072, 768, 768, _lib.EPI_STORE, torch.float16),
     ('attn_out accf32', 131072, 768, 768, _lib.EPI_ACCUM_F32, torch.float16),
+    ('attn_out wrf32', 131072, 768, 768, _lib.EPI_ACCUM_F32, torch.float16),
     ('fc2 res', 131072, 768, 3072, _lib.EPI_GATE_RESIDUAL, torch.float16),
     ('vocab', 131072, 30522, 768, _lib.EPI_STORE, torch.bfloat16),
   ]
