@@ -213,7 +213,7 @@ template <> __device__ __forceinline__ uint32_t pack16<__nv_bfloat16>(float a, f
 // issue slots of the generic kernel, which matters at the ~1.3 GHz the SMs run at inside
 // a long power-capped step.  Same arithmetic order as the generic kernel (bit-identical).
 template <typename T, int NV>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, 4)
 ln_modulate_stream_kernel(const float* __restrict__ x, int64_t rows, const float* __restrict__ ln_w,
                           const T* __restrict__ shift, const T* __restrict__ ops, int64_t mod_stride,
                           int64_t rows_per_mod, T* __restrict__ out) {
@@ -427,7 +427,7 @@ extern "C" int ddg_ln_modulate(float* x, int64_t rows, int32_t hidden, const int
   if (!ids && rows >= 4096 && (hidden == 512 || hidden == 768) &&
       (dtype == DDG_F16 || dtype == DDG_BF16)) {
     // streaming variant: contiguous rows per warp, modulation vectors cached in registers
-    const unsigned sgrid = (unsigned)(sm_count() * 3);
+    const unsigned sgrid = (unsigned)(sm_count() * 4);
 #define DDG_LNS_LAUNCH(T, NV)                                                                        \
   ln_modulate_stream_kernel<T, NV><<<sgrid, 128, 0, s>>>(x, rows, ln_weight, reinterpret_cast<const T*>(shift), \
                                                          reinterpret_cast<const T*>(one_plus_scale), mod_stride, \
