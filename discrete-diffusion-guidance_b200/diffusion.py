@@ -729,6 +729,11 @@ class _GraphLoop:
       self.xt.copy_(xt)
       self.step.zero_()
 
+  def reset(self, xt):
+    """Back to step 0 of the schedule tables with a fresh prior."""
+    self.xt.copy_(xt)
+    self.step.zero_()
+
   def replay(self, n):
     for _ in range(n):
       self.graph.replay()

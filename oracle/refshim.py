@@ -1,15 +1,17 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the *unmodified* reference sampler.
 
-Imports /root/reference (read-only, exists only in the build container) with
-import-time stubs for the packages this image lacks (lightning, hydra,
+Imports /root/reference (read-only, exists only in the build container) or, on
+the GPU box, its staged byte-for-byte copy `baseline/_ref/` (git-ignored, made by
+oracle/stage_reference.py at build() time) with import-time stubs for the packages this image lacks (lightning, hydra,
 omegaconf, torchmetrics, mamba_ssm, causal_conv1d, timm) and a pure-torch
 stand-in for flash_attn's Triton-only rotary (reference models/dit.py:116-121).
 Nothing of the reference is copied: the modules are imported where they lie.
 
-Used by tests/golden/make_golden.py (golden-vector generator) and by
-tests/test_oracle_pins.py (skipped when /root/reference is absent, e.g. on the
-GPU box).  Never imported by the product package, bench.py's timed path or
-smoke().
+Used by tests/golden/make_golden.py (golden-vector generator), by
+tests/test_oracle_pins.py / tests/test_gpu_reference.py (skipped when no copy of
+the reference is reachable) and by `bench.py --impl reference` (the CPU arm:
+the reference's own step on the host cores).  Never imported by the product
+package, bench.py's GPU arm or smoke().
 """
 from __future__ import annotations
 
@@ -18,7 +20,23 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('DDG_REFERENCE_ROOT', '/root/reference')
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED_ROOT = os.path.join(_REPO, 'baseline', '_ref')   # oracle/stage_reference.py
+
+
+def _find_root() -> str:
+  """/root/reference in the build container; on the GPU box the byte-for-byte
+  copy `__graft_entry__.build()` staged under baseline/_ref (git-ignored)."""
+  env = os.environ.get('DDG_REFERENCE_ROOT')
+  if env:
+    return env
+  for cand in ('/root/reference', STAGED_ROOT):
+    if os.path.isfile(os.path.join(cand, 'diffusion.py')):
+      return cand
+  return '/root/reference'
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

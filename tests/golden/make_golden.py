@@ -15,6 +15,13 @@ writes `<case>_amp.npz` instead: the same unmodified reference code, but with
 reference rounds it on a GPU (fp16 blocks, bf16 final layer, bf16 log-softmax
 and exp).  These vectors pin the ROUNDING POINTS of the path; `*_dtype`
 entries record the dtype each traced tensor had.
+
+    python tests/golden/make_golden.py --gpu --out gpurun_out/golden_gpu [case ...]
+
+(on the B200 box, from the staged copy baseline/_ref) writes `<case>_gpu.npz`:
+the unmodified reference ON THE GPU under its real cuda autocast (cuBLAS fp16 /
+bf16 GEMMs, flash-attn Triton rotary, SDPA) -- the pin SURVEY.md 8a' asks to
+"confirm on the first gpurun".  The committed `*_gpu.npz` were produced that way.
 """
 from __future__ import annotations
 
@@ -29,38 +36,22 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
-import ddg_b200  # noqa: E402
 from golden import cases  # noqa: E402
-from oracle import refshim  # noqa: E402
+from oracle import ref_model, refshim  # noqa: E402
 
 TOPK = 8
 
 
-def build_reference_model(ref, case):
-  cfg = refshim.to_attrdict(cases.config_dict(case))
+def build_reference_model(ref, case, device='cpu'):
   tok = cases.Tok(case.vocab)
-  model = ref.diffusion.Diffusion(cfg, tok)
-  sd = ddg_b200.weights.random_state_dict(
-    ddg_b200.config.to_config(cases.config_dict(case)), tok.vocab_size,
-    seed=case.seed)
-  missing, unexpected = model.load_state_dict(sd, strict=False)
-  assert not unexpected, unexpected
-  assert set(missing) <= {'limiting_distribution'}, missing
-  model.eval()
-  clf = None
-  if case.guidance == 'cbg':
-    clf = ref.classifier.Classifier(cfg, tok)
-    csd = ddg_b200.weights.random_state_dict(
-      ddg_b200.config.to_config(cases.config_dict(case)), tok.vocab_size,
-      seed=case.seed + 1, classifier=True)
-    missing, unexpected = clf.load_state_dict(csd, strict=False)
-    assert not unexpected and not missing, (missing, unexpected)
-    clf.eval()
+  model, clf, cfg, _, _ = ref_model.build_reference(
+    cases.config_dict(case), tok, case.seed, device=device,
+    with_classifier=case.guidance == 'cbg')
   return model, clf, cfg
 
 
 def summarise(name, t, out, big):
-  t = t.detach().float()
+  t = t.detach().float().cpu()
   if not big:
     out[name] = t.numpy()
     return
@@ -72,16 +63,16 @@ def summarise(name, t, out, big):
   out[name + '_cols'] = t[..., ::997].numpy()
 
 
-def run_case(ref, case):
+def run_case(ref, case, device='cpu'):
   torch.manual_seed(0)
-  model, clf, cfg = build_reference_model(ref, case)
+  model, clf, cfg = build_reference_model(ref, case, device)
   big = case.vocab == 'bert'
   out = {}
-  xt0 = cases.prior_ids(case)
+  xt0 = cases.prior_ids(case).to(device)
   model._sample_prior = lambda *dims: xt0.clone()
 
   if case.parameterization == 'ar':
-    G = cases.ar_gumbel(case)
+    G = cases.ar_gumbel(case).to(device)
 
     class FakeGumbel:
       def __init__(self, *a, **k):
@@ -97,7 +88,7 @@ def run_case(ref, case):
         x = model.sample()
     finally:
       torch.distributions.Gumbel = real
-    out['samples'] = x.numpy().astype(np.int32)
+    out['samples'] = x.cpu().numpy().astype(np.int32)
     # log-probs of the final sequence pin the causal forward
     with torch.no_grad():
       lp = model.forward(x, None)
@@ -115,7 +106,7 @@ def run_case(ref, case):
   def fake_rand_like(t, *a, **k):
     U = cases.step_noise(case, step_counter['i'])
     assert U.shape == t.shape, (U.shape, t.shape)
-    return U.to(t.dtype)
+    return U.to(t.device, t.dtype)
 
   def wrap(fn_name):
     orig = getattr(model, fn_name)
@@ -146,11 +137,11 @@ def run_case(ref, case):
   finally:
     torch.rand_like = real_rand_like
   assert len(trace) == case.steps, (len(trace), case.steps)
-  out['samples'] = samples.numpy().astype(np.int32)
-  out['xt0'] = xt0.numpy().astype(np.int32)
+  out['samples'] = samples.cpu().numpy().astype(np.int32)
+  out['xt0'] = xt0.cpu().numpy().astype(np.int32)
   for i, rec in enumerate(trace):
-    out[f's{i}_xt'] = rec['xt'].numpy().astype(np.int32)
-    out[f's{i}_xs'] = rec['xs'].numpy().astype(np.int32)
+    out[f's{i}_xt'] = rec['xt'].cpu().numpy().astype(np.int32)
+    out[f's{i}_xs'] = rec['xs'].cpu().numpy().astype(np.int32)
     out[f's{i}_scalars'] = np.array(
       [rec['sigma_t'].item(), rec['mc_t'].item(), rec['mc_s'].item()],
       dtype=np.float32)
@@ -167,16 +158,25 @@ def run_case(ref, case):
 def main(argv):
   ref = refshim.load_reference()
   amp = '--amp' in argv
-  argv = [a for a in argv if a != '--amp']
-  names = argv or (cases.AMP_CASES if amp else [c.name for c in cases.CASES])
+  gpu = '--gpu' in argv
+  out_dir = HERE
+  if '--out' in argv:
+    out_dir = argv[argv.index('--out') + 1]
+    argv = [a for i, a in enumerate(argv) if a != '--out' and argv[i - 1] != '--out']
+    os.makedirs(out_dir, exist_ok=True)
+  argv = [a for a in argv if a not in ('--amp', '--gpu')]
+  names = argv or (cases.AMP_CASES if (amp or gpu) else [c.name for c in cases.CASES])
   for name in names:
     case = cases.CASE_BY_NAME[name]
-    if amp:
+    if gpu:      # the reference itself on the GPU under its REAL cuda autocast policy
+      out = run_case(ref, case, device='cuda')
+    elif amp:
       with refshim.cuda_autocast_on_cpu():
         out = run_case(ref, case)
     else:
       out = run_case(ref, case)
-    path = os.path.join(HERE, f'{name}_amp.npz' if amp else f'{name}.npz')
+    suffix = '_gpu' if gpu else ('_amp' if amp else '')
+    path = os.path.join(out_dir, f'{name}{suffix}.npz')
     np.savez_compressed(path, **out)
     print(f'{name}: {len(out)} arrays, {os.path.getsize(path) / 1024:.1f} KiB')
 

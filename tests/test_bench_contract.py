@@ -18,10 +18,12 @@ def test_reference_arm_prints_one_contract_line():
   assert d['impl'] == 'reference' and d['higher_is_better'] is True and d['unit'] == 'sequences/s'
   assert d['metric'].startswith('sampled sequences/sec, LM1B UDLM D-CFG')
   assert d['value'] > 0 and d['ms_per_step'] > 0 and d['n_gpus'] == 1
-  assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+  assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['cores'] >= 1
   assert d['cpu_baseline']['value'] == d['value'] == d['e2e']['value']
   assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
   assert 'workload' in d['config'] and d['vs_baseline'] is None
+  # the reference arm runs the reference alone: it never loads the product package / library
+  assert d['product_modules_loaded'] == [] and d['native_so_loaded'] == []
 
 
 def test_reference_arm_other_ranks_stay_silent():
