@@ -59,12 +59,24 @@ class Classifier:
     return sigma
 
   def get_log_probs(self, x, sigma, x_emb=None, seqs_per_mod=1):
-    """classifier.py:316-327 for token ids (n, L) -> (n, classes) fp32.
+    """classifier.py:316-327 -> (n, classes) fp32 log-probs.  `x` is (n, L) token
+    ids or, like `DITClassifier.forward` (models/dit.py:518-522), (n, L, V)
+    one-hots: `one_hot @ embedding` is the embedding gather, so one-hot rows are
+    turned back into ids (rows that are not one-hot raise ValueError; the gradient
+    w.r.t. a one-hot input is `first_order_term`).
     `seqs_per_mod` > 1: sigma holds one value per that many consecutive sequences."""
-    if x_emb is not None or x.ndim != 2:
+    if x_emb is not None:
       raise NotImplementedError(
-        'one-hot / x_emb classifier inputs (first-order CBG, NOS) are not '
-        'implemented yet')
+        'x_emb inputs (NOS / PPLM hidden-state guidance) are outside the sampling path')
+    if x.ndim == 3:
+      if x.shape[-1] != self.vocab_size:
+        raise ValueError(f'one-hot input has {x.shape[-1]} columns, vocab is {self.vocab_size}')
+      top, ids = x.max(dim=-1)
+      if not bool(((top == 1) & (x.sum(dim=-1) == 1) & (x.min(dim=-1).values == 0)).all()):
+        raise ValueError('classifier input of shape (n, L, V) must be one-hot rows')
+      x = ids
+    elif x.ndim != 2:
+      raise ValueError(f'classifier input must be (n, L) ids or (n, L, V) one-hots, got {tuple(x.shape)}')
     return self.classifier_model.classify(x, self._process_sigma(sigma),
                                           round_bf16=self.round_bf16,
                                           seqs_per_mod=seqs_per_mod)

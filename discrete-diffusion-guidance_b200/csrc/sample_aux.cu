@@ -238,8 +238,10 @@ low_confidence_kernel(const float* __restrict__ probs, int64_t ld, int64_t rows,
       for (int i = 0; i < w; ++i) base += sm_cnt[i];
       tie_rank0 = base + v - my_ties;
     }
-    // ---- race / arg-max over the kept entries (probs / E in fp32, diffusion.py:1748-1755)
-    double best = 0.;                             // dropped entries score 0: all-zero -> index 0
+    // ---- race / arg-max over the kept entries (probs / E in fp32, diffusion.py:1748-1755);
+    // AR (`_sample_token`, diffusion.py:1030-1038): argmax of log p + G over the kept entries
+    const bool gumbel = select == DDG_SELECT_GUMBEL && noise != nullptr;
+    double best = gumbel ? -INFINITY : 0.;        // dropped entries score 0 / -inf: none kept -> index 0
     int bidx = 0x7fffffff;
     int rank = tie_rank0;
     for (int j = j_lo; j < j_hi; ++j) {
@@ -248,7 +250,9 @@ low_confidence_kernel(const float* __restrict__ probs, int64_t ld, int64_t rows,
       if (!all_kept && pj == vstar) { keep = rank < k_ties; ++rank; }
       if (!keep || !(pj > 0.f)) continue;
       float score = pj;
-      if (select != DDG_SELECT_ARGMAX) {
+      if (gumbel) {
+        score = __fadd_rn(logf(pj), noise[row * ld_noise + j]);
+      } else if (select != DDG_SELECT_ARGMAX) {   // Gumbel-max without injected noise == the race
         const float u = noise ? noise[row * ld_noise + j] : philox_u(j, row, step, key);
         score = __fdiv_rn(pj, __fadd_rn(1e-10f, -logf(__fadd_rn(u, 1e-10f))));
       }
@@ -284,8 +288,8 @@ extern "C" int ddg_low_confidence_select(const float* probs, int64_t ld, int64_t
   int rc = ddg_device_check();
   if (rc) return rc;
   DDG_REQUIRE(probs && xs && rows >= 0 && vocab > 0 && ld >= vocab, DDG_ERR_INVALID, "low_confidence: bad args");
-  DDG_REQUIRE(select == DDG_SELECT_RACE || select == DDG_SELECT_ARGMAX, DDG_ERR_INVALID,
-              "low_confidence: select must be race or argmax");
+  DDG_REQUIRE(select == DDG_SELECT_RACE || select == DDG_SELECT_ARGMAX || select == DDG_SELECT_GUMBEL,
+              DDG_ERR_INVALID, "low_confidence: select must be race, argmax or gumbel");
   if (noise) DDG_REQUIRE(ld_noise >= vocab, DDG_ERR_INVALID, "low_confidence: ld_noise < vocab");
   const size_t smem = (size_t)vocab * sizeof(float);
   DDG_REQUIRE(smem <= 200 * 1024, DDG_ERR_UNSUPPORTED, "low_confidence: vocab %d does not fit shared memory", vocab);

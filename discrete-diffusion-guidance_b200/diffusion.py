@@ -14,13 +14,34 @@ device tables.
 """
 from __future__ import annotations
 
+import collections
 import typing
+import warnings
 
 import torch
 
 from . import _lib, config as config_lib, noise_schedule, weights
 from ._lib import check, lib, ptr, stream_ptr
 from .dit import DIT, ModSpec
+
+
+_MAX_STEP_GRAPHS = 2
+
+
+def _attach_stats(logits, stats, row_offset):
+  """The vocab GEMM's log-softmax partials travel WITH the logits tensor they
+  describe (as an attribute, so the cache dicts of the per-step API carry them and
+  their lifetime is the tensor's), tagged with the tensor's version counter: an
+  in-place write to the logits afterwards invalidates them."""
+  logits._ddg_stats = (stats, int(row_offset), logits._version)
+  return logits
+
+
+def _get_stats(logits):
+  tag = getattr(logits, '_ddg_stats', None)
+  if tag is None or tag[2] != logits._version:
+    return None
+  return tag[0], tag[1]
 
 
 class Diffusion:
@@ -72,8 +93,9 @@ class Diffusion:
     self.seed = int(config.get('seed', 1))
     self._call_count = 0
     self._loop = None
-    self._stats = {}            # logits data_ptr -> (stats tensor, row offset)
-    self._step_graphs = {}
+    self._step_index = 0        # Philox counter word of the next eager sampler launch
+    self._step_graphs = collections.OrderedDict()   # LRU, at most _MAX_STEP_GRAPHS
+    self._warned_use_cache = False
 
   # ---------------------------------------------------------------- weights
   def load_state_dict(self, state_dict, strict=True):
@@ -174,8 +196,7 @@ class Diffusion:
     stats = self.backbone.alloc_stats(B * L)
     logits = self.backbone.forward(x, sigma, cond, stats_out=stats,
                                    stats_mask_col=self._stats_mask_col)
-    self._stats = {logits.data_ptr(): (stats, 0)}
-    return logits
+    return _attach_stats(logits, stats, 0)
 
   def forward(self, x, sigma, cond=None, x_emb=None, **kwargs):
     """Returns log-probs (B, L, V) fp32 like `Diffusion.forward`
@@ -218,6 +239,20 @@ class Diffusion:
     sigma_s = self.noise.total_noise(t - dt)
     return sigma_t, 1 - torch.exp(-sigma_t), 1 - torch.exp(-sigma_s)
 
+  @staticmethod
+  def _stats_of(a, b=None):
+    """Log-softmax partials the vocab GEMM left for these logits tensors, if they
+    travel with them (`_attach_stats`) and the tensors were not written since."""
+    sa = _get_stats(a)
+    if sa is None:
+      return None
+    if b is None:
+      return (sa[0], sa[1], 0)
+    sb = _get_stats(b)
+    if sb is None or sb[0] is not sa[0]:
+      return None
+    return (sa[0], sa[1], sb[1])
+
   def _launch_sampler(self, *, logits_a, ld_a, logits_b=None, ld_b=0, clf=None,
                       noise=None, xt, xs, mc_t=None, mc_s=None, rows, seq_len,
                       mc_seq_stride=0, mc_step_stride=0, step_ptr=None, step=0,
@@ -227,11 +262,8 @@ class Diffusion:
                       clf_round_bf16=False):
     V = self.vocab_size
     # log-softmax partials of these logits, if our own vocab GEMM made them:
-    # stats = (tensor (chunks, rows_total, 2), row offset of a, row offset of b)
-    if stats is None and logits_a in self._stats:
-      st, off = self._stats[logits_a]
-      off_b = self._stats.get(logits_b, (None, 0))[1] if logits_b else 0
-      stats = (st, off, off_b)
+    # stats = (tensor (chunks, rows_total, 2), row offset of a, row offset of b); they
+    # are handed in by the caller together with the logits (never looked up by address)
     st_a = st_b = st_ld = st_chunks = 0
     if stats is not None:
       st, off_a, off_b = stats
@@ -274,7 +306,13 @@ class Diffusion:
            self.race_group)
     sg = self._step_graphs.get(key)
     if sg is None:
+      # each graph owns its logits buffer (8 GB at B=512, L=128, V=30522 for cfg2): keep
+      # the most recently used few, so a gamma sweep does not grow HBM use without bound
+      while len(self._step_graphs) >= _MAX_STEP_GRAPHS:
+        self._step_graphs.popitem(last=False)
       sg = self._step_graphs[key] = _StepGraph(self, kind, B, L, float(gamma))
+    else:
+      self._step_graphs.move_to_end(key)
     return sg
 
   def _step_noise(self, B, L):
@@ -282,8 +320,6 @@ class Diffusion:
       return None
     U = self.noise_fn(self._step_index).to(self.device, torch.float32)
     return U.reshape(B * L, self.vocab_size).contiguous()
-
-  _step_index = 0
 
   # ---------------------------------------------------------------- per step
   def _ddpm_denoise(self, xt, time_conditioning, move_chance_t, move_chance_s,
@@ -305,11 +341,12 @@ class Diffusion:
     self._launch_sampler(
       logits_a=logits.data_ptr(), ld_a=logits.stride(1), xt=xt, xs=xs, mc_t=mct,
       mc_s=mcs, rows=B * L, seq_len=L, mc_seq_stride=1 if mct.numel() > 1 else 0,
-      noise=noise, q_out=q, step=self._step_index,
+      noise=noise, q_out=q, step=self._step_index, stats=self._stats_of(logits),
       compute_f64=self._use_float64)
     if self._low_confidence:
       self._low_confidence_draw(q, xt, xs, noise,
                                 carry=self.diffusion == 'absorbing_state')
+    self._step_index += 1       # successive API calls draw fresh noise
     return xs, q if self.return_q_xs else None, {'log_x_theta': logits}
 
   def _cfg_denoise(self, cond, gamma, xt, time_conditioning, move_chance_t,
@@ -350,8 +387,8 @@ class Diffusion:
       self.backbone.run(xt, 2 * B, L, mod, buf, ids_period=B * L,
                         stats_out=stats, stats_mask_col=self._stats_mask_col)
       both = buf.view(2, B, L, self.backbone.vocab_ld)[..., :self.vocab_size]
-      lc, lu = both[0], both[1]
-      self._stats = {lc.data_ptr(): (stats, 0), lu.data_ptr(): (stats, B * L)}
+      lc = _attach_stats(both[0], stats, 0)
+      lu = _attach_stats(both[1], stats, B * L)
     xs = torch.empty_like(xt)
     q = self._q_buffer(B, L)
     mct, mcs = self._mc(move_chance_t), self._mc(move_chance_s)
@@ -361,14 +398,17 @@ class Diffusion:
                   noise=noise, q_out=q, step=self._step_index)
     if lc is None or lu is None:
       one = lu if lu is not None else lc
-      self._launch_sampler(logits_a=one.data_ptr(), ld_a=one.stride(1), **common)
+      self._launch_sampler(logits_a=one.data_ptr(), ld_a=one.stride(1),
+                           stats=self._stats_of(one), **common)
     else:
       self._launch_sampler(logits_a=lc.data_ptr(), ld_a=lc.stride(1),
                            logits_b=lu.data_ptr(), ld_b=lu.stride(1),
+                           stats=self._stats_of(lc, lu),
                            guidance=_lib.GUIDE_CFG, gamma=gamma, **common)
     if self._low_confidence:
       self._low_confidence_draw(q, xt, xs, noise,
                                 carry=self.diffusion == 'absorbing_state')
+    self._step_index += 1
     return xs, q if self.return_q_xs else None, {
       'log_x_theta_uncond': lu, 'log_x_theta_cond': lc}
 
@@ -422,11 +462,13 @@ class Diffusion:
       xt=xt, xs=xs, mc_t=mct, mc_s=mcs, rows=B * L, seq_len=L,
       mc_seq_stride=1 if mct.numel() > 1 else 0, noise=noise,
       q_out=q, guidance=_lib.GUIDE_CBG, gamma=gamma, step=self._step_index,
+      stats=self._stats_of(logits),
       # exact term: bf16 tensor in the reference, so gamma * term rounds to bf16
       clf_round_bf16=self.round_bf16 and not use_approx)
     if self._low_confidence:
       self._low_confidence_draw(q, xt, xs, noise,
                                 carry=self.diffusion == 'absorbing_state')
+    self._step_index += 1
     return xs, q if self.return_q_xs else None, {
       'log_x_theta': logits, 'classifier_log_prob': term}
 
@@ -444,8 +486,19 @@ class Diffusion:
       raise NotImplementedError(f'Guidance method {method} not implemented.')
     xt = self._sample_prior(B, L)
     sigma_t, mc_t, mc_s = self._step_scalars(steps, eps)
+    if (self.config.sampling.get('use_cache', False) and self.time_conditioning
+        and not self._warned_use_cache):
+      # reference diffusion.py:1371-1374 keeps the cached log-probs (computed at an OLDER
+      # sigma) while NO token of the batch changes; here every step recomputes them at the
+      # current sigma (documented deviation, only reachable when a
+      # whole batch stays unchanged for a step)
+      warnings.warn('sampling.use_cache with time_conditioning=True: log-probs are '
+                    'recomputed at every step instead of being reused across unchanged '
+                    'steps (see DESIGN.md)', stacklevel=2)
+      self._warned_use_cache = True
+    mixed_cond = cond is not None and not bool((cond == cond.reshape(-1)[0]).all())
     if self.noise_fn is not None or self.return_q_xs or method == 'cbg' \
-        or not self.use_cuda_graph or self._low_confidence \
+        or not self.use_cuda_graph or self._low_confidence or mixed_cond \
         or (self._use_float64 and method is None):
       return self._eager_loop(xt, sigma_t, mc_t, mc_s, method, guidance,
                               classifier_model, cond)
@@ -517,9 +570,6 @@ class Diffusion:
     method = None if guidance is None else guidance.method
     if method not in (None, 'cfg'):
       raise NotImplementedError(f'Guidance method {method} not implemented.')
-    if self._low_confidence:
-      raise NotImplementedError(
-        'eval.low_confidence_sampling is not implemented for the AR sampler')
     B = self.config.sampling.batch_size
     L = self.config.model.length
     V, ld = self.vocab_size, self.backbone.vocab_ld
@@ -529,6 +579,10 @@ class Diffusion:
     n_fwd = 2 if two else 1
     buf = None if self.ar_kv_cache else self.backbone.alloc_logits(n_fwd * B * L)
     y = torch.empty(B, dtype=torch.int64, device=self.device)
+    # eval.low_confidence_sampling in `_sample_token` (diffusion.py:1030-1037): the fused
+    # kernel leaves softmax(next_log_probs), the low-confidence kernel draws from its kept set
+    q_next = (torch.empty(B, V, dtype=torch.float32, device=self.device)
+              if self._low_confidence else None)
     labels = None
     if method == 'cfg':
       mask_cond = torch.ones_like(cond) * self.config.data.num_classes
@@ -560,8 +614,14 @@ class Diffusion:
         ld_b=ldb if two else 0, noise=noise, xt=y, xs=y, rows=B, seq_len=1,
         guidance=_lib.GUIDE_CFG if two else _lib.GUIDE_NONE,
         gamma=guidance.gamma if two else 1.0, diffusion=_lib.AR,
-        select=_lib.SELECT_GUMBEL, step=i,
-        compute_f64=self._use_float64 and method is None)
+        select=_lib.SELECT_GUMBEL, step=i, q_out=q_next,
+        compute_f64=self._use_float64 and method is None and q_next is None)
+      if q_next is not None:
+        thr = float(self.config.eval.get('low_confidence_threshold', 0.3))
+        check(lib.ddg_low_confidence_select(
+          ptr(q_next), V, B, V, thr, ptr(noise), V if noise is not None else 0,
+          _lib.SELECT_GUMBEL, self.seed + 7919 * self._call_count, 0, i, 0, 0, -1, ptr(y),
+          stream_ptr()))
       x[:, i + 1] = y
     return x
 

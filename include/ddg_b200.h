@@ -156,7 +156,10 @@ DDG_API int ddg_sample_step(const ddg_sample_step_args* args, ddg_stream_t strea
  * of ddg_sample_step -- keep the entries whose cumulative mass in ascending
  * probability order is <= threshold (ties in index order, i.e. a stable sort),
  * zero the rest, then draw by the exponential race (noise: injected U or NULL
- * for the Philox stream of ddg_sample_step) or take the arg-max.  xt != NULL
+ * for the Philox stream of ddg_sample_step) or take the arg-max; select =
+ * DDG_SELECT_GUMBEL with injected Gumbel noise is the AR sampler's
+ * `_sample_token` (diffusion.py:1024-1038): argmax of log p + G over the kept
+ * entries (without injected noise it is the same race).  xt != NULL
  * and carry_mask_index >= 0: rows with xt != carry_mask_index are copied
  * through afterwards (absorbing carry-over, diffusion.py:1414-1418).          */
 DDG_API int ddg_low_confidence_select(const float* probs, int64_t ld, int64_t rows, int32_t vocab,

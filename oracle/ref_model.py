@@ -127,3 +127,49 @@ class ReferenceStepper:
                                   time_conditioning=sigma_t, move_chance_t=mct,
                                   move_chance_s=mcs, cache=None)
     return xs
+
+
+def make_reference_checkpoints(cfg_dict: dict, tok, seed: int, out_dir: str,
+                               with_classifier: bool = True):
+  """Writes Lightning-format `.ckpt` files from the REFERENCE modules the way
+  `on_save_checkpoint` (reference diffusion.py:208-250) shapes them:
+  `{'state_dict': ..., 'ema': ema.state_dict(), 'loops': ...}` with the EMA shadow
+  parameters perturbed away from the raw ones, and a classifier checkpoint
+  (`classifier_model.*`).  Also returns what the reference itself would sample
+  with: the state_dict after its own `ema.copy_to(...)` (diffusion.py:923-930).
+
+  -> dict(diffusion=path, classifier=path|None, raw_sd, ema_sd, clf_sd)"""
+  import copy
+  import itertools
+
+  import torch
+  cfg_dict = copy.deepcopy(cfg_dict)
+  cfg_dict['weights_averaging'] = dict(type='ema', decay=0.9999)
+  model, clf, cfg, sd, csd = build_reference(cfg_dict, tok, seed,
+                                             with_classifier=with_classifier)
+  assert model.ema is not None
+  g = torch.Generator().manual_seed(seed + 77)
+  for p in model.ema.shadow_params:          # an EMA that differs from the raw weights
+    p.add_(torch.randn(p.shape, generator=g) * 0.01 * (p.abs().mean() + 0.01))
+  raw_sd = {k: v.clone() for k, v in model.state_dict().items()
+            if k != 'limiting_distribution'}
+  ckpt = {'state_dict': raw_sd, 'ema': model.ema.state_dict(),
+          'loops': {'fit_loop': {'epoch_progress': {'current': {'completed': 0}},
+                                 'epoch_loop.batch_progress': {
+                                   'current': {'completed': 0},
+                                   'total': {'completed': 0}}}},
+          'pytorch-lightning_version': 'stub', 'global_step': 0, 'epoch': 0}
+  os.makedirs(out_dir, exist_ok=True)
+  dpath = os.path.join(out_dir, 'diffusion.ckpt')
+  torch.save(ckpt, dpath)
+  # what the reference samples with (diffusion.py:1054-1055): its own copy_to
+  model.ema.copy_to(itertools.chain(model.backbone.parameters(),
+                                    model.noise.parameters()))
+  ema_sd = {k: v.clone() for k, v in model.state_dict().items()
+            if k != 'limiting_distribution'}
+  cpath = None
+  if clf is not None:
+    cpath = os.path.join(out_dir, 'classifier.ckpt')
+    torch.save({'state_dict': {k: v.clone() for k, v in clf.state_dict().items()}}, cpath)
+  return dict(diffusion=dpath, classifier=cpath, raw_sd=raw_sd, ema_sd=ema_sd,
+              clf_sd=csd)

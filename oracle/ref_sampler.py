@@ -265,8 +265,17 @@ def cbg_classifier_term_approx(clf_fn_onehot, xt, sigma, vocab_size,
 # --------------------------------------------------------------------------
 # AR
 # --------------------------------------------------------------------------
-def ar_select(next_log_probs, gumbel):
-  """`_sample_token` (diffusion.py:1024-1038) without low-confidence mode."""
+def ar_select(next_log_probs, gumbel, low_confidence=None):
+  """`_sample_token` (diffusion.py:1024-1038): Gumbel-max; with
+  `eval.low_confidence_sampling` only the bottom `low_confidence` cumulative
+  probability mass stays eligible (:1030-1037)."""
+  if low_confidence is not None:
+    probs = next_log_probs.softmax(dim=-1)
+    sorted_probs, sorted_idx = probs.sort(dim=-1)
+    mask_sorted = sorted_probs.cumsum(dim=-1) <= low_confidence
+    mask = torch.zeros_like(mask_sorted)
+    mask.scatter_(1, sorted_idx, mask_sorted)
+    next_log_probs = next_log_probs.masked_fill(~mask, -float('inf'))
   return (next_log_probs + gumbel).argmax(-1)
 
 

@@ -81,6 +81,11 @@ CASES = [
        steps=2),
   Case('ar_null', parameterization='ar', diffusion='absorbing_state',
        time_conditioning=False, length=16, steps=0),
+  Case('ar_cfg_g2', parameterization='ar', diffusion='absorbing_state',
+       time_conditioning=False, guidance='cfg', gamma=2.0, length=16, steps=0),
+  Case('ar_lowconf', parameterization='ar', diffusion='absorbing_state',
+       time_conditioning=False, low_confidence=True,
+       low_confidence_threshold=0.6, length=16, steps=0),
 ]
 CASE_BY_NAME = {c.name: c for c in CASES}
 # cases also run with the reference's GPU autocast policy emulated on the CPU

@@ -91,8 +91,13 @@ def run_case(ref, case, device='cpu'):
     out['samples'] = x.cpu().numpy().astype(np.int32)
     # log-probs of the final sequence pin the causal forward
     with torch.no_grad():
-      lp = model.forward(x, None)
-    summarise('log_probs_final', lp, out, big)
+      if case.guidance == 'cfg':
+        cond = torch.full((case.batch,), case.condition, dtype=torch.long, device=device)
+        summarise('log_probs_final_cond', model.forward(x, None, cond=cond), out, big)
+        summarise('log_probs_final_uncond', model.forward(
+          x, None, cond=torch.full_like(cond, case.num_classes)), out, big)
+      else:
+        summarise('log_probs_final', model.forward(x, None), out, big)
     return out
 
   if clf is not None:

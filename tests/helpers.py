@@ -230,3 +230,94 @@ def make_stats(logits, vocab, mask_col=-1):
   m = v.amax(-1)
   s = torch.exp2((v - m[..., None]) * 1.4426950408889634).sum(-1)
   return torch.stack([m, s], -1).permute(1, 0, 2).contiguous()
+
+
+# ----------------------------------------------------------------- reference traces
+def gpu_diffusion(case):
+  cfg, tok, sd, csd = case_state(case)
+  model = ddg_b200.Diffusion(cfg, tok, device='cuda').load_state_dict(sd)
+  if csd is not None:
+    model.set_classifier(ddg_b200.Classifier(cfg, tok, device='cuda').load_state_dict(csd))
+  return model, cfg, tok
+
+
+def _full(gold, key, big):
+  """Tensor stored under `key` (full) or None when only a summary was kept."""
+  return None if big else torch.from_numpy(gold[key]).float()
+
+
+def check_against_reference_trace(case, gold, *, min_exact, max_rel_lp, q_med, q_max,
+                                  id_frac):
+  """Replays the reference's trace `gold` (per-step xt, scalars, log-probs,
+  posterior, ids) through the CUDA per-step API with the same injected noise.
+
+  * bf16 log-probs: two pipelines that round at the same points agree bit for bit
+    wherever accumulation-order noise did not flip a rounding -> a share
+    `min_exact` of the entries must be EXACTLY equal, the rest within `max_rel_lp`
+    (a few bf16 ulps);
+  * posterior q_xs: median / max relative deviation;
+  * ids: may differ only on a small fraction (near-ties of the race under
+    bf16-rounded probabilities).
+  Returns the measured statistics."""
+  model, cfg, tok = gpu_diffusion(case)
+  model.return_q_xs = True
+  big = case.vocab == 'bert'
+  B, L, V = case.batch, case.length, tok.vocab_size
+  stats = dict(exact=[], rel_lp=[], q_med=[], q_max=[], n_ids=0, n_diff=0)
+  for i in range(case.steps):
+    U = cases.step_noise(case, i)
+    model.noise_fn = lambda _i, U=U: U
+    xt = torch.from_numpy(gold[f's{i}_xt']).long().to('cuda')
+    sc = gold[f's{i}_scalars']
+    sigma_t = torch.full((B,), float(sc[0]), device='cuda')
+    mc_t = torch.full((B, 1, 1), float(sc[1]), device='cuda')
+    mc_s = torch.full((B, 1, 1), float(sc[2]), device='cuda')
+    if case.guidance is None:
+      xs, q, cache = model._ddpm_denoise(xt, sigma_t, mc_t, mc_s)
+    elif case.guidance == 'cfg':
+      cond = torch.full((B,), case.condition, dtype=torch.long, device='cuda')
+      xs, q, cache = model._cfg_denoise(cond, case.gamma, xt, sigma_t, mc_t, mc_s)
+    else:
+      xs, q, cache = model._cbg_denoise(
+        case.condition, case.gamma, model.classifier_model, xt, sigma_t, mc_t, mc_s,
+        use_approx=case.use_approx)
+    torch.cuda.synchronize()
+    for k, v in cache.items():
+      if v is None or not k.startswith('log_x_theta'):
+        continue
+      # the API caches logits; the reference caches their (bf16) log-softmax
+      lp = ref_sampler.log_probs_from_logits(
+        v.float().cpu(), xt.cpu(), parameterization=case.parameterization,
+        mask_index=tok.mask_token_id, subs_masking=case.subs_masking,
+        lp_dtype=torch.bfloat16)
+      if big:
+        g = torch.from_numpy(gold[f's{i}_{k}_cols']).float()
+        lp = lp[..., ::997]
+      else:
+        g = torch.from_numpy(gold[f's{i}_{k}']).float()
+      fin = torch.isfinite(g) & (g > -1e5) & (g != 0)
+      rel = ((lp - g).abs() / g.abs())[fin]
+      stats['exact'].append((rel == 0).float().mean().item())
+      stats['rel_lp'].append(rel.max().item())
+    qc = q.float().cpu().view(B, L, V)
+    if big:
+      g = torch.from_numpy(gold[f's{i}_q_xs_cols']).float()
+      qc = qc[..., ::997]
+    else:
+      g = torch.from_numpy(gold[f's{i}_q_xs']).float()
+    pos = g > 1e-9
+    rel = ((qc - g).abs() / g.clamp_min(1e-30))[pos]
+    stats['q_med'].append(rel.median().item())
+    stats['q_max'].append(rel.max().item())
+    gx = torch.from_numpy(gold[f's{i}_xs']).long()
+    stats['n_ids'] += gx.numel()
+    stats['n_diff'] += int((xs.cpu() != gx).sum())
+  summary = dict(exact=min(stats['exact']), rel_lp=max(stats['rel_lp']),
+                 q_med=max(stats['q_med']), q_max=max(stats['q_max']),
+                 n_diff=stats['n_diff'], n_ids=stats['n_ids'])
+  print(f'[reference-on-gpu] {case.name}: {summary}')
+  assert summary['exact'] >= min_exact, summary
+  assert summary['rel_lp'] <= max_rel_lp, summary
+  assert summary['q_med'] <= q_med and summary['q_max'] <= q_max, summary
+  assert summary['n_diff'] <= max(2, int(id_frac * summary['n_ids'])), summary
+  return summary

@@ -255,8 +255,7 @@ def test_ar_kv_cache_equals_prefix_reencode(guidance):
     assert ok >= 3 * (case.length - 1) - 2
 
 
-@pytest.mark.parametrize('name', [n for n in cases.AMP_CASES
-                                  if cases.CASE_BY_NAME[n].vocab != 'bert'])
+@pytest.mark.parametrize('name', cases.AMP_CASES)
 def test_step_api_against_reference_under_gpu_autocast(name):
   """The CUDA path (forward + sampler through the per-step API, injected noise)
   against `<case>_amp.npz`: the UNMODIFIED reference run with its cuda autocast
@@ -265,51 +264,9 @@ def test_step_api_against_reference_under_gpu_autocast(name):
   same points agree bit for bit wherever upstream accumulation-order noise did
   not flip a rounding, so the bf16 log-probs must share >= 25 % of their entries
   exactly (an fp32 pipeline shares ~0 %, tests/test_oracle_pins.py), stay within
-  3 bf16 ulps everywhere, and the ids may differ only at a few near-ties."""
-  case = cases.CASE_BY_NAME[name]
-  gold = helpers.load_golden(name + '_amp')
-  model, cfg, tok = _diffusion(case)
-  model.return_q_xs = True
-  B, L, V = case.batch, case.length, tok.vocab_size
-  n_ids = n_diff = 0
-  for i in range(case.steps):
-    U = cases.step_noise(case, i)
-    model.noise_fn = lambda _i, U=U: U
-    xt = torch.from_numpy(gold[f's{i}_xt']).long().to(DEV)
-    sc = gold[f's{i}_scalars']
-    sigma_t = torch.full((B,), float(sc[0]), device=DEV)
-    mc_t = torch.full((B, 1, 1), float(sc[1]), device=DEV)
-    mc_s = torch.full((B, 1, 1), float(sc[2]), device=DEV)
-    if case.guidance is None:
-      xs, q, cache = model._ddpm_denoise(xt, sigma_t, mc_t, mc_s)
-    elif case.guidance == 'cfg':
-      cond = torch.full((B,), case.condition, dtype=torch.long, device=DEV)
-      xs, q, cache = model._cfg_denoise(cond, case.gamma, xt, sigma_t, mc_t, mc_s)
-    else:
-      xs, q, cache = model._cbg_denoise(
-        case.condition, case.gamma, model.classifier_model, xt, sigma_t, mc_t, mc_s,
-        use_approx=case.use_approx)
-    torch.cuda.synchronize()
-    param = case.parameterization
-    for k, v in cache.items():
-      if v is None or not k.startswith('log_x_theta'):
-        continue
-      # the API caches logits; the reference caches their (bf16) log-softmax
-      lp = ref_sampler.log_probs_from_logits(
-        v.float().cpu(), xt.cpu(), parameterization=param,
-        mask_index=tok.mask_token_id, subs_masking=case.subs_masking,
-        lp_dtype=torch.bfloat16)
-      g = torch.from_numpy(gold[f's{i}_{k}']).float()
-      fin = torch.isfinite(g) & (g > -1e5) & (g != 0)
-      rel = ((lp - g).abs() / g.abs())[fin]
-      assert (rel == 0).float().mean().item() >= 0.25, (name, i, k)
-      assert rel.max().item() <= 2.5e-2, (name, i, k, rel.max().item())
-    g = torch.from_numpy(gold[f's{i}_q_xs']).float()
-    pos = g > 1e-9
-    rel = ((q.float().cpu().view_as(g) - g).abs() / g.clamp_min(1e-30))[pos]
-    assert rel.median().item() <= 3e-2 and rel.max().item() <= 0.35, (
-      name, i, rel.median().item(), rel.max().item())
-    gx = torch.from_numpy(gold[f's{i}_xs']).long()
-    n_ids += gx.numel()
-    n_diff += int((xs.cpu() != gx).sum())
-  assert n_diff <= max(2, n_ids // 20), (name, n_diff, n_ids)
+  3 bf16 ulps everywhere, and the ids may differ only at a few near-ties.  The
+  V = 30522 cases compare the strided column summary the fixtures keep.  (The same
+  comparison against the reference run ON the GPU: tests/test_gpu_reference.py.)"""
+  helpers.check_against_reference_trace(
+    cases.CASE_BY_NAME[name], helpers.load_golden(name + '_amp'), min_exact=0.25,
+    max_rel_lp=2.5e-2, q_med=3e-2, q_max=0.35, id_frac=0.05)

@@ -48,27 +48,39 @@ def test_oracle_replays_reference(name):
   assert torch.equal(xt, torch.from_numpy(gold['samples']).long())
 
 
-def test_oracle_replays_reference_ar():
-  case = cases.CASE_BY_NAME['ar_null']
-  gold = helpers.load_golden('ar_null')
+@pytest.mark.parametrize('name', ['ar_null', 'ar_cfg_g2', 'ar_lowconf'])
+def test_oracle_replays_reference_ar(name):
+  """AR sampler incl. `_ar_cfg_denoise` (diffusion.py:1188-1236) and the
+  low-confidence `_sample_token` (:1024-1038): ids bit-exact."""
+  case = cases.CASE_BY_NAME[name]
+  gold = helpers.load_golden(name)
   cfg, tok, sd, _ = helpers.case_state(case)
   G = cases.ar_gumbel(case)
-  x = torch.zeros(case.batch, case.length, dtype=torch.long)
+  B = case.batch
+  x = torch.zeros(B, case.length, dtype=torch.long)
   x[:, 0] = tok.bos_token_id
+  cond = torch.full((B,), case.condition, dtype=torch.long)
+  uncond = torch.full((B,), case.num_classes, dtype=torch.long)
+  lowc = case.low_confidence_threshold if case.low_confidence else None
+
+  def log_probs(ids, c):
+    logits = ref_dit.dit_forward(sd, ids, None, c, n_heads=case.n_heads, causal=True)
+    return ref_sampler.log_probs_from_logits(logits, ids, parameterization='ar',
+                                             mask_index=tok.mask_token_id)
   for i in range(case.length - 1):
-    logits = ref_dit.dit_forward(sd, x[:, :i + 1], None, None,
-                                 n_heads=case.n_heads, causal=True)
-    lp = ref_sampler.log_probs_from_logits(
-      logits, x[:, :i + 1], parameterization='ar',
-      mask_index=tok.mask_token_id)
-    x[:, i + 1] = ref_sampler.ar_select(lp[:, -1], G[:, i])
+    if case.guidance == 'cfg':
+      lp = ref_sampler.ar_cfg_mix(log_probs(x[:, :i + 1], cond)[:, -1],
+                                  log_probs(x[:, :i + 1], uncond)[:, -1], case.gamma)
+    else:
+      lp = log_probs(x[:, :i + 1], None)[:, -1]
+    x[:, i + 1] = ref_sampler.ar_select(lp, G[:, i], low_confidence=lowc)
   assert torch.equal(x, torch.from_numpy(gold['samples']).long())
   # causal: the full-length forward reproduces every prefix forward's last row
-  logits = ref_dit.dit_forward(sd, x, None, None, n_heads=case.n_heads,
-                               causal=True)
-  lp = ref_sampler.log_probs_from_logits(
-    logits, x, parameterization='ar', mask_index=tok.mask_token_id)
-  helpers.check_summary('log_probs_final', lp, gold, False, 2e-4, 2e-4)
+  if case.guidance == 'cfg':
+    helpers.check_summary('log_probs_final_cond', log_probs(x, cond), gold, False, 2e-4, 2e-4)
+    helpers.check_summary('log_probs_final_uncond', log_probs(x, uncond), gold, False, 2e-4, 2e-4)
+  else:
+    helpers.check_summary('log_probs_final', log_probs(x, None), gold, False, 2e-4, 2e-4)
 
 
 # ---------------------------------------------------------------- GPU rounding points
