@@ -59,7 +59,7 @@ classifier_head_bwd_kernel(const float* __restrict__ x, int seq_len, int hidden,
     const float ls = logf(s);
     for (int c = 0; c < n_classes; ++c) {
       const float lp = (logit[c] - m) - ls;
-      log_probs[n * n_classes + c] = round_bf16 ? bf16_round(lp) : lp;
+      log_probs[n * n_classes + c] = lp;   // fp32 log_softmax of the bf16 logits (classifier.py:325-327)
       logit[c] = (c == target ? 1.f : 0.f) - expf(lp);       // d log p[target] / d logit[c]
     }
   }

@@ -340,9 +340,11 @@ classifier_head_kernel(const float* __restrict__ x, int seq_len, int hidden,
     for (int c = 0; c < n_classes; ++c) s += expf(logit[c] - m);
     const float ls = logf(s);
     for (int c = 0; c < n_classes; ++c) {
-      float v = (logit[c] - m) - ls;
-      if (round_bf16) v = bf16_round(v);
-      log_probs[n * n_classes + c] = v;
+      // fp32 even on the reference's GPU path: `get_log_probs` runs log_softmax inside
+      // `torch.cuda.amp.autocast(dtype=torch.float32)` (classifier.py:325-327), which CUDA
+      // autocast honours by casting the bf16 class logits up (measured on the B200:
+      // classifier_log_prob is float32, tests/golden/*_cbg_gpu.npz)
+      log_probs[n * n_classes + c] = (logit[c] - m) - ls;
     }
   }
 }

@@ -59,6 +59,8 @@ struct GemmParams {
   int mask_col;         // column excluded from the partials (-1: none)
   int accumulate;       // ACCUM_F32: add to the existing output
   int rope_pos0;        // QKV_ROPE: position offset
+  int stream_out;       // output larger than L2 (the vocab head's logits): evict-first stores,
+                        // evict-last operand loads, so the write stream does not push W out of L2
 };
 
 // ------------------------------------------------------------------ PTX
@@ -138,6 +140,30 @@ __device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* m, uint32_t 
     "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
     ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
     : "memory");
+}
+// L2 eviction-priority policies (PTX createpolicy) for cache-hinted loads / stores
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_2cta_hint(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst,
+                                                      int c0, int c1, uint64_t policy) {
+  asm volatile(
+    "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+    "[%0], [%1, {%3, %4}], [%2], %5;"
+    ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
+    : "memory");
+}
+__device__ __forceinline__ void st_global_v4_hint(void* ptr, uint4 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w), "l"(policy)
+               : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -428,6 +454,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t keep = policy_evict_last();
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m0 = (tile / num_n) * (2 * BM) + (int)cta_rank * BM;     // this CTA's A rows
         const int nb0 = (tile % num_n) * BN + (int)cta_rank * BNH;         // this CTA's half of W
@@ -436,8 +463,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const uint32_t full_leader = map_to_cta(smem_u32(&full_bar[stage]), 0);
           // only the leader arrives; its expect-tx covers both CTAs' bytes
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-          tma_load_2d_2cta(&tma_a, full_leader, smem_a + stage * A_STAGE_BYTES, kb * BK, m0);
-          tma_load_2d_2cta(&tma_b, full_leader, smem_b + stage * B_STAGE_BYTES, kb * BK, nb0);
+          if (p.stream_out) {
+            // W (and the A block the concurrent tiles share) are re-read by every M-block:
+            // keep them in L2 ahead of the output stream
+            tma_load_2d_2cta_hint(&tma_a, full_leader, smem_a + stage * A_STAGE_BYTES, kb * BK, m0, keep);
+            tma_load_2d_2cta_hint(&tma_b, full_leader, smem_b + stage * B_STAGE_BYTES, kb * BK, nb0, keep);
+          } else {
+            tma_load_2d_2cta(&tma_a, full_leader, smem_a + stage * A_STAGE_BYTES, kb * BK, m0);
+            tma_load_2d_2cta(&tma_b, full_leader, smem_b + stage * B_STAGE_BYTES, kb * BK, nb0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -641,6 +675,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                        __float_as_uint(b23.y));
         }
         __syncwarp();
+        const uint64_t pol_out = policy_evict_first();
         // stages 32 columns (16 packed words per row) through the slab and stores them coalesced
         auto store_chunk = [&](const uint32_t (&w)[16], int nc) {
           __syncwarp();
@@ -655,7 +690,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (mw + row < p.M) {
               T* dst = oslab + (int64_t)row * p.ld_out + nc;
               if (col + 8 <= p.N) {
-                *reinterpret_cast<uint4*>(dst) = y;
+                if (p.stream_out) st_global_v4_hint(dst, y, pol_out);
+                else *reinterpret_cast<uint4*>(dst) = y;
               } else {
                 const T* ye = reinterpret_cast<const T*>(&y);
                 for (int k = 0; k < 8; ++k)
@@ -927,6 +963,11 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
   p.stats = reinterpret_cast<float2*>(a.stats); p.stats_ld = a.stats_ld; p.mask_col = a.stats_mask_col;
   p.accumulate = a.accumulate;
   p.rope_pos0 = a.rope_pos0;
+  // a 16-bit output that cannot stay in the 126 MB L2 anyway (the vocab head: 8 GB of logits at
+  // 131072 rows) is written with an evict-first policy and its operands are loaded evict-last:
+  // without this the write-allocate stream kept evicting W (47 MB) and ncu showed 4.4 GB of DRAM
+  // reads per launch against 0.25 GB algorithmic (profiles/r01_traffic.json)
+  p.stream_out = (a.epilogue == DDG_EPI_STORE && (int64_t)a.M * a.N * 2 >= ((int64_t)256 << 20)) ? 1 : 0;
   if (a.stats) {
     DDG_REQUIRE(a.epilogue == DDG_EPI_STORE && a.stats_ld >= a.M &&
                 reinterpret_cast<uintptr_t>(a.stats) % 8 == 0, DDG_ERR_INVALID,

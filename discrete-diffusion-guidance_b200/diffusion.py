@@ -463,8 +463,10 @@ class Diffusion:
       mc_seq_stride=1 if mct.numel() > 1 else 0, noise=noise,
       q_out=q, guidance=_lib.GUIDE_CBG, gamma=gamma, step=self._step_index,
       stats=self._stats_of(logits),
-      # exact term: bf16 tensor in the reference, so gamma * term rounds to bf16
-      clf_round_bf16=self.round_bf16 and not use_approx)
+      # the classifier term is fp32 in the reference on a GPU too (its log_softmax runs under
+      # autocast(float32), classifier.py:325-327; measured: tests/golden/*_cbg_gpu.npz), so
+      # gamma * term is an fp32 product: no bf16 rounding of it
+      clf_round_bf16=False)
     if self._low_confidence:
       self._low_confidence_draw(q, xt, xs, noise,
                                 carry=self.diffusion == 'absorbing_state')

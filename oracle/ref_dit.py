@@ -237,4 +237,9 @@ def classifier_log_probs(sd, ids_or_one_hot, sigma, *, n_heads,
     sigma = torch.zeros_like(sigma)
   logits = classifier_forward(sd, ids_or_one_hot, sigma, n_heads=n_heads,
                               prefix=prefix, rounding=rounding)
-  return _r(F.log_softmax(logits, dim=-1), rounding.head)
+  # fp32 on the GPU as well: the log_softmax sits inside `autocast(dtype=float32)`
+  # (classifier.py:325-327), which CUDA autocast does NOT disable -- log_softmax is on
+  # its fp32 list, so the bf16 class logits are cast up.  Measured on the B200
+  # (classifier_log_prob_dtype == float32 in tests/golden/*_cbg_gpu.npz); SURVEY 8a'
+  # item 6 assumed bf16.
+  return F.log_softmax(logits, dim=-1)

@@ -204,10 +204,10 @@ def cbg_update(lp, clf_log_prob, gamma, xt, mc_t, mc_s, U, *, diffusion,
                low_confidence=None, clf_dtype=None):
   """`_cbg_denoise` after the forward and classifier term
   (diffusion.py:1587-1621).  clf_log_prob (B,L,V) fp32 values.  `clf_dtype`:
-  dtype the classifier term HAS in the reference -- bf16 for the exact term on a
-  GPU (classifier.py:325-327 returns the bf16 log_softmax), so that
-  `gamma * classifier_log_prob` (python float x bf16 tensor, :1607, :1612) is
-  itself rounded to bf16; the first-order term is fp32 (:1540-1547) -> None."""
+  dtype of the classifier term when it is not fp32 (then `gamma * term`, :1607,
+  :1612, rounds to it).  The reference's term is fp32 on CPU AND on a GPU (exact:
+  log_softmax under autocast(float32), classifier.py:325-327, measured on the B200;
+  first-order: fp32 autograd result, :1540-1547), so this stays None."""
   gc = gamma * clf_log_prob
   if clf_dtype is not None:
     gc = gc.to(clf_dtype).float()
@@ -367,7 +367,7 @@ class OracleSampler:
         term = cbg_classifier_term_exact(
           self.clf_log_probs, xt, sigma_t, self.V, condition)
       xs, q = cbg_update(lp, term, gamma, xt, mc_t, mc_s, U,
-                         clf_dtype=None if use_approx else self.lp_dtype, **kw)
+                         clf_dtype=None, **kw)   # the term is fp32 on a GPU too (ref_dit.classifier_log_probs)
       return xs, q, {'log_x_theta': lp, 'classifier_log_prob': term}
     raise NotImplementedError(
       f'Guidance method {guidance} not implemented.')

@@ -228,23 +228,47 @@ def load_reference():
 class _CpuAutocast:
   """Stand-in for `torch.cuda.amp.autocast` that applies the SAME dtype policy
   with CPU autocast, so that the unmodified reference rounds on the CPU where it
-  rounds on a GPU: fp16 / bf16 requests become `torch.autocast('cpu', dtype)`;
-  any other dtype (the reference asks for float32, diffusion.py:353,
-  classifier.py:312,325) disables autocast, which is what CUDA autocast does with
-  an unsupported dtype (torch/amp/autocast_mode.py)."""
+  rounds on a GPU: fp16 / bf16 requests become `torch.autocast('cpu', dtype)`.
+  A float32 request (diffusion.py:353, classifier.py:312,325) is NOT a no-op on
+  CUDA: torch keeps that autocast enabled (torch/amp/autocast_mode.py only rejects
+  unsupported dtypes for non-cuda devices), so ops on autocast's fp32 list --
+  on this path `log_softmax` in `Classifier.get_log_probs` -- get their 16-bit
+  inputs cast up to float32.  Confirmed by the reference's own run on the B200
+  (classifier_log_prob is float32 there).  CPU autocast has no float32 mode, so it
+  is emulated: nested lower-precision autocast is switched off and
+  `F.log_softmax` upcasts while the block is active."""
+  _fp32_depth = 0
 
   def __init__(self, enabled=True, dtype=None, cache_enabled=True):
     import torch
     dtype = torch.float16 if dtype is None else dtype
-    if dtype not in (torch.float16, torch.bfloat16):
+    self._fp32 = enabled and dtype not in (torch.float16, torch.bfloat16)
+    if self._fp32:
       enabled, dtype = False, torch.bfloat16
     self._ctx = torch.autocast('cpu', dtype=dtype, enabled=enabled,
                                cache_enabled=cache_enabled)
 
   def __enter__(self):
+    import torch.nn.functional as F
+    if self._fp32:
+      cls = _CpuAutocast
+      if cls._fp32_depth == 0:
+        cls._orig_log_softmax = F.log_softmax
+
+        def log_softmax(x, *a, **k):
+          # inner fp16 / bf16 blocks have exited by the time the reference calls this
+          return cls._orig_log_softmax(x.float(), *a, **k)
+        F.log_softmax = log_softmax
+      cls._fp32_depth += 1
     return self._ctx.__enter__()
 
   def __exit__(self, *exc):
+    import torch.nn.functional as F
+    if self._fp32:
+      cls = _CpuAutocast
+      cls._fp32_depth -= 1
+      if cls._fp32_depth == 0:
+        F.log_softmax = cls._orig_log_softmax
     return self._ctx.__exit__(*exc)
 
 

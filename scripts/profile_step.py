@@ -17,11 +17,11 @@ def main():
   ap.add_argument('--steps', type=int, default=3)
   args = ap.parse_args()
   dev = torch.device('cuda', 0)
-  model, cfg = bench.build_model(args.batch, dev, 1)
+  model, cfg = bench.build_model(bench.WORKLOADS['c3'], args.batch, dev, 1)
   B, L = args.batch, bench.L
   cond = torch.full((B,), 1, dtype=torch.long, device=dev)
   xt0 = model._sample_prior(B, L)
-  sig, mct, mcs = model._step_scalars(bench.SAMPLING_STEPS, 1e-5)
+  sig, mct, mcs = model._step_scalars(1000, 1e-5)
   loop = model._get_loop(B, L, 'cfg', cfg.guidance)
   model.use_cuda_graph = False
   # tables + labels without capturing a graph

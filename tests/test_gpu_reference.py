@@ -47,9 +47,11 @@ def test_step_api_against_live_reference_on_gpu(name):
     if k.endswith('_dtype') and k.startswith('log_x_theta'):
       assert str(v) == 'torch.bfloat16', (k, v)
   assert str(gold['q_xs_dtype']) == 'torch.float32'
-  if 'classifier_log_prob_dtype' in gold:   # exact term bf16, first-order term fp32
-    assert str(gold['classifier_log_prob_dtype']) == (
-      'torch.float32' if case.use_approx else 'torch.bfloat16')
+  if 'classifier_log_prob_dtype' in gold:
+    # fp32 for the exact term too: `get_log_probs` runs log_softmax inside
+    # autocast(dtype=float32) (classifier.py:325-327), which CUDA autocast honours
+    # (SURVEY 8a' item 6 expected bf16; this run is what corrected it)
+    assert str(gold['classifier_log_prob_dtype']) == 'torch.float32'
   helpers.check_against_reference_trace(case, gold, **TOL)
 
 

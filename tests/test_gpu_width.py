@@ -205,7 +205,7 @@ def test_ar_cfg_sample_follows_oracle_mix_of_own_logits():
   logits), except isolated near-ties."""
   import dataclasses
   case = dataclasses.replace(cases.CASE_BY_NAME['ar_null'], name='ar_cfg', guidance='cfg',
-                             gamma=2.0, length=24, batch=3)
+                             gamma=2.0, length=32, batch=3)
   cfg, tok, sd, _ = helpers.case_state(case)
   model = ddg_b200.Diffusion(cfg, tok, device=DEV).load_state_dict(sd)
   model.round_bf16 = False

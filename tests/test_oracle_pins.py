@@ -94,7 +94,9 @@ def test_oracle_replays_reference_ar(name):
 EXPECTED_DTYPES = {'q_xs': 'torch.float32', 'log_x_theta': 'torch.bfloat16',
                    'log_x_theta_cond': 'torch.bfloat16',
                    'log_x_theta_uncond': 'torch.bfloat16',
-                   'classifier_log_prob': 'torch.bfloat16'}
+                   # fp32 on a GPU as well: log_softmax under autocast(float32)
+                   # (classifier.py:325-327); measured on the B200 (`*_gpu.npz`)
+                   'classifier_log_prob': 'torch.float32'}
 
 
 def _amp_replay(case, gold, gpu_rounding):
@@ -120,13 +122,16 @@ def _amp_replay(case, gold, gpu_rounding):
       yield i, k, (v.float()[..., ::997] if big else v.float()), g
 
 
+@pytest.mark.parametrize('source', ['amp', 'gpu'])
 @pytest.mark.parametrize('name', cases.AMP_CASES)
-def test_oracle_rounding_points_match_reference_under_autocast(name):
+def test_oracle_rounding_points_match_reference_under_autocast(name, source):
+  """`amp`: the reference with its cuda autocast policy emulated on the CPU
+  (make_golden.py --amp); `gpu`: the reference's OWN run on a B200 under real cuda
+  autocast -- cuBLAS / flash-attn / SDPA kernels -- recorded by
+  `make_golden.py --gpu` (tests/golden/<case>_gpu.npz)."""
   case = cases.CASE_BY_NAME[name]
-  gold = helpers.load_golden(name + '_amp')
+  gold = helpers.load_golden(f'{name}_{source}')
   want_dtypes = dict(EXPECTED_DTYPES)
-  if case.use_approx:   # first-order term: fp32 gradient + bf16 scalar (diffusion.py:1540-1547)
-    want_dtypes['classifier_log_prob'] = 'torch.float32'
   for k, want in want_dtypes.items():
     if f'{k}_dtype' in gold:
       assert str(gold[f'{k}_dtype']) == want, (k, gold[f'{k}_dtype'])
@@ -169,15 +174,17 @@ def test_fp32_oracle_is_told_apart_by_the_rounding_pin(name):
 SMALL_AMP_CASES = [n for n in cases.AMP_CASES if cases.CASE_BY_NAME[n].vocab != 'bert']
 
 
+@pytest.mark.parametrize('source', ['amp', 'gpu'])
 @pytest.mark.parametrize('name', SMALL_AMP_CASES)
-def test_sampler_stage_rounding_is_exact_on_reference_log_probs(name):
-  """Feeds the reference's own bf16 log-probs (and bf16 classifier term) of every
+def test_sampler_stage_rounding_is_exact_on_reference_log_probs(name, source):
+  """Feeds the reference's own bf16 log-probs (and fp32 classifier term) of every
   traced step into the oracle's per-step update with the GPU rounding switches on:
   with identical inputs, the posterior must agree to fp32 round-off and the ids
   exactly -- exp / D-CFG mix / softmax round where the reference rounds them
-  (diffusion.py:1395, 1476-1477, 1484-1489, 1596)."""
+  (diffusion.py:1395, 1476-1477, 1484-1489, 1596).  `gpu`: the log-probs, posterior
+  and ids are those of the reference's own B200 run."""
   case = cases.CASE_BY_NAME[name]
-  gold = helpers.load_golden(name + '_amp')
+  gold = helpers.load_golden(f'{name}_{source}')
   tok = cases.Tok(case.vocab)
   B = case.batch
   kw = dict(diffusion=case.diffusion, mask_index=tok.mask_token_id,
@@ -197,17 +204,15 @@ def test_sampler_stage_rounding_is_exact_on_reference_log_probs(name):
       xs, q = ref_sampler.cfg_update(lp['log_x_theta_cond'], lp['log_x_theta_uncond'],
                                      case.gamma, xt, mc_t, mc_s, U, **kw)
     else:
-      # the exact classifier term is a bf16 tensor: gamma * term rounds to bf16
+      # the classifier term is fp32 (classifier.py:325-327): gamma * term stays fp32
       xs, q = ref_sampler.cbg_update(lp['log_x_theta'], lp['classifier_log_prob'],
-                                     case.gamma, xt, mc_t, mc_s, U,
-                                     clf_dtype=None if case.use_approx else torch.bfloat16,
-                                     **kw)
+                                     case.gamma, xt, mc_t, mc_s, U, **kw)
     g = torch.from_numpy(gold[f's{i}_q_xs']).float()
     torch.testing.assert_close(q.float(), g, rtol=2e-5, atol=1e-9)
     assert torch.equal(xs, torch.from_numpy(gold[f's{i}_xs']).long()), (name, i)
     # and the switches matter: without the bf16 roundings the posterior moves by > 1e-4
-    # (MDLM + first-order D-CBG has no rounding after the log-probs: nothing to tell apart)
-    if not (case.use_approx and case.diffusion == 'absorbing_state'):
+    # (MDLM + D-CBG has no rounding after the log-probs: nothing to tell apart)
+    if not (case.guidance == 'cbg' and case.diffusion == 'absorbing_state'):
       kw32 = dict(kw, lp_dtype=None)
       if case.guidance is None:
         _, q32 = ref_sampler.ddpm_update(lp['log_x_theta'], xt, mc_t, mc_s, U, **kw32)
