@@ -412,12 +412,13 @@ def side_config(key, world, rank, device, K, W):
       steps_timed = Kc
     else:
       absorbing = 'diffusion=absorbing_state' in wl.overrides
-      # MDLM: the work per step follows the masked fraction (1 -> 0 over a run), so time
-      # one WHOLE trajectory compressed into Kc steps; uniform: steps are shape-identical
-      Kc = max(8, min(K, 64 if absorbing else 24))
-      run = GraphRun(wl, B, device, ddist.rank_seed(1, rank),
-                     table_steps=Kc if absorbing else None)
-      run.replay(min(W, Kc))
+      # MDLM: the work per step depends on where the run is (masked fraction 1 -> 0, and
+      # with the per-sequence logits cache on how many sequences a step changes, which is
+      # set by sampling.steps), so time one WHOLE sample() of the config's own 1000 steps;
+      # uniform: steps are shape-identical
+      Kc = wl.sampling_steps if absorbing else max(8, min(K, 24))
+      run = GraphRun(wl, B, device, ddist.rank_seed(1, rank))
+      run.replay(min(W, 8))
       run.restart()
       ms, _ = run.timed(Kc, world, device, gather=True)
       steps_timed = Kc
@@ -601,17 +602,26 @@ def run_gpu_arm(args, rank, world, local_rank):
   # ---- graph loop: tables for a full run of the config, one captured step
   run = GraphRun(wl, B, device, seed)
   model, cfg, loop = run.model, run.cfg, run.loop
+  if 'diffusion=absorbing_state' in wl.overrides:
+    # data-dependent work per step: the timed region is one whole sample() of the config
+    run.replay(W)
+    run.restart()
+    K = wl.sampling_steps
+    args.no_settle = True
   # warm-up: W steps, and at least ~2 s of replay so the board reaches its power-capped
   # steady state before the timed region (clocks settle over the first second)
-  run.replay(W)
-  torch.cuda.synchronize()
-  t0 = time.perf_counter()
-  run.replay(8)
-  torch.cuda.synchronize()
-  per = (time.perf_counter() - t0) / 8
-  settle = 0 if args.no_settle else int(min(400, max(0, 2.0 / max(per, 1e-4) - W - 8)))
-  run.replay(settle)
-  W_eff = W + 8 + settle
+  if args.no_settle:
+    settle, W_eff = 0, W
+  else:
+    run.replay(W)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run.replay(8)
+    torch.cuda.synchronize()
+    per = (time.perf_counter() - t0) / 8
+    settle = int(min(400, max(0, 2.0 / max(per, 1e-4) - W - 8)))
+    run.replay(settle)
+    W_eff = W + 8 + settle
   ms_per_step, clk = run.timed(K, world, device, gather=True, clock_index=local_rank)
   value = world * B / (wl.sampling_steps * ms_per_step * 1e-3)
 

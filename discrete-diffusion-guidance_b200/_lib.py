@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DDG_B200_LIB: developer knob for same-box A/B runs of two builds of the library
 LIB_PATH = os.environ.get('DDG_B200_LIB') or os.path.join(_HERE, 'libddg_b200.so')
 
-ABI_VERSION = 3   # DDG_ABI_VERSION of include/ddg_b200.h these bindings were written for
+ABI_VERSION = 4   # DDG_ABI_VERSION of include/ddg_b200.h these bindings were written for
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 F32, F16, BF16 = 0, 1, 2
 ABSORBING, UNIFORM, AR = 0, 1, 2
@@ -26,8 +26,8 @@ DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 EXPORTS = (
   'ddg_abi_version', 'ddg_last_error', 'ddg_device_check', 'ddg_sm_count',
   'ddg_sample_step', 'ddg_low_confidence_select', 'ddg_log_probs', 'ddg_sample_prior', 'ddg_step_advance',
-  'ddg_cond_embed', 'ddg_adaln', 'ddg_ln_modulate', 'ddg_gemm',
-  'ddg_attention', 'ddg_attention_decode', 'ddg_cast', 'ddg_classifier_head', 'ddg_cbg_candidates',
+  'ddg_cond_embed', 'ddg_adaln', 'ddg_ln_modulate', 'ddg_ln_modulate_live', 'ddg_seq_compact', 'ddg_gemm',
+  'ddg_attention', 'ddg_attention_live', 'ddg_attention_decode', 'ddg_cast', 'ddg_classifier_head', 'ddg_cbg_candidates',
   'ddg_classifier_head_backward', 'ddg_gate_mul', 'ddg_gelu_backward',
   'ddg_ln_modulate_backward', 'ddg_attention_backward', 'ddg_split16',
   'ddg_cbg_first_order')
@@ -50,7 +50,8 @@ class SampleStepArgs(C.Structure):
     ('seed', C.c_uint64), ('step', C.c_int32), ('stats_chunks', C.c_int32),
     ('stats_a', C.c_void_p), ('stats_b', C.c_void_p), ('stats_ld', C.c_int64),
     ('race_group', C.c_int32), ('compute_f64', C.c_int32),
-    ('clf_round_bf16', C.c_int32), ('reserved0', C.c_int32)]   # ABI v3
+    ('clf_round_bf16', C.c_int32), ('reserved0', C.c_int32),   # ABI v3
+    ('seq_changed', C.c_void_p)]                               # ABI v4
 
 
 class GemmArgs(C.Structure):
@@ -64,7 +65,8 @@ class GemmArgs(C.Structure):
     ('seq_len', C.c_int32), ('head_dim', C.c_int32), ('rope_cols', C.c_int32),
     ('stats', C.c_void_p), ('stats_ld', C.c_int64),
     ('stats_mask_col', C.c_int32), ('accumulate', C.c_int32),
-    ('rope_pos0', C.c_int32), ('reserved', C.c_int32)]
+    ('rope_pos0', C.c_int32), ('reserved', C.c_int32),
+    ('live_seqs', C.c_void_p), ('out_seq_map', C.c_void_p)]      # ABI v4
 
 
 def _load():
@@ -95,8 +97,12 @@ def _load():
                             i64, vp]
   lib.ddg_ln_modulate.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, vp, i64,
                                   i64, i32, vp, vp]
+  lib.ddg_ln_modulate_live.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, vp, i64,
+                                       i64, i32, vp, vp, i32, vp, vp]
+  lib.ddg_seq_compact.argtypes = [vp, i32, vp, vp, vp]
   lib.ddg_gemm.argtypes = [C.POINTER(GemmArgs), vp]
   lib.ddg_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+  lib.ddg_attention_live.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
   lib.ddg_attention_decode.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
   lib.ddg_cast.argtypes = [vp, vp, i64, i32, vp]
   lib.ddg_classifier_head.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp,

@@ -99,7 +99,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // the 128B swizzle), then two mbarriers.
 template <typename T, bool CAUSAL, bool FULL>
 __global__ void __launch_bounds__(512)
-attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__ out, int L, int H, int n_items) {
+attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__ out, int L, int H, int n_items,
+                 const int32_t* __restrict__ live_seqs) {
+  if (live_seqs) n_items = min(n_items, __ldg(live_seqs) * H);   // dynamic batch
   extern __shared__ uint8_t sm_raw[];
   const uint32_t sm_base = (static_cast<uint32_t>(__cvta_generic_to_shared(sm_raw)) + 1023u) & ~1023u;
   uint8_t* sm_gen = sm_raw + (sm_base - static_cast<uint32_t>(__cvta_generic_to_shared(sm_raw)));
@@ -387,7 +389,11 @@ template <typename T> __device__ __forceinline__ constexpr uint32_t idesc(int n,
 template <typename T, int LSEQ>
 __global__ void __launch_bounds__(160, LSEQ > 128 ? 1 : 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__ out, int H, int n_items,
-                    int64_t total_rows) {
+                    int64_t total_rows, const int32_t* __restrict__ live_seqs) {
+  if (live_seqs) {       // dynamic batch: the live rows are the first *live_seqs sequences
+    total_rows = min(total_rows, (int64_t)__ldg(live_seqs) * LSEQ);
+    n_items = min(n_items, (int)((total_rows + L_TC - 1) / L_TC) * H);
+  }
   constexpr int NK = LSEQ > L_TC ? LSEQ / L_TC : 1;      // 128-key tiles
   constexpr int NKEY = NK * L_TC;
   constexpr uint32_t TMEM_COLS = NK == 1 ? 256u : 512u;  // S (NKEY) + O (64), power of two
@@ -575,7 +581,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
 }  // namespace tc
 
 template <typename T, bool CAUSAL, bool FULL>
-int launch_attention_k(const void* qkv, void* out, int batch, int L, int H, int dtype, cudaStream_t s) {
+int launch_attention_k(const void* qkv, void* out, int batch, int L, int H, int dtype, const int32_t* live,
+                       cudaStream_t s) {
   const int buf = (3 * L * 128 + 1023) / 1024 * 1024;
   const int smem = 2 * buf + 1024 /*align slack*/ + 64 /*barriers*/;
   static bool attr_done[64] = {false};
@@ -594,12 +601,14 @@ int launch_attention_k(const void* qkv, void* out, int batch, int L, int H, int 
   const int ctas_per_sm = smem <= 100 * 1024 ? 2 : 1;
   int grid = sm_count() * ctas_per_sm;
   if (grid > n_items) grid = n_items;
-  attention_kernel<T, CAUSAL, FULL><<<grid, (L / 16) * 32, smem, s>>>(map, reinterpret_cast<T*>(out), L, H, n_items);
+  attention_kernel<T, CAUSAL, FULL><<<grid, (L / 16) * 32, smem, s>>>(map, reinterpret_cast<T*>(out), L, H, n_items,
+                                                                      live);
   return check_cuda(cudaGetLastError(), "attention launch");
 }
 
 template <typename T, bool CAUSAL>
-int launch_attention(const void* qkv, void* out, int batch, int L, int H, int dtype, cudaStream_t s) {
+int launch_attention(const void* qkv, void* out, int batch, int L, int H, int dtype, const int32_t* live,
+                     cudaStream_t s) {
   if (!CAUSAL && (L == 256 || L == tc::L_TC || L == 64 || L == 32) && (int64_t)batch * L >= tc::L_TC) {
     // tensor-memory kernel: the benchmark shape, short sequences packed 128 rows per item,
     // and 256-token sequences as two query tiles against 256 keys
@@ -622,15 +631,15 @@ int launch_attention(const void* qkv, void* out, int batch, int L, int H, int dt
       attr_done[dev] = true;                                                                                  \
     }                                                                                                         \
     tc::attention_tc_kernel<T, LSEQ><<<grid, 160, tc::smem_tc(LSEQ > 128 ? LSEQ / 128 : 1), s>>>(               \
-      map, reinterpret_cast<T*>(out), H, n_items, rows);                                                      \
+      map, reinterpret_cast<T*>(out), H, n_items, rows, live);                                                \
   }
     if (L == 256) DDG_TC_LAUNCH(256) else if (L == tc::L_TC) DDG_TC_LAUNCH(128)
     else if (L == 64) DDG_TC_LAUNCH(64) else DDG_TC_LAUNCH(32)
 #undef DDG_TC_LAUNCH
     return check_cuda(cudaGetLastError(), "attention_tc launch");
   }
-  if (!CAUSAL && L % 64 == 0) return launch_attention_k<T, false, true>(qkv, out, batch, L, H, dtype, s);
-  return launch_attention_k<T, CAUSAL, false>(qkv, out, batch, L, H, dtype, s);
+  if (!CAUSAL && L % 64 == 0) return launch_attention_k<T, false, true>(qkv, out, batch, L, H, dtype, live, s);
+  return launch_attention_k<T, CAUSAL, false>(qkv, out, batch, L, H, dtype, live, s);
 }
 
 }  // namespace
@@ -662,9 +671,10 @@ extern "C" int ddg_attention_decode(const void* qkv_cache, void* out, int32_t ba
   return check_cuda(cudaGetLastError(), "attention_decode launch");
 }
 
-extern "C" int ddg_attention(const void* qkv, void* out, int32_t batch, int32_t seq_len, int32_t n_heads,
-                             int32_t head_dim, int32_t causal, int32_t dtype, ddg_stream_t stream) {
-  using namespace ddg;
+namespace ddg {
+namespace {
+int attention_impl(const void* qkv, void* out, int32_t batch, int32_t seq_len, int32_t n_heads,
+                   int32_t head_dim, int32_t causal, int32_t dtype, const int32_t* live, ddg_stream_t stream) {
   int rc = ddg_device_check();
   if (rc) return rc;
   DDG_REQUIRE(qkv && out && batch >= 0 && n_heads > 0, DDG_ERR_INVALID, "attention: bad args");
@@ -676,11 +686,24 @@ extern "C" int ddg_attention(const void* qkv, void* out, int32_t batch, int32_t 
   if (batch == 0) return DDG_OK;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == DDG_F16)
-    return causal ? launch_attention<__half, true>(qkv, out, batch, seq_len, n_heads, dtype, s)
-                  : launch_attention<__half, false>(qkv, out, batch, seq_len, n_heads, dtype, s);
+    return causal ? launch_attention<__half, true>(qkv, out, batch, seq_len, n_heads, dtype, live, s)
+                  : launch_attention<__half, false>(qkv, out, batch, seq_len, n_heads, dtype, live, s);
   if (dtype == DDG_BF16)
-    return causal ? launch_attention<__nv_bfloat16, true>(qkv, out, batch, seq_len, n_heads, dtype, s)
-                  : launch_attention<__nv_bfloat16, false>(qkv, out, batch, seq_len, n_heads, dtype, s);
+    return causal ? launch_attention<__nv_bfloat16, true>(qkv, out, batch, seq_len, n_heads, dtype, live, s)
+                  : launch_attention<__nv_bfloat16, false>(qkv, out, batch, seq_len, n_heads, dtype, live, s);
   set_error("attention: dtype must be f16 or bf16");
   return DDG_ERR_INVALID;
+}
+}  // namespace
+}  // namespace ddg
+
+extern "C" int ddg_attention(const void* qkv, void* out, int32_t batch, int32_t seq_len, int32_t n_heads,
+                             int32_t head_dim, int32_t causal, int32_t dtype, ddg_stream_t stream) {
+  return ddg::attention_impl(qkv, out, batch, seq_len, n_heads, head_dim, causal, dtype, nullptr, stream);
+}
+
+extern "C" int ddg_attention_live(const void* qkv, void* out, int32_t batch, int32_t seq_len, int32_t n_heads,
+                                  int32_t head_dim, int32_t causal, int32_t dtype, const int32_t* live_seqs,
+                                  ddg_stream_t stream) {
+  return ddg::attention_impl(qkv, out, batch, seq_len, n_heads, head_dim, causal, dtype, live_seqs, stream);
 }

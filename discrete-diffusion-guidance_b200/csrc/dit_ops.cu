@@ -123,13 +123,18 @@ ln_modulate_kernel(float* __restrict__ x, int64_t rows, int hidden,
                    const float* __restrict__ embedding,
                    const float* __restrict__ ln_w, const T* __restrict__ shift,
                    const T* __restrict__ ops, int64_t mod_stride, int64_t rows_per_mod,
-                   T* __restrict__ out) {
+                   T* __restrict__ out, const int32_t* __restrict__ live_seqs, int seq_len,
+                   const int32_t* __restrict__ seq_map) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // dynamic batch: only the first *live_seqs sequences of the (compact) activations exist
+  if (live_seqs) rows = min(rows, (int64_t)*live_seqs * seq_len);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nv = hidden >> 7;  // float4 per lane
   float4 v[MAXV];
-  const float* src = ids ? embedding + ids[row % ids_period] * (int64_t)hidden : x + row * (int64_t)hidden;
+  // compact row -> position of its token id (sequence seq_map[s] of the id buffer)
+  const int64_t id_row = seq_map ? (int64_t)seq_map[row / seq_len] * seq_len + row % seq_len : row;
+  const float* src = ids ? embedding + ids[id_row % ids_period] * (int64_t)hidden : x + row * (int64_t)hidden;
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
@@ -216,8 +221,10 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(128, 4)
 ln_modulate_stream_kernel(const float* __restrict__ x, int64_t rows, const float* __restrict__ ln_w,
                           const T* __restrict__ shift, const T* __restrict__ ops, int64_t mod_stride,
-                          int64_t rows_per_mod, T* __restrict__ out) {
+                          int64_t rows_per_mod, T* __restrict__ out, const int32_t* __restrict__ live_seqs,
+                          int seq_len) {
   constexpr int hidden = NV * 128;
+  if (live_seqs) rows = min(rows, (int64_t)*live_seqs * seq_len);
   const int lane = threadIdx.x & 31;
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -412,10 +419,13 @@ extern "C" int ddg_adaln(const float* c, int32_t n_rows, int32_t cond_dim, const
   return check_cuda(cudaGetLastError(), "adaln launch");
 }
 
-extern "C" int ddg_ln_modulate(float* x, int64_t rows, int32_t hidden, const int64_t* ids,
-                               int64_t ids_period, const float* embedding, const float* ln_weight, const void* shift,
-                               const void* one_plus_scale, int64_t mod_stride, int64_t rows_per_mod,
-                               int32_t dtype, void* out, ddg_stream_t stream) {
+namespace ddg {
+namespace {
+int ln_modulate_impl(float* x, int64_t rows, int32_t hidden, const int64_t* ids,
+                     int64_t ids_period, const float* embedding, const float* ln_weight, const void* shift,
+                     const void* one_plus_scale, int64_t mod_stride, int64_t rows_per_mod,
+                     int32_t dtype, void* out, const int32_t* live_seqs, int32_t seq_len,
+                     const int32_t* seq_map, ddg_stream_t stream) {
   int rc = ddg_device_check();
   if (rc) return rc;
   DDG_REQUIRE(x && ln_weight && out && rows >= 0, DDG_ERR_INVALID, "ln_modulate: bad args");
@@ -433,7 +443,7 @@ extern "C" int ddg_ln_modulate(float* x, int64_t rows, int32_t hidden, const int
 #define DDG_LNS_LAUNCH(T, NV)                                                                        \
   ln_modulate_stream_kernel<T, NV><<<sgrid, 128, 0, s>>>(x, rows, ln_weight, reinterpret_cast<const T*>(shift), \
                                                          reinterpret_cast<const T*>(one_plus_scale), mod_stride, \
-                                                         rows_per_mod, reinterpret_cast<T*>(out))
+                                                         rows_per_mod, reinterpret_cast<T*>(out), live_seqs, seq_len)
     if (dtype == DDG_F16) {
       if (hidden == 512) DDG_LNS_LAUNCH(__half, 4); else DDG_LNS_LAUNCH(__half, 6);
     } else {
@@ -447,7 +457,8 @@ extern "C" int ddg_ln_modulate(float* x, int64_t rows, int32_t hidden, const int
   ln_modulate_kernel<T, MAXV><<<grid, 256, 0, s>>>(x, rows, hidden, ids, ids_period, embedding, ln_weight,      \
                                                    reinterpret_cast<const T*>(shift),               \
                                                    reinterpret_cast<const T*>(one_plus_scale),      \
-                                                   mod_stride, rows_per_mod, reinterpret_cast<T*>(out))
+                                                   mod_stride, rows_per_mod, reinterpret_cast<T*>(out), \
+                                                   live_seqs, seq_len, seq_map)
   if (dtype == DDG_F16) {
     if (hidden <= 1024) DDG_LN_LAUNCH(__half, 8); else DDG_LN_LAUNCH(__half, 16);
   } else if (dtype == DDG_BF16) {
@@ -458,6 +469,69 @@ extern "C" int ddg_ln_modulate(float* x, int64_t rows, int32_t hidden, const int
   }
 #undef DDG_LN_LAUNCH
   return check_cuda(cudaGetLastError(), "ln_modulate launch");
+}
+
+// Ordered compaction of the flagged sequences: seq_map[0..count) = indices s with
+// flags[s] != 0 in increasing order; flags are cleared for the next step.  One CTA.
+__global__ void __launch_bounds__(1024)
+seq_compact_kernel(int32_t* __restrict__ flags, int n_seqs, int32_t* __restrict__ seq_map,
+                   int32_t* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (int s0 = 0; s0 < n_seqs; s0 += 1024) {
+    const int s = s0 + tid;
+    const int f = (s < n_seqs && flags[s] != 0) ? 1 : 0;
+    if (s < n_seqs) flags[s] = 0;
+    int v = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (f) seq_map[off + v - 1] = s;
+    __syncthreads();
+    if (tid == 1023) base = off + v;
+    __syncthreads();
+  }
+  if (tid == 0) *count = base;
+}
+
+}  // namespace
+}  // namespace ddg
+
+extern "C" int ddg_ln_modulate(float* x, int64_t rows, int32_t hidden, const int64_t* ids,
+                               int64_t ids_period, const float* embedding, const float* ln_weight, const void* shift,
+                               const void* one_plus_scale, int64_t mod_stride, int64_t rows_per_mod,
+                               int32_t dtype, void* out, ddg_stream_t stream) {
+  return ddg::ln_modulate_impl(x, rows, hidden, ids, ids_period, embedding, ln_weight, shift, one_plus_scale,
+                               mod_stride, rows_per_mod, dtype, out, nullptr, 1, nullptr, stream);
+}
+
+extern "C" int ddg_ln_modulate_live(float* x, int64_t rows, int32_t hidden, const int64_t* ids,
+                                    int64_t ids_period, const float* embedding, const float* ln_weight,
+                                    const void* shift, const void* one_plus_scale, int64_t mod_stride,
+                                    int64_t rows_per_mod, int32_t dtype, void* out, const int32_t* live_seqs,
+                                    int32_t seq_len, const int32_t* seq_map, ddg_stream_t stream) {
+  DDG_REQUIRE(seq_len > 0, DDG_ERR_INVALID, "ln_modulate_live: seq_len must be positive");
+  if (seq_map) DDG_REQUIRE(ids != nullptr, DDG_ERR_INVALID, "ln_modulate_live: seq_map only applies to the id gather");
+  return ddg::ln_modulate_impl(x, rows, hidden, ids, ids_period, embedding, ln_weight, shift, one_plus_scale,
+                               mod_stride, rows_per_mod, dtype, out, live_seqs, seq_len, seq_map, stream);
+}
+
+extern "C" int ddg_seq_compact(int32_t* flags, int32_t n_seqs, int32_t* seq_map, int32_t* count,
+                               ddg_stream_t stream) {
+  int rc = ddg_device_check();
+  if (rc) return rc;
+  DDG_REQUIRE(flags && seq_map && count && n_seqs >= 0, DDG_ERR_INVALID, "seq_compact: bad args");
+  ddg::seq_compact_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(flags, n_seqs, seq_map, count);
+  return ddg::check_cuda(cudaGetLastError(), "seq_compact launch");
 }
 
 extern "C" int ddg_cast(const float* src, void* dst, int64_t n, int32_t dtype, ddg_stream_t stream) {

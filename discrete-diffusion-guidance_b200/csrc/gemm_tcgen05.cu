@@ -59,6 +59,8 @@ struct GemmParams {
   int mask_col;         // column excluded from the partials (-1: none)
   int accumulate;       // ACCUM_F32: add to the existing output
   int rope_pos0;        // QKV_ROPE: position offset
+  const int32_t* live_seqs;    // optional device scalar: only the first *live_seqs * seq_len rows of A exist
+  const int32_t* out_seq_map;  // optional (STORE): compact sequence s is written to output sequence out_seq_map[s]
   int stream_out;       // output larger than L2 (the vocab head's logits): evict-first stores,
                         // evict-last operand loads, so the write stream does not push W out of L2
 };
@@ -401,6 +403,24 @@ __device__ __forceinline__ float gelu_tanh(float v) {
   return v * r;
 }
 
+// Tile order.  Default: N inner (consecutive tiles = the N-blocks of one M-block, so the
+// clusters running at the same time share one A block and W -- a few MB -- stays in L2).
+// `group_m` > 1 (the vocab head: 120 N-blocks, W = 47 MB, 8 GB of output streaming through
+// L2): M-blocks are taken `group_m` at a time and walked M-inner inside the group, so a W
+// tile is reused by `group_m` tiles in flight at once instead of once per 120-tile sweep.
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& mb, int& nb) {
+  if (group_m <= 1) {
+    mb = tile / num_n;
+    nb = tile % num_n;
+    return;
+  }
+  const int per_group = group_m * num_n;
+  const int g = tile / per_group, r = tile - g * per_group;
+  const int cnt = min(group_m, num_m - g * group_m);
+  nb = r / cnt;
+  mb = g * group_m + (r - nb * cnt);
+}
+
 // ------------------------------------------------------------------ kernel
 template <typename T, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -426,10 +446,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const bool leader = cta_rank == 0;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
+  // dynamic batch (per-sequence logits cache of the MDLM loop): the live row count is a device scalar
+  const int M = p.live_seqs ? min(p.M, __ldg(p.live_seqs) * p.seq_len) : p.M;
+  const int num_m = (M + 2 * BM - 1) / (2 * BM);
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + BK - 1) / BK;
+  const int group_m = p.stream_out ? 8 : 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -456,8 +479,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       uint32_t phase = 0;
       const uint64_t keep = policy_evict_last();
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / num_n) * (2 * BM) + (int)cta_rank * BM;     // this CTA's A rows
-        const int nb0 = (tile % num_n) * BN + (int)cta_rank * BNH;         // this CTA's half of W
+        int mb, nb;
+        tile_coords(tile, num_m, num_n, group_m, mb, nb);
+        const int m0 = mb * (2 * BM) + (int)cta_rank * BM;     // this CTA's A rows
+        const int nb0 = nb * BN + (int)cta_rank * BNH;         // this CTA's half of W
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t full_leader = map_to_cta(smem_u32(&full_bar[stage]), 0);
@@ -531,10 +556,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint32_t acc_phase = 0;
     const uint32_t tmem_empty_leader0 = map_to_cta(smem_u32(&tmem_empty[0]), 0);
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m0 = (tile / num_n) * (2 * BM) + (int)cta_rank * BM;
-      const int n0 = (tile % num_n) * BN + chalf * (BN / 2);
+      int mb, nb;
+      tile_coords(tile, num_m, num_n, group_m, mb, nb);
+      const int m0 = mb * (2 * BM) + (int)cta_rank * BM;
+      const int n0 = nb * BN + chalf * (BN / 2);
       const int m = m0 + row_in_tile;
-      const bool row_ok = m < p.M;
+      const bool row_ok = m < M;
       const int mw = m0 + quarter * 32;         // first row of this warp's slab
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -556,8 +583,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (!PLAIN && p.gate) {
           const int rpm = p.rows_per_mod > 0x7fffffff ? 0x7fffffff : (int)p.rows_per_mod;
           // rows of this warp that exist: [mw, last]; a warp past the end of A uses row 0's gate
-          const int first = mw < p.M ? mw : 0;
-          const int last = mw < p.M ? (mw + 31 < p.M ? mw + 31 : p.M - 1) : 0;
+          const int first = mw < M ? mw : 0;
+          const int last = mw < M ? (mw + 31 < M ? mw + 31 : M - 1) : 0;
           const int mod_first = first / rpm, mod_last = last / rpm;
           gate_uniform = mod_first == mod_last;
           const int mrow = gate_uniform ? mod_first : (row_ok ? m / rpm : 0);
@@ -586,7 +613,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int row = 8 * i + crow;
-              const bool ok = (mw + row < p.M) && (nc + h * 16 + cchunk * 4 < p.N) && (!PLAIN || p.accumulate);
+              const bool ok = (mw + row < M) && (nc + h * 16 + cchunk * 4 < p.N) && (!PLAIN || p.accumulate);
               xn[h][i] = ok ? *reinterpret_cast<const float4*>(xslab + (int64_t)row * p.ld_out + nc + h * 16)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -652,7 +679,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             for (int i = 0; i < 4; ++i) {
               const int row = 8 * i + crow;
               const uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
-              if ((mw + row < p.M) && (nc + h * 16 + cchunk * 4 < p.N)) {
+              if ((mw + row < M) && (nc + h * 16 + cchunk * 4 < p.N)) {
                 float4 o = xc[h][i];
                 o.x += __uint_as_float(y.x); o.y += __uint_as_float(y.y);
                 o.z += __uint_as_float(y.z); o.w += __uint_as_float(y.w);
@@ -665,7 +692,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         // -------- 16-bit outputs: store / rotary / bias+GELU.  Register phase in packed
         // f32x2 arithmetic on column pairs; the bias of this warp's 128 columns sits as
         // fp32 in warp-private shared memory (one broadcast LDS.128 per 4 columns).
-        T* oslab = reinterpret_cast<T*>(p.out) + (int64_t)mw * p.ld_out + cchunk * 8;
+        // a warp's 32 rows lie in one sequence (seq_len % 32 == 0 whenever a map is given)
+        const int mw_out = (p.out_seq_map && mw < M)
+                             ? __ldg(p.out_seq_map + mw / p.seq_len) * p.seq_len + mw % p.seq_len : mw;
+        T* oslab = reinterpret_cast<T*>(p.out) + (int64_t)mw_out * p.ld_out + cchunk * 8;
         const bool have_bias = p.bias != nullptr;
         const uint32_t bias_s = smem_u32(smem_bias) + (uint32_t)e * (BN / 2) * 4;   // shared-window address
         if (have_bias && n0 < p.N) {
@@ -687,7 +717,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int i = 0; i < 4; ++i) {
             const int row = 8 * i + crow;
             const uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
-            if (mw + row < p.M) {
+            if (mw + row < M) {
               T* dst = oslab + (int64_t)row * p.ld_out + nc;
               if (col + 8 <= p.N) {
                 if (p.stream_out) st_global_v4_hint(dst, y, pol_out);
@@ -822,7 +852,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             store_chunk(w, nc);
           }
           if (want_stats && row_ok && n0 < p.N)
-            p.stats[(int64_t)(n0 / (BN / 2)) * p.stats_ld + m] = make_float2(st_m, st_s);
+            p.stats[(int64_t)(n0 / (BN / 2)) * p.stats_ld + (mw_out + (m - mw))] = make_float2(st_m, st_s);
         }
       }
       // this warp has drained its part of the accumulator: one arrival per warp
@@ -963,6 +993,14 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
   p.stats = reinterpret_cast<float2*>(a.stats); p.stats_ld = a.stats_ld; p.mask_col = a.stats_mask_col;
   p.accumulate = a.accumulate;
   p.rope_pos0 = a.rope_pos0;
+  p.live_seqs = a.live_seqs;
+  p.out_seq_map = a.out_seq_map;
+  if (a.live_seqs || a.out_seq_map)
+    DDG_REQUIRE(a.seq_len > 0 && a.M % a.seq_len == 0, DDG_ERR_INVALID,
+                "gemm: live_seqs / out_seq_map need seq_len > 0 dividing M");
+  if (a.out_seq_map)
+    DDG_REQUIRE(a.epilogue == DDG_EPI_STORE && a.seq_len % 32 == 0, DDG_ERR_INVALID,
+                "gemm: out_seq_map needs the STORE epilogue and seq_len %% 32 == 0");
   // a 16-bit output that cannot stay in the 126 MB L2 anyway (the vocab head: 8 GB of logits at
   // 131072 rows) is written with an evict-first policy and its operands are loaded evict-last:
   // without this the write-allocate stream kept evicting W (47 MB) and ncu showed 4.4 GB of DRAM

@@ -268,6 +268,7 @@ low_confidence_kernel(const float* __restrict__ probs, int64_t ld, int64_t rows,
 int launch_sample_f64(const ddg_sample_step_args& a, cudaStream_t s) {
   DDG_REQUIRE(a.guidance == DDG_GUIDE_NONE, DDG_ERR_UNSUPPORTED,
               "use_float64 is only honoured without guidance (reference diffusion.py:1393); not implemented");
+  DDG_REQUIRE(a.seq_changed == nullptr, DDG_ERR_UNSUPPORTED, "seq_changed is not supported with compute_f64");
   int64_t grid = (int64_t)sm_count() * 8;
   if (grid > a.rows) grid = a.rows;
   if (a.logits_dtype == DDG_BF16)

@@ -281,7 +281,11 @@ sample_fused_kernel(const ddg_sample_step_args a) {
         const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
         if (os > best || (os == best && oi < bidx)) { best = os; bidx = oi; }
       }
-      if (lane == 0) a.xs[row] = bidx == 0x7fffffff ? 0 : bidx;
+      if (lane == 0) {
+        const int pick_id = bidx == 0x7fffffff ? 0 : bidx;
+        a.xs[row] = pick_id;
+        if (a.seq_changed && pick_id != z) a.seq_changed[row / a.seq_len] = 1;
+      }
     }
     __syncthreads();
   }

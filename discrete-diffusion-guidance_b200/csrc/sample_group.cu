@@ -725,7 +725,7 @@ sample_group_kernel(const ddg_sample_step_args a) {
     __syncthreads();                                     // B3
     const int win = s_win;
     if (win == 0x7fffffff) {
-      if (tid == 0) a.xs[row] = 0;                      // all-zero row: cannot happen with finite logits
+      if (tid == 0) { a.xs[row] = 0; if (a.seq_changed && z != 0) a.seq_changed[seq] = 1; }   // all-zero row: cannot happen with finite logits
       if (WIDE) { __syncthreads(); __syncthreads(); }   // keep the barrier count of the pick below
     } else if (WIDE) {
       // ---- inverse-CDF pick inside the winning 64-column group: thread i < 64 takes column
@@ -779,7 +779,9 @@ sample_group_kernel(const ddg_sample_step_args a) {
         else if (s_pick_i[1] >= 0) i = 32 + s_pick_i[1];
         else if (s_pick_i[3] >= 0) i = 32 + s_pick_i[3];
         else i = s_pick_i[2] >= 0 ? s_pick_i[2] : 0;
-        a.xs[row] = (int64_t)(wt + kThreads * (8 * wk8 + (i >> 3))) * 8 + (i & 7);
+        const int64_t pick_id = (int64_t)(wt + kThreads * (8 * wk8 + (i >> 3))) * 8 + (i & 7);
+        a.xs[row] = pick_id;
+        if (a.seq_changed && pick_id != z) a.seq_changed[seq] = 1;   // this sequence needs a new forward
       }
     } else if (tid == (win & (kThreads - 1))) {
       // ---- inverse-CDF pick inside the winning group
@@ -802,7 +804,9 @@ sample_group_kernel(const ddg_sample_step_args a) {
         if (pr[e] > 0.f) last = e;
         if (pick < 0 && cum > target) pick = e;
       }
-      a.xs[row] = win * 8 + (pick < 0 ? last : pick);
+      const int pick_id = win * 8 + (pick < 0 ? last : pick);
+      a.xs[row] = pick_id;
+      if (a.seq_changed && pick_id != z) a.seq_changed[seq] = 1;
     }
     // Shared state is rewritten by the next row only before its B1 (s_k, tables, the other
     // s_st buffer), before its B2 (s_red / s_idx) and before its B3 (s_win); every read of

@@ -413,7 +413,10 @@ sample_step_kernel(const ddg_sample_step_args a) {
     }
     Grp<GROUP>::argmax(best, bidx, sm);
     if (bidx == 0x7fffffff) bidx = 0;   // every score was -inf / NaN
-    if (lane_in_group == 0) a.xs[row] = (int64_t)bidx;
+    if (lane_in_group == 0) {
+      a.xs[row] = (int64_t)bidx;
+      if (a.seq_changed && bidx != z) a.seq_changed[seq] = 1;
+    }
     // ---------------- pass 3 (debug / API): q_xs as the reference returns it
     if (a.q_out) {
       float lse = 0.f;

@@ -86,6 +86,11 @@ class Diffusion:
                                 # groups (same distribution, 64x less noise
                                 # work); 8 = 8-column groups; 0 = one
                                 # exponential per vocab entry
+    self.logits_cache = True    # MDLM without time conditioning: a sequence whose tokens did
+                                # not change keeps its logits; only changed sequences go
+                                # through the network (the per-sequence form of the
+                                # reference's sampling.use_cache, diffusion.py:1371-1374;
+                                # ids identical to recomputing everything)
     self.return_q_xs = False    # materialise q_xs (B, L, V) fp32 per step
     self.use_cuda_graph = True
     self.noise_fn = None        # i -> injected U (B, L, V); None -> Philox
@@ -259,7 +264,7 @@ class Diffusion:
                       guidance=_lib.GUIDE_NONE, gamma=1.0, q_out=None,
                       select=None, diffusion=None, logits_dtype=_lib.BF16,
                       seed_ptr=None, stats=None, compute_f64=False,
-                      clf_round_bf16=False):
+                      clf_round_bf16=False, seq_changed=None):
     V = self.vocab_size
     # log-softmax partials of these logits, if our own vocab GEMM made them:
     # stats = (tensor (chunks, rows_total, 2), row offset of a, row offset of b); they
@@ -288,7 +293,7 @@ class Diffusion:
       step=int(step), stats_chunks=st_chunks, stats_a=st_a,
       stats_b=st_b if logits_b else 0, stats_ld=st_ld,
       race_group=int(self.race_group), compute_f64=1 if compute_f64 else 0,
-      clf_round_bf16=1 if clf_round_bf16 else 0)
+      clf_round_bf16=1 if clf_round_bf16 else 0, seq_changed=ptr(seq_changed))
     check(lib.ddg_sample_step(a, stream_ptr()))
 
   def _mc(self, mc):
@@ -530,7 +535,7 @@ class Diffusion:
   def _get_loop(self, B, L, method, guidance):
     gamma = None if guidance is None else float(guidance.gamma)
     key = (B, L, method, gamma, self.round_bf16, self.fast_math,
-           self.race_group)
+           self.race_group, self.logits_cache)
     if self._loop is None or self._loop.key != key:
       self._loop = _GraphLoop(self, B, L, method, gamma, key)
     return self._loop
@@ -730,6 +735,21 @@ class _GraphLoop:
     self.graph = None
     self.ws_generation = -1
     self.steps = 0
+    # Per-sequence logits cache.  Without time conditioning the logits of a sequence are a
+    # function of its tokens alone, and absorbing diffusion changes L / steps tokens per
+    # sequence per step on average (0.128 at L = 128, 1000 steps): most sequences are
+    # untouched by a step.  The sampler flags the sequences it changes, `ddg_seq_compact`
+    # turns the flags into the next step's dynamic batch, and the forward runs on those
+    # sequences only, writing their rows of the persistent logits buffer.  The reference
+    # does this for the whole batch at once (sampling.use_cache: reuse when NO token
+    # changed, diffusion.py:1371-1374); same results, the forward being deterministic per
+    # sequence.
+    self.cached = bool(model.logits_cache and method is None and not model.time_conditioning
+                       and model.diffusion == 'absorbing_state' and L % 32 == 0)
+    if self.cached:
+      self.changed = torch.ones(B, dtype=torch.int32, device=dev)
+      self.seq_map = torch.zeros(B, dtype=torch.int32, device=dev)
+      self.n_live = torch.zeros(1, dtype=torch.int32, device=dev)
 
   def _body(self):
     m, B, L = self.model, self.B, self.L
@@ -737,9 +757,14 @@ class _GraphLoop:
     mod = ModSpec(n_mod=self.n_fwd, seqs_per_mod=B, sigma=sig,
                   sigma_row_stride=0, sigma_step_stride=1, step_ptr=self.step,
                   labels=self.labels)
+    live = None
+    if self.cached:    # flags of the previous step (all set at step 0) -> this step's batch
+      check(lib.ddg_seq_compact(ptr(self.changed), B, ptr(self.seq_map), ptr(self.n_live),
+                                stream_ptr()))
+      live = (self.seq_map, self.n_live)
     m.backbone.run(self.xt, self.n_fwd * B, L, mod, self.logits,
                    ids_period=B * L, stats_out=self.stats,
-                   stats_mask_col=m._stats_mask_col)
+                   stats_mask_col=m._stats_mask_col, live=live)
     ld = m.backbone.vocab_ld
     m._launch_sampler(
       logits_a=self.logits.data_ptr(), ld_a=ld,
@@ -749,7 +774,8 @@ class _GraphLoop:
       step_ptr=self.step, seed_ptr=self.seed_dev,
       stats=(self.stats, 0, B * L if self.two else 0),
       guidance=_lib.GUIDE_CFG if self.two else _lib.GUIDE_NONE,
-      gamma=self.gamma if self.two else 1.0)
+      gamma=self.gamma if self.two else 1.0,
+      seq_changed=self.changed if self.cached else None)
     check(lib.ddg_step_advance(ptr(self.step), stream_ptr()))
 
   def prepare(self, xt, sigma_t, mc_t, mc_s, cond):
@@ -777,24 +803,26 @@ class _GraphLoop:
     self.seed_dev.fill_(m.seed + 7919 * m._call_count)
     if self.graph is not None and self.ws_generation != m.backbone.ws_generation:
       self.graph = None    # workspace buffers were reallocated since capture
+    if self.cached:
+      self.changed.fill_(1)      # new prior: every sequence needs its first forward
     if self.graph is None:
       # one eager step first (lazy attribute / module setup), then capture
       self._body()
       torch.cuda.synchronize()
-      self.xt.copy_(xt)
-      self.step.zero_()
+      self.reset(xt)
       g = torch.cuda.CUDAGraph()
       with torch.cuda.graph(g):
         self._body()
       self.graph = g
       self.ws_generation = m.backbone.ws_generation
-      self.xt.copy_(xt)
-      self.step.zero_()
+      self.reset(xt)
 
   def reset(self, xt):
     """Back to step 0 of the schedule tables with a fresh prior."""
     self.xt.copy_(xt)
     self.step.zero_()
+    if self.cached:
+      self.changed.fill_(1)
 
   def replay(self, n):
     for _ in range(n):

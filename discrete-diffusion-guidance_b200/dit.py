@@ -217,11 +217,18 @@ class DIT:
           ids_period: typing.Optional[int] = None,
           stats_out: typing.Optional[torch.Tensor] = None,
           stats_mask_col: int = -1,
-          save_for_backward: typing.Optional[list] = None):
+          save_for_backward: typing.Optional[list] = None,
+          live: typing.Optional[tuple] = None):
     """Launches one forward over `n_seqs` sequences of length L.  `ids` holds
     `ids_period` (default n_seqs*L) int64 token ids, reused cyclically.
     Denoiser: writes logits (rows, vocab_ld) bf16 into `logits_out`.
-    Classifier: returns the fp32 residual stream (rows, hidden)."""
+    Classifier: returns the fp32 residual stream (rows, hidden).
+
+    `live = (seq_map, n_live)` (device int32 tensors) runs the forward over a
+    DYNAMIC batch: only the sequences `seq_map[0..n_live)` of `ids` go through the
+    network (compact activations), and their logits / partials are written back at
+    their own rows of `logits_out` / `stats_out`; every launch is sized for
+    `n_seqs` and reads the live count on the device (graph-capturable)."""
     assert self._loaded, 'load_state_dict first'
     M = n_seqs * L
     h, nb = self.hidden, self.n_blocks
@@ -255,7 +262,9 @@ class DIT:
       raise ValueError('Conditioning variable provided, but Model was not '
                        'initialized with condition embedding layer.')
     cos, sin = self._rope_tables(L)
-    seg_rows = M if (self.seg_seqs is None or save_for_backward is not None) \
+    if live is not None and (self.classifier or save_for_backward is not None or L % 32):
+      raise ValueError('dynamic batch: denoiser forward only, seq_len % 32 == 0')
+    seg_rows = M if (self.seg_seqs is None or save_for_backward is not None or live is not None) \
         else max(1, self.seg_seqs) * L
     for r0 in range(0, M, seg_rows):
       n = min(seg_rows, M - r0)
@@ -269,15 +278,16 @@ class DIT:
         raise ValueError('micro-batch straddles the id period')
       self._run_segment(ws, ids, r0, n, L, period, mod0, rpm_arg, mod_stride,
                         cos, sin, logits_out, bcode, hcode, s, stats_out,
-                        stats_mask_col, save_for_backward)
+                        stats_mask_col, save_for_backward, live)
     if self.classifier:
       return ws['x'][:M]
     return logits_out
 
   def _run_segment(self, ws, ids, r0, n, L, period, mod0, rpm, mod_stride, cos,
                    sin, logits_out, bcode, hcode, s, stats_out=None,
-                   stats_mask_col=-1, saved=None):
+                   stats_mask_col=-1, saved=None, live=None):
     h, nb = self.hidden, self.n_blocks
+    seq_map, n_live = (ptr(live[0]), ptr(live[1])) if live is not None else (0, 0)
     x = ptr(ws['x']) + r0 * h * 4
     a16, qkv, h4 = ptr(ws['a16']), ptr(ws['qkv']), ptr(ws['h4'])
     modb = ptr(ws['mod_blk']) + mod0 * mod_stride * 2
@@ -285,21 +295,29 @@ class DIT:
     ada = self.use_adaln
 
     def gemm(a, lda, w, ldw, out, ld_out, N, K, epi, dtype, bias=0, gate=0,
-             gate_stride=0, stats=0, stats_ld=0):
+             gate_stride=0, stats=0, stats_ld=0, out_map=0):
       g = _lib.GemmArgs(
         a=a, w=w, out=out, bias=bias, gate=gate, rope_cos=ptr(cos),
         rope_sin=ptr(sin), lda=lda, ldw=ldw, ld_out=ld_out,
         gate_stride=gate_stride, rows_per_mod=rpm, M=n, N=N, K=K, dtype=dtype,
         epilogue=epi, seq_len=L, head_dim=self.head_dim, rope_cols=2 * h,
-        stats=stats, stats_ld=stats_ld, stats_mask_col=stats_mask_col)
+        stats=stats, stats_ld=stats_ld, stats_mask_col=stats_mask_col,
+        live_seqs=n_live, out_seq_map=out_map)
       check(lib.ddg_gemm(g, s))
+
+    def ln(xp, ids_arg, emb, w, shift, scale, stride, code, out):
+      if live is None:
+        check(lib.ddg_ln_modulate(xp, n, h, ids_arg, period, emb, w, shift, scale,
+                                  stride, rpm, code, out, s))
+      else:
+        check(lib.ddg_ln_modulate_live(xp, n, h, ids_arg, period, emb, w, shift, scale,
+                                       stride, rpm, code, out, n_live, L,
+                                       seq_map if ids_arg else 0, s))
 
     for i in range(nb):
       mb = modb + i * 6 * h * 2
-      check(lib.ddg_ln_modulate(
-        x, n, h, ids_p if i == 0 else 0, period, ptr(self.embedding),
-        ptr(self.ln1[i]), mb if ada else 0, mb + h * 2 if ada else 0,
-        mod_stride, rpm, bcode, a16, s))
+      ln(x, ids_p if i == 0 else 0, ptr(self.embedding), ptr(self.ln1[i]),
+         mb if ada else 0, mb + h * 2 if ada else 0, mod_stride, bcode, a16)
       qkv_i = qkv
       if saved is not None:   # block input (set by the gather above for i == 0); the rotated
         # QKV of this block is written straight into its own buffer (kept for the backward)
@@ -308,15 +326,18 @@ class DIT:
         qkv_i = ptr(keep)
       gemm(a16, h, ptr(self.w_qkv[i]), h, qkv_i, 3 * h, 3 * h, h,
            _lib.EPI_QKV_ROPE, bcode)
-      check(lib.ddg_attention(qkv_i, a16, n // L, L, self.n_heads, self.head_dim,
-                              1 if self.causal else 0, bcode, s))
+      if live is None:
+        check(lib.ddg_attention(qkv_i, a16, n // L, L, self.n_heads, self.head_dim,
+                                1 if self.causal else 0, bcode, s))
+      else:
+        check(lib.ddg_attention_live(qkv_i, a16, n // L, L, self.n_heads, self.head_dim,
+                                     1 if self.causal else 0, bcode, n_live, s))
       gemm(a16, h, ptr(self.w_out[i]), h, x, h, h, h, _lib.EPI_GATE_RESIDUAL,
            bcode, gate=mb + 2 * h * 2 if ada else 0, gate_stride=mod_stride)
       if saved is not None:
         saved[-1][1] = ws['x'][:n].clone()
-      check(lib.ddg_ln_modulate(
-        x, n, h, 0, period, 0, ptr(self.ln2[i]), mb + 3 * h * 2 if ada else 0,
-        mb + 4 * h * 2 if ada else 0, mod_stride, rpm, bcode, a16, s))
+      ln(x, 0, 0, ptr(self.ln2[i]), mb + 3 * h * 2 if ada else 0,
+         mb + 4 * h * 2 if ada else 0, mod_stride, bcode, a16)
       gemm(a16, h, ptr(self.w_fc1[i]), h, h4, 4 * h, 4 * h, h,
            _lib.EPI_BIAS_GELU, bcode, bias=ptr(self.b_fc1[i]))
       gemm(h4, 4 * h, ptr(self.w_fc2[i]), 4 * h, x, h, h, 4 * h,
@@ -326,15 +347,14 @@ class DIT:
       return
     fin = self.use_adaln and self.final_adaln
     mf = ptr(ws['mod_fin']) + mod0 * 2 * h * 2
-    check(lib.ddg_ln_modulate(
-      x, n, h, 0, period, 0, ptr(self.ln_f), mf if fin else 0,
-      mf + h * 2 if fin else 0, 2 * h, rpm, hcode, a16, s))
+    ln(x, 0, 0, ptr(self.ln_f), mf if fin else 0, mf + h * 2 if fin else 0, 2 * h,
+       hcode, a16)
     st, st_ld = 0, 0
     if stats_out is not None:    # (chunks, rows_total, 2): this segment starts at row r0
       st, st_ld = ptr(stats_out) + r0 * 8, stats_out.shape[1]
     gemm(a16, h, ptr(self.w_vocab), h, ptr(logits_out) + r0 * self.vocab_ld * 2,
          self.vocab_ld, self.vocab_size, h, _lib.EPI_STORE, hcode,
-         bias=ptr(self.b_vocab), stats=st, stats_ld=st_ld)
+         bias=ptr(self.b_vocab), stats=st, stats_ld=st_ld, out_map=seq_map)
 
   # ------------------------------------------------------------------ AR decode
   def alloc_kv_cache(self, n_seqs: int, L: int):

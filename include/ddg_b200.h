@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DDG_ABI_VERSION 3
+#define DDG_ABI_VERSION 4
 #define DDG_API __attribute__((visibility("default")))
 
 typedef void* ddg_stream_t; /* cudaStream_t */
@@ -147,6 +147,12 @@ typedef struct ddg_sample_step_args {
    * first-order term (fp32 in the reference, :1540-1547) or fp32 parity runs.  */
   int32_t clf_round_bf16;
   int32_t reserved0;
+  /* ABI v4.  Optional (n_seqs,) flags: set to 1 for the sequence of every row whose
+   * token changes in this step (xs != xt).  The MDLM loop (time_conditioning =
+   * false) recomputes the denoiser only for the flagged sequences: an unchanged
+   * sequence has unchanged logits -- the per-sequence form of the reference's
+   * `sampling.use_cache` (diffusion.py:1371-1374), result-identical.           */
+  int32_t* seq_changed;
 } ddg_sample_step_args;
 
 DDG_API int ddg_sample_step(const ddg_sample_step_args* args, ddg_stream_t stream);
@@ -230,6 +236,23 @@ DDG_API int ddg_ln_modulate(float* x, int64_t rows, int32_t hidden,
                     int64_t mod_stride, int64_t rows_per_mod,
                     int32_t dtype, void* out, ddg_stream_t stream);
 
+/* The same over a dynamic batch: only the first *live_seqs sequences of
+ * `seq_len` rows exist (`rows` is the upper bound); with the id gather,
+ * seq_map[s] is the sequence of the id buffer that compact sequence s holds.  */
+DDG_API int ddg_ln_modulate_live(float* x, int64_t rows, int32_t hidden,
+                         const int64_t* ids, int64_t ids_period,
+                         const float* embedding, const float* ln_weight,
+                         const void* shift, const void* one_plus_scale,
+                         int64_t mod_stride, int64_t rows_per_mod,
+                         int32_t dtype, void* out, const int32_t* live_seqs,
+                         int32_t seq_len, const int32_t* seq_map, ddg_stream_t stream);
+
+/* seq_map[0..*count) = the indices s with flags[s] != 0, ascending; the flags are
+ * cleared.  Builds the dynamic batch of the MDLM loop from the `seq_changed` flags
+ * of ddg_sample_step (no host round trip: graph-capturable).                   */
+DDG_API int ddg_seq_compact(int32_t* flags, int32_t n_seqs, int32_t* seq_map, int32_t* count,
+                    ddg_stream_t stream);
+
 /* GEMM epilogues (models/dit.py:284-293, 312-316, 242-245/324-325, 359-366) */
 enum ddg_epilogue {
   DDG_EPI_STORE = 0,        /* out = round(acc [+ bias])            16-bit   */
@@ -269,6 +292,14 @@ typedef struct ddg_gemm_args {
   int32_t rope_pos0;    /* QKV_ROPE: position = rope_pos0 + m % seq_len (the
                            incremental AR decode passes the current position) */
   int32_t reserved;
+  /* ABI v4, dynamic batch (both optional, need seq_len > 0 dividing M):
+   * live_seqs  device scalar: only the first *live_seqs sequences (seq_len rows
+   *            each) of `a` exist in this launch; M stays the upper bound the
+   *            buffers and the grid are sized for (graph-capturable).
+   * out_seq_map (STORE, seq_len % 32 == 0): rows of compact sequence s (and
+   *            their `stats`) are written at output sequence out_seq_map[s].  */
+  const int32_t* live_seqs;
+  const int32_t* out_seq_map;
 } ddg_gemm_args;
 
 /* tcgen05 / TMEM / TMA GEMM: out = epilogue(a @ w^T). */
@@ -281,6 +312,12 @@ DDG_API int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream);
 DDG_API int ddg_attention(const void* qkv, void* out, int32_t batch, int32_t seq_len,
                   int32_t n_heads, int32_t head_dim, int32_t causal,
                   int32_t dtype, ddg_stream_t stream);
+
+/* ddg_attention over a dynamic batch: only the first *live_seqs sequences exist
+ * (`batch` is the upper bound).                                                */
+DDG_API int ddg_attention_live(const void* qkv, void* out, int32_t batch, int32_t seq_len,
+                       int32_t n_heads, int32_t head_dim, int32_t causal,
+                       int32_t dtype, const int32_t* live_seqs, ddg_stream_t stream);
 
 /* One decode step of causal attention with a KV cache (AR sampler,
  * diffusion.py:1085-1186: the reference re-encodes the whole prefix for the DiT

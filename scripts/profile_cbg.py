@@ -1,38 +1,38 @@
-"""Kernel-time breakdown of one QM9-shaped D-CBG step (torch profiler / CUPTI).
-`python scripts/profile_cbg.py [B] [exact]`  (default: first-order, B = 4096)"""
+"""Kernel-time breakdown of one D-CBG step (torch profiler / CUPTI) of a bench workload.
+`python scripts/profile_cbg.py [c4|c4_exact|c5_cbg] [B]`  (default: c4 = QM9-shaped
+first-order D-CBG at B = 4096; c5_cbg = Amazon-shaped: DiT-small denoiser + classifier,
+L = 128, V = 30522)"""
 import os
 import sys
+import time
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-import config_sweep
-import ddg_b200
+import bench
 
 
 def main():
-  B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+  key = sys.argv[1] if len(sys.argv) > 1 else 'c4'
+  wl = bench.WORKLOADS[key]
+  B = int(sys.argv[2]) if len(sys.argv) > 2 else wl.batch
+  steps = 4
   dev = torch.device('cuda', 0)
-  exact = len(sys.argv) > 2 and sys.argv[2] == 'exact'
-  over, _, steps = config_sweep.CBG_CONFIGS[
-    'C4 QM9 cbg exact B=64' if exact else 'C4 QM9 cbg first-order B=4096']
-  cfg = ddg_b200.compose(list(over) + [f'sampling.batch_size={B}', f'sampling.steps={steps}'])
-  tok = config_sweep.Qm9Tok()
-  model = ddg_b200.Diffusion(cfg, tok, device=dev).load_state_dict(
-    ddg_b200.weights.random_state_dict(cfg, tok.vocab_size, seed=1))
-  model.set_classifier(ddg_b200.Classifier(cfg, tok, device=dev).load_state_dict(
-    ddg_b200.weights.random_state_dict(cfg, tok.vocab_size, seed=2, classifier=True)))
+  model, cfg = bench.build_model(wl, B, dev, 1, steps=steps)
   model.sample()
   torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  model.sample()
+  torch.cuda.synchronize()
+  print(f'{key} B={B}: {(time.perf_counter() - t0) / steps * 1e3:.2f} ms/step wall')
   with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
     model.sample()
     torch.cuda.synchronize()
   rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
   tot = sum(e.device_time_total for e in rows)
   print(f'total device time {tot / 1e3 / steps:.2f} ms/step over {steps} steps')
-  for e in rows[:25]:
-    print(f'{e.device_time_total / 1e3 / steps:9.3f} ms/step  {e.count / steps:6.1f} launches/step  {e.key[:110]}')
+  for e in rows[:26]:
+    print(f'{e.device_time_total / 1e3 / steps:9.3f} ms/step  {e.count / steps:6.1f} launches/step  {e.key[:120]}')
 
 
 if __name__ == '__main__':
