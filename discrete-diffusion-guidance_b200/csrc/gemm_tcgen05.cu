@@ -405,20 +405,24 @@ __device__ __forceinline__ float gelu_tanh(float v) {
 
 // Tile order.  Default: N inner (consecutive tiles = the N-blocks of one M-block, so the
 // clusters running at the same time share one A block and W -- a few MB -- stays in L2).
-// `group_m` > 1 (the vocab head: 120 N-blocks, W = 47 MB, 8 GB of output streaming through
-// L2): M-blocks are taken `group_m` at a time and walked M-inner inside the group, so a W
-// tile is reused by `group_m` tiles in flight at once instead of once per 120-tile sweep.
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& mb, int& nb) {
-  if (group_m <= 1) {
+// The vocab head (120 N-blocks, W = 47 MB, 8 GB of output streaming through L2) does not
+// keep W resident that way: ncu showed 3-4.4 GB of DRAM reads per launch against 0.25 GB
+// algorithmic.  `n_panel` > 0 splits N into panels of `n_panel` blocks and finishes all
+// M-blocks of one panel before the next: the W panel (24 MB for two panels) is what has to
+// stay in L2, at the price of reading A (0.2 GB) once per panel.
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int n_panel, int& mb, int& nb) {
+  if (n_panel <= 0 || n_panel >= num_n) {
     mb = tile / num_n;
     nb = tile % num_n;
     return;
   }
-  const int per_group = group_m * num_n;
-  const int g = tile / per_group, r = tile - g * per_group;
-  const int cnt = min(group_m, num_m - g * group_m);
-  nb = r / cnt;
-  mb = g * group_m + (r - nb * cnt);
+  const int per_panel = num_m * n_panel;           // tiles of a full panel
+  const int pnl = tile / per_panel;
+  const int n_first = pnl * n_panel;
+  const int width = min(n_panel, num_n - n_first); // the last panel may be narrower
+  const int r = tile - pnl * per_panel;            // per_panel is exact for every earlier panel
+  mb = r / width;
+  nb = n_first + (r - mb * width);
 }
 
 // ------------------------------------------------------------------ kernel
@@ -452,7 +456,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + BK - 1) / BK;
-  const int group_m = p.stream_out ? 8 : 1;
+  const int n_panel = p.stream_out ? (num_n + 1) / 2 : 0;   // two N panels for the vocab head
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -480,7 +484,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const uint64_t keep = policy_evict_last();
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         int mb, nb;
-        tile_coords(tile, num_m, num_n, group_m, mb, nb);
+        tile_coords(tile, num_m, num_n, n_panel, mb, nb);
         const int m0 = mb * (2 * BM) + (int)cta_rank * BM;     // this CTA's A rows
         const int nb0 = nb * BN + (int)cta_rank * BNH;         // this CTA's half of W
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -557,7 +561,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const uint32_t tmem_empty_leader0 = map_to_cta(smem_u32(&tmem_empty[0]), 0);
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int mb, nb;
-      tile_coords(tile, num_m, num_n, group_m, mb, nb);
+      tile_coords(tile, num_m, num_n, n_panel, mb, nb);
       const int m0 = mb * (2 * BM) + (int)cta_rank * BM;
       const int n0 = nb * BN + chalf * (BN / 2);
       const int m = m0 + row_in_tile;

@@ -418,12 +418,14 @@ class Diffusion:
       'log_x_theta_uncond': lu, 'log_x_theta_cond': lc}
 
   def _classifier_term(self, classifier_model, xt, time_conditioning,
-                       conditioning_class, use_approx):
-    """(B, L, V) fp32 classifier log-prob term of D-CBG."""
+                       conditioning_class, use_approx, raw_ok=False):
+    """(B, L, V) fp32 classifier log-prob term of D-CBG.  `raw_ok`: the caller only
+    samples from it (the term is not handed back), so the row-constant part of the
+    first-order term, which cancels in the guided softmax, may be left out."""
     if use_approx:
       # first order (diffusion.py:1532-1548): one classifier forward + backward
       term, _ = classifier_model.first_order_term(xt, time_conditioning,
-                                                  conditioning_class)
+                                                  conditioning_class, finalize=not raw_ok)
       return term
     # exact: every single-token edit of xt (diffusion.py:1549-1585), generated
     # chunk by chunk on the device and never materialised as a whole.
@@ -447,8 +449,10 @@ class Diffusion:
 
   def _cbg_denoise(self, conditioning_class, gamma, classifier_model, xt,
                    time_conditioning, move_chance_t, move_chance_s,
-                   use_approx=False, cache=None):
-    """diffusion.py:1511-1624 -> (xs, guided_probs | None, cache)."""
+                   use_approx=False, cache=None, _sampling_only=False):
+    """diffusion.py:1511-1624 -> (xs, guided_probs | None, cache).
+    `_sampling_only` (the `sample()` loop, which drops the cache): see
+    `_classifier_term(raw_ok=...)`; the returned cache then holds no classifier term."""
     B, L = xt.shape
     xt = xt.to(self.device, torch.int64).contiguous()
     if cache is not None:
@@ -456,7 +460,8 @@ class Diffusion:
     else:
       logits = self._logits(xt, time_conditioning, None)
       term = self._classifier_term(classifier_model, xt, time_conditioning,
-                                   conditioning_class, use_approx)
+                                   conditioning_class, use_approx,
+                                   raw_ok=_sampling_only and self.noise_fn is None)
     xs = torch.empty_like(xt)
     q = self._q_buffer(B, L)
     mct, mcs = self._mc(move_chance_t), self._mc(move_chance_s)
@@ -477,7 +482,8 @@ class Diffusion:
                                 carry=self.diffusion == 'absorbing_state')
     self._step_index += 1
     return xs, q if self.return_q_xs else None, {
-      'log_x_theta': logits, 'classifier_log_prob': term}
+      'log_x_theta': logits,
+      'classifier_log_prob': None if (_sampling_only and self.noise_fn is None) else term}
 
   # ---------------------------------------------------------------- loops
   @torch.no_grad()
@@ -528,7 +534,7 @@ class Diffusion:
       else:
         xt, _, _ = self._cbg_denoise(
           guidance.condition, guidance.gamma, classifier_model, xt, sig, mct,
-          mcs, use_approx=guidance.get('use_approx', False))
+          mcs, use_approx=guidance.get('use_approx', False), _sampling_only=True)
     self._step_index = 0
     return xt
 

@@ -491,13 +491,19 @@ class DIT:
                                   stream_ptr()))
     return out
 
-  def first_order_term(self, indices, sigma, target, round_bf16=True):
+  def first_order_term(self, indices, sigma, target, round_bf16=True, finalize=True):
     """First-order D-CBG classifier term (diffusion.py:1532-1548): one forward
     and the backward of log p(target | x) w.r.t. the one-hot input, then
     `grad - grad[xt] + log p(target | xt)` -> (n, L, V) fp32.  The forward is
     the one of `classify` (a one-hot input times the embedding matrix is the
     embedding gather, models/dit.py:518-522) with each block's residual-stream
-    inputs and rotated QKV kept for the backward."""
+    inputs and rotated QKV kept for the backward.
+
+    `finalize=False` returns the raw gradient `grad` instead: the other two terms
+    are the same for every vocabulary entry of a row, and a row-constant shift of
+    the classifier term cancels in the softmax of `log q + gamma * term`
+    (diffusion.py:1612-1617), i.e. it changes neither q_xs nor the ids -- the
+    sampling loop skips that extra pass over (n, L, V)."""
     assert self.classifier
     n, L = indices.shape
     h, nb, V, M = self.hidden, self.n_blocks, self.vocab_size, n * L
@@ -570,7 +576,8 @@ class DIT:
     term = torch.empty(M, ldv, dtype=torch.float32, device=dev)
     gemm(ptr(g_cat), 3 * h, ptr(self.emb_cat), 3 * h, ptr(term), ldv, V, 3 * h,
          epi=_lib.EPI_ACCUM_F32)
-    check(lib.ddg_cbg_first_order(
-      ptr(term), ldv, ptr(ids), ptr(lp), self.num_classes, int(target), L, V, M,
-      ptr(term), ldv, s))
+    if finalize:
+      check(lib.ddg_cbg_first_order(
+        ptr(term), ldv, ptr(ids), ptr(lp), self.num_classes, int(target), L, V, M,
+        ptr(term), ldv, s))
     return term.view(n, L, ldv)[:, :, :V], lp
