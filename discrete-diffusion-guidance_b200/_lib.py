@@ -99,7 +99,7 @@ def _load():
                                   i64, i32, vp, vp]
   lib.ddg_ln_modulate_live.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, vp, i64,
                                        i64, i32, vp, vp, i32, vp, vp]
-  lib.ddg_seq_compact.argtypes = [vp, i32, vp, vp, vp]
+  lib.ddg_seq_compact.argtypes = [vp, i32, vp, vp, i32, vp]
   lib.ddg_gemm.argtypes = [C.POINTER(GemmArgs), vp]
   lib.ddg_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
   lib.ddg_attention_live.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]

@@ -475,10 +475,22 @@ int ln_modulate_impl(float* x, int64_t rows, int32_t hidden, const int64_t* ids,
 // flags[s] != 0 in increasing order; flags are cleared for the next step.  One CTA.
 __global__ void __launch_bounds__(1024)
 seq_compact_kernel(int32_t* __restrict__ flags, int n_seqs, int32_t* __restrict__ seq_map,
-                   int32_t* __restrict__ count) {
+                   int32_t* __restrict__ count, int all_total) {
   __shared__ int warp_tot[32];
   __shared__ int base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (all_total > 0) {
+    // whole-batch form (the reference's sampling.use_cache, diffusion.py:1371-1374): every
+    // sequence is recomputed if ANY token of the batch changed, none otherwise
+    int any = 0;
+    for (int s = tid; s < n_seqs; s += 1024) {
+      any |= flags[s];
+      flags[s] = 0;
+    }
+    any = __syncthreads_or(any);
+    if (tid == 0) *count = any ? all_total : 0;
+    return;
+  }
   if (tid == 0) base = 0;
   __syncthreads();
   for (int s0 = 0; s0 < n_seqs; s0 += 1024) {
@@ -526,11 +538,13 @@ extern "C" int ddg_ln_modulate_live(float* x, int64_t rows, int32_t hidden, cons
 }
 
 extern "C" int ddg_seq_compact(int32_t* flags, int32_t n_seqs, int32_t* seq_map, int32_t* count,
-                               ddg_stream_t stream) {
+                               int32_t all_total, ddg_stream_t stream) {
   int rc = ddg_device_check();
   if (rc) return rc;
-  DDG_REQUIRE(flags && seq_map && count && n_seqs >= 0, DDG_ERR_INVALID, "seq_compact: bad args");
-  ddg::seq_compact_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(flags, n_seqs, seq_map, count);
+  DDG_REQUIRE(flags && count && n_seqs >= 0 && (seq_map || all_total > 0), DDG_ERR_INVALID,
+              "seq_compact: bad args");
+  ddg::seq_compact_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(flags, n_seqs, seq_map, count,
+                                                                                 all_total);
   return ddg::check_cuda(cudaGetLastError(), "seq_compact launch");
 }
 

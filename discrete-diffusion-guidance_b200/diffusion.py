@@ -15,8 +15,8 @@ device tables.
 from __future__ import annotations
 
 import collections
+import gc
 import typing
-import warnings
 
 import torch
 
@@ -26,6 +26,25 @@ from .dit import DIT, ModSpec
 
 
 _MAX_STEP_GRAPHS = 2
+
+
+def _capture(body):
+  """Captures `body()` into a new CUDA graph.  Dead Python cycles that hold an older
+  `torch.cuda.CUDAGraph` (a discarded model and its step graphs) must not be collected
+  WHILE the stream is capturing -- destroying a graph is not a capturable operation and
+  invalidates the capture -- so they are collected first and the cyclic collector stays
+  off until the capture ends (torch.cuda.graph no longer collects on entry)."""
+  gc.collect()
+  was_enabled = gc.isenabled()
+  gc.disable()
+  try:
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, capture_error_mode='thread_local'):
+      body()
+  finally:
+    if was_enabled:
+      gc.enable()
+  return g
 
 
 def _attach_stats(logits, stats, row_offset):
@@ -100,7 +119,6 @@ class Diffusion:
     self._loop = None
     self._step_index = 0        # Philox counter word of the next eager sampler launch
     self._step_graphs = collections.OrderedDict()   # LRU, at most _MAX_STEP_GRAPHS
-    self._warned_use_cache = False
 
   # ---------------------------------------------------------------- weights
   def load_state_dict(self, state_dict, strict=True):
@@ -499,16 +517,6 @@ class Diffusion:
       raise NotImplementedError(f'Guidance method {method} not implemented.')
     xt = self._sample_prior(B, L)
     sigma_t, mc_t, mc_s = self._step_scalars(steps, eps)
-    if (self.config.sampling.get('use_cache', False) and self.time_conditioning
-        and not self._warned_use_cache):
-      # reference diffusion.py:1371-1374 keeps the cached log-probs (computed at an OLDER
-      # sigma) while NO token of the batch changes; here every step recomputes them at the
-      # current sigma (documented deviation, only reachable when a
-      # whole batch stays unchanged for a step)
-      warnings.warn('sampling.use_cache with time_conditioning=True: log-probs are '
-                    'recomputed at every step instead of being reused across unchanged '
-                    'steps (see DESIGN.md)', stacklevel=2)
-      self._warned_use_cache = True
     mixed_cond = cond is not None and not bool((cond == cond.reshape(-1)[0]).all())
     if self.noise_fn is not None or self.return_q_xs or method == 'cbg' \
         or not self.use_cuda_graph or self._low_confidence or mixed_cond \
@@ -706,10 +714,7 @@ class _StepGraph:
       self._body()              # eager (also warms lazy attributes), then capture
       torch.cuda.current_stream().synchronize()
       out = self.xs.clone()
-      g = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(g):
-        self._body()
-      self.graph = g
+      self.graph = _capture(self._body)
       self.ws_generation = m.backbone.ws_generation
       return out
     self.graph.replay()
@@ -741,20 +746,31 @@ class _GraphLoop:
     self.graph = None
     self.ws_generation = -1
     self.steps = 0
-    # Per-sequence logits cache.  Without time conditioning the logits of a sequence are a
-    # function of its tokens alone, and absorbing diffusion changes L / steps tokens per
-    # sequence per step on average (0.128 at L = 128, 1000 steps): most sequences are
-    # untouched by a step.  The sampler flags the sequences it changes, `ddg_seq_compact`
-    # turns the flags into the next step's dynamic batch, and the forward runs on those
-    # sequences only, writing their rows of the persistent logits buffer.  The reference
-    # does this for the whole batch at once (sampling.use_cache: reuse when NO token
-    # changed, diffusion.py:1371-1374); same results, the forward being deterministic per
-    # sequence.
-    self.cached = bool(model.logits_cache and method is None and not model.time_conditioning
-                       and model.diffusion == 'absorbing_state' and L % 32 == 0)
+    # Logits caches (both result-identical to what the reference computes):
+    # 'seq'   Without time conditioning the logits of a sequence are a function of its tokens
+    #         alone, and absorbing diffusion changes L / steps tokens per sequence per step on
+    #         average (0.128 at L = 128, 1000 steps): most sequences are untouched by a step.
+    #         The sampler flags the sequences it changes, `ddg_seq_compact` turns the flags
+    #         into the next step's dynamic batch, and the forward runs on those sequences
+    #         only, writing their rows of the persistent logits buffer.  The reference does
+    #         this for the whole batch at once (sampling.use_cache: reuse when NO token
+    #         changed, diffusion.py:1371-1374); same results, the forward being deterministic
+    #         per sequence.
+    # 'batch' With time conditioning the reference's `sampling.use_cache` is NOT a no-op: while
+    #         no token of the batch changes it keeps the log-probs computed at an OLDER sigma
+    #         (diffusion.py:1371-1374 with :1386-1390, 1448-1470).  Reproduced exactly: the
+    #         forward of a step runs on all sequences if any token changed in the previous
+    #         step and on none otherwise (device-side count, no host sync).
+    self.cached = None
+    if (model.logits_cache and method is None and not model.time_conditioning
+        and model.diffusion == 'absorbing_state' and L % 32 == 0):
+      self.cached = 'seq'
+    elif model.config.sampling.get('use_cache', False) and model.time_conditioning:
+      self.cached = 'batch'
     if self.cached:
       self.changed = torch.ones(B, dtype=torch.int32, device=dev)
-      self.seq_map = torch.zeros(B, dtype=torch.int32, device=dev)
+      self.seq_map = (torch.zeros(B, dtype=torch.int32, device=dev)
+                      if self.cached == 'seq' else None)
       self.n_live = torch.zeros(1, dtype=torch.int32, device=dev)
 
   def _body(self):
@@ -766,7 +782,7 @@ class _GraphLoop:
     live = None
     if self.cached:    # flags of the previous step (all set at step 0) -> this step's batch
       check(lib.ddg_seq_compact(ptr(self.changed), B, ptr(self.seq_map), ptr(self.n_live),
-                                stream_ptr()))
+                                self.n_fwd * B if self.cached == 'batch' else 0, stream_ptr()))
       live = (self.seq_map, self.n_live)
     m.backbone.run(self.xt, self.n_fwd * B, L, mod, self.logits,
                    ids_period=B * L, stats_out=self.stats,
@@ -816,10 +832,7 @@ class _GraphLoop:
       self._body()
       torch.cuda.synchronize()
       self.reset(xt)
-      g = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(g):
-        self._body()
-      self.graph = g
+      self.graph = _capture(self._body)
       self.ws_generation = m.backbone.ws_generation
       self.reset(xt)
 

@@ -228,7 +228,9 @@ class DIT:
     DYNAMIC batch: only the sequences `seq_map[0..n_live)` of `ids` go through the
     network (compact activations), and their logits / partials are written back at
     their own rows of `logits_out` / `stats_out`; every launch is sized for
-    `n_seqs` and reads the live count on the device (graph-capturable)."""
+    `n_seqs` and reads the live count on the device (graph-capturable).
+    `seq_map = None`: the live sequences are the first `n_live` ones in place (the
+    whole-batch cache: n_live is n_seqs or 0)."""
     assert self._loaded, 'load_state_dict first'
     M = n_seqs * L
     h, nb = self.hidden, self.n_blocks
@@ -262,8 +264,9 @@ class DIT:
       raise ValueError('Conditioning variable provided, but Model was not '
                        'initialized with condition embedding layer.')
     cos, sin = self._rope_tables(L)
-    if live is not None and (self.classifier or save_for_backward is not None or L % 32):
-      raise ValueError('dynamic batch: denoiser forward only, seq_len % 32 == 0')
+    if live is not None and (self.classifier or save_for_backward is not None
+                             or (live[0] is not None and L % 32)):
+      raise ValueError('dynamic batch: denoiser forward only; with a sequence map seq_len % 32 == 0')
     seg_rows = M if (self.seg_seqs is None or save_for_backward is not None or live is not None) \
         else max(1, self.seg_seqs) * L
     for r0 in range(0, M, seg_rows):

@@ -249,9 +249,11 @@ DDG_API int ddg_ln_modulate_live(float* x, int64_t rows, int32_t hidden,
 
 /* seq_map[0..*count) = the indices s with flags[s] != 0, ascending; the flags are
  * cleared.  Builds the dynamic batch of the MDLM loop from the `seq_changed` flags
- * of ddg_sample_step (no host round trip: graph-capturable).                   */
+ * of ddg_sample_step (no host round trip: graph-capturable).  all_total > 0: the
+ * whole-batch form of `sampling.use_cache` (diffusion.py:1371-1374) instead --
+ * *count = all_total if any flag is set, else 0; seq_map is not written.       */
 DDG_API int ddg_seq_compact(int32_t* flags, int32_t n_seqs, int32_t* seq_map, int32_t* count,
-                    ddg_stream_t stream);
+                    int32_t all_total, ddg_stream_t stream);
 
 /* GEMM epilogues (models/dit.py:284-293, 312-316, 242-245/324-325, 359-366) */
 enum ddg_epilogue {

@@ -23,7 +23,7 @@ def test_seq_compact_orders_and_clears_flags():
     seq_map = torch.full((n,), -1, dtype=torch.int32, device=DEV)
     count = torch.zeros(1, dtype=torch.int32, device=DEV)
     _lib.check(_lib.lib.ddg_seq_compact(flags.data_ptr(), n, seq_map.data_ptr(), count.data_ptr(),
-                                        _lib.stream_ptr()))
+                                        0, _lib.stream_ptr()))
     torch.cuda.synchronize()
     assert int(count) == want.numel()
     assert torch.equal(seq_map[:want.numel()], want)
