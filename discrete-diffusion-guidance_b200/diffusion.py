@@ -470,7 +470,8 @@ class Diffusion:
                    use_approx=False, cache=None, _sampling_only=False):
     """diffusion.py:1511-1624 -> (xs, guided_probs | None, cache).
     `_sampling_only` (the `sample()` loop, which drops the cache): see
-    `_classifier_term(raw_ok=...)`; the returned cache then holds no classifier term."""
+    `_classifier_term(raw_ok=...)`; the classifier term in the returned cache then
+    lacks its row-constant part (good for re-use by this loop only)."""
     B, L = xt.shape
     xt = xt.to(self.device, torch.int64).contiguous()
     if cache is not None:
@@ -501,7 +502,7 @@ class Diffusion:
     self._step_index += 1
     return xs, q if self.return_q_xs else None, {
       'log_x_theta': logits,
-      'classifier_log_prob': None if (_sampling_only and self.noise_fn is None) else term}
+      'classifier_log_prob': term}
 
   # ---------------------------------------------------------------- loops
   @torch.no_grad()
@@ -528,21 +529,30 @@ class Diffusion:
 
   def _eager_loop(self, xt, sigma_t, mc_t, mc_s, method, guidance,
                   classifier_model, cond):
+    """Step loop of `_diffusion_sample` through the per-step API, with the reference's
+    cache rule (diffusion.py:1371-1374): with `sampling.use_cache` the (logits,
+    classifier term) of a step are reused by the next one while NO token changed."""
     B = xt.shape[0]
     dev = self.device
+    use_cache = bool(self.config.sampling.get('use_cache', False))
+    cache = None
     for i in range(sigma_t.numel()):
       self._step_index = i
       sig = sigma_t[i].to(dev).expand(B)
       mct = mc_t[i].to(dev).expand(B)[:, None, None]
       mcs = mc_s[i].to(dev).expand(B)[:, None, None]
       if method is None:
-        xt, _, _ = self._ddpm_denoise(xt, sig, mct, mcs)
+        xs, _, new_cache = self._ddpm_denoise(xt, sig, mct, mcs, cache=cache)
       elif method == 'cfg':
-        xt, _, _ = self._cfg_denoise(cond, guidance.gamma, xt, sig, mct, mcs)
+        xs, _, new_cache = self._cfg_denoise(cond, guidance.gamma, xt, sig, mct, mcs,
+                                             cache=cache)
       else:
-        xt, _, _ = self._cbg_denoise(
+        xs, _, new_cache = self._cbg_denoise(
           guidance.condition, guidance.gamma, classifier_model, xt, sig, mct,
-          mcs, use_approx=guidance.get('use_approx', False), _sampling_only=True)
+          mcs, use_approx=guidance.get('use_approx', False), cache=cache,
+          _sampling_only=True)
+      cache = new_cache if (use_cache and torch.equal(xs, xt)) else None
+      xt = xs
     self._step_index = 0
     return xt
 

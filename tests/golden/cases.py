@@ -32,6 +32,7 @@ class Case:
   use_float64: bool = False
   low_confidence: bool = False          # eval.low_confidence_sampling
   low_confidence_threshold: float = 0.3
+  use_cache: bool = False               # sampling.use_cache (diffusion.py:1371-1374)
   batch: int = 2
   length: int = 32
   steps: int = 4
@@ -79,6 +80,9 @@ CASES = [
        low_confidence_threshold=0.5, steps=2),
   Case('bert_udlm_lowconf', vocab='bert', low_confidence=True, length=16,
        steps=2),
+  Case('udlm_use_cache', use_cache=True, batch=1, length=16, steps=24),
+  Case('udlm_cfg_use_cache', use_cache=True, guidance='cfg', gamma=2.0, batch=1,
+       length=16, steps=24),
   Case('ar_null', parameterization='ar', diffusion='absorbing_state',
        time_conditioning=False, length=16, steps=0),
   Case('ar_cfg_g2', parameterization='ar', diffusion='absorbing_state',
@@ -136,7 +140,7 @@ def config_dict(case: Case) -> dict:
     noise=dict(type='loglinear', sigma_min=1e-4, sigma_max=20),
     data=dict(train='synthetic', valid='synthetic',
               num_classes=case.num_classes),
-    sampling=dict(use_cache=False, steps=max(case.steps, 1),
+    sampling=dict(use_cache=case.use_cache, steps=max(case.steps, 1),
                   batch_size=case.batch, num_sample_batches=1,
                   use_float64=case.use_float64),
     training=dict(guidance=(dict(cond_dropout=0.1)

@@ -120,6 +120,7 @@ def run_case(ref, case, device='cpu'):
       xt = k['xt']
       xs, q, cache = orig(*a, **k)
       rec = {'xt': xt.clone(), 'xs': xs.clone(), 'q_xs': q.clone(),
+             'cached': k.get('cache') is not None,
              'dtypes': {'q_xs': str(q.dtype), **{
                ck: str(cv.dtype) for ck, cv in cache.items() if cv is not None}},
              'mc_t': k['move_chance_t'].reshape(-1)[0].clone(),
@@ -147,6 +148,8 @@ def run_case(ref, case, device='cpu'):
   for i, rec in enumerate(trace):
     out[f's{i}_xt'] = rec['xt'].cpu().numpy().astype(np.int32)
     out[f's{i}_xs'] = rec['xs'].cpu().numpy().astype(np.int32)
+    if case.use_cache:   # 1 = the reference re-used the cached log-probs in this step
+      out[f's{i}_cached'] = np.array(int(rec['cached']), dtype=np.int32)
     out[f's{i}_scalars'] = np.array(
       [rec['sigma_t'].item(), rec['mc_t'].item(), rec['mc_s'].item()],
       dtype=np.float32)

@@ -90,7 +90,7 @@ def test_cached_loop_ids_equal_full_recompute(name, L, steps):
     b = model.sample()             # second call: graph replay with a fresh prior
     torch.cuda.synchronize()
     outs[cache] = (a.cpu(), b.cpu())
-    assert model._loop.cached == cache
+    assert model._loop.cached == ('seq' if cache else None)
     assert int((a == tok.mask_token_id).sum()) == 0    # MDLM ends fully unmasked (eps = 1e-5)
   assert torch.equal(outs[True][0], outs[False][0])
   assert torch.equal(outs[True][1], outs[False][1])
@@ -108,7 +108,7 @@ def test_cache_counts_live_sequences():
   xt = model._sample_prior(B, L)
   sig, mct, mcs = model._step_scalars(400, 1e-5)
   loop = model._get_loop(B, L, None, None)
-  assert loop.cached
+  assert loop.cached == 'seq'
   loop.prepare(xt, sig, mct, mcs, None)
   lives, prev = [], loop.xt.clone()
   for i in range(400):
@@ -125,9 +125,42 @@ def test_cache_counts_live_sequences():
   assert int((loop.xt == tok.mask_token_id).sum()) == 0
 
 
-def test_time_conditioned_and_guided_loops_do_not_cache():
+def test_time_conditioned_and_guided_loops_do_not_cache_per_sequence():
   for name in ('udlm_null', 'mdlm_cfg_g2', 'd3pm_abs_submask'):
     case = cases.CASE_BY_NAME[name]
     model, tok = _model(case)
     model.sample()
-    assert model._loop is None or not model._loop.cached, name
+    assert model._loop is None or model._loop.cached is None, name
+
+
+@pytest.mark.parametrize('name', ['udlm_use_cache', 'udlm_cfg_use_cache'])
+def test_use_cache_with_time_conditioning_matches_reference_rule(name):
+  """`sampling.use_cache` + time conditioning: the reference keeps the
+  log-probs of the previous step -- computed at an OLDER sigma -- while no token of the
+  batch changes (diffusion.py:1371-1374; rule pinned to the reference's own trace in
+  tests/test_oracle_pins.py).  The captured loop does it on the device (the forward of a
+  step runs on all sequences if the previous step changed a token, on none otherwise);
+  the eager loop does it on the host like the reference.  Same Philox key -> the two
+  must agree bit for bit, both must skip forwards, and switching the cache off must
+  change the result (the stale-sigma log-probs matter)."""
+  case = cases.CASE_BY_NAME[name]
+  outs, n_fwd = {}, {}
+  for mode in ('graph', 'eager', 'nocache'):
+    model, tok = _model(case)
+    model.config.sampling.steps = 200          # small moves per step: many unchanged steps
+    model.config.sampling.use_cache = mode != 'nocache'
+    model.use_cuda_graph = mode != 'eager'
+    calls = {'n': 0}
+    orig = model.backbone.run
+
+    def counted(*a, _orig=orig, **k):
+      calls['n'] += 1
+      return _orig(*a, **k)
+    model.backbone.run = counted
+    outs[mode] = model.sample().cpu()
+    n_fwd[mode] = calls['n']
+    if mode == 'graph':
+      assert model._loop.cached == 'batch'
+  assert torch.equal(outs['graph'], outs['eager'])
+  assert n_fwd['eager'] < 0.8 * 200, n_fwd          # the host rule skipped forwards
+  assert not torch.equal(outs['graph'], outs['nocache'])

@@ -29,7 +29,7 @@ def _diffusion(case, **over):
 
 
 @pytest.mark.parametrize('name', [c.name for c in cases.CASES
-                                  if c.parameterization != 'ar'])
+                                  if c.parameterization != 'ar' and not c.use_cache])
 def test_step_api_ids_follow_own_logits(name):
   """Per-step API with injected noise: the ids must be what the oracle's
   update (with the reference's GPU roundings) selects from the logits the

@@ -15,7 +15,7 @@ from oracle import ref_dit, ref_sampler
 
 pytestmark = pytest.mark.gpu
 
-DIFFUSION_CASES = [c.name for c in cases.CASES if c.parameterization != 'ar']
+DIFFUSION_CASES = [c.name for c in cases.CASES if c.parameterization != 'ar' and not c.use_cache]
 
 
 def _oracle_logits(case, oracle, xt, sigma_t, cond):

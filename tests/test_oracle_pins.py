@@ -9,7 +9,7 @@ import helpers
 from golden import cases
 from oracle import ref_dit, ref_sampler
 
-DIFFUSION_CASES = [c.name for c in cases.CASES if c.parameterization != 'ar']
+DIFFUSION_CASES = [c.name for c in cases.CASES if c.parameterization != 'ar' and not c.use_cache]
 
 
 @pytest.mark.parametrize('name', DIFFUSION_CASES)
@@ -224,3 +224,42 @@ def test_sampler_stage_rounding_is_exact_on_reference_log_probs(name, source):
                                         case.gamma, xt, mc_t, mc_s, U, **kw32)
       pos = g > 1e-12
       assert ((q32.float() - g).abs() / g.clamp_min(1e-30))[pos].max().item() > 1e-4
+
+
+@pytest.mark.parametrize('name', ['udlm_use_cache', 'udlm_cfg_use_cache'])
+def test_oracle_replays_reference_use_cache_rule(name):
+  """`sampling.use_cache` with time conditioning (diffusion.py:1371-1374): while no
+  token changes, the reference re-uses the log-probs computed at an OLDER sigma.
+  The traced `cached` flags, ids and posteriors of the reference must follow from:
+  keep the cache iff xs == xt."""
+  case = cases.CASE_BY_NAME[name]
+  gold = helpers.load_golden(name)
+  oracle = helpers.make_oracle(case)
+  tok = cases.Tok(case.vocab)
+  B = case.batch
+  sig, mct, mcs = ref_sampler.step_scalars(case.steps, 1e-5, case.T)
+  cond = torch.full((B,), case.condition, dtype=torch.long) if case.guidance == 'cfg' else None
+  kw = dict(diffusion=case.diffusion, mask_index=tok.mask_token_id)
+  xt = torch.from_numpy(gold['xt0']).long()
+  cache, n_cached = None, 0
+  for i in range(case.steps):
+    assert torch.equal(xt, torch.from_numpy(gold[f's{i}_xt']).long())
+    assert int(gold[f's{i}_cached']) == int(cache is not None), (name, i)
+    mc_t, mc_s = mct[i].expand(B)[:, None, None], mcs[i].expand(B)[:, None, None]
+    U = cases.step_noise(case, i)
+    if cache is None:
+      xs, q, lps = oracle.step(xt, sig[i].expand(B), mc_t, mc_s, U, guidance=case.guidance,
+                               cond=cond, gamma=case.gamma)
+    else:
+      n_cached += 1
+      lps = cache
+      if case.guidance == 'cfg':
+        xs, q = ref_sampler.cfg_update(lps['log_x_theta_cond'], lps['log_x_theta_uncond'],
+                                       case.gamma, xt, mc_t, mc_s, U, **kw)
+      else:
+        xs, q = ref_sampler.ddpm_update(lps['log_x_theta'], xt, mc_t, mc_s, U, **kw)
+    assert torch.equal(xs, torch.from_numpy(gold[f's{i}_xs']).long()), (name, i)
+    helpers.check_summary(f's{i}_q_xs', q, gold, False, 2e-4, 1e-6)
+    cache = lps if torch.equal(xs, xt) else None
+    xt = xs
+  assert n_cached >= 3
