@@ -463,12 +463,10 @@ def kernel_breakdown(model, cfg, loop):
   the launching stream -> per-kernel-family device time."""
   from ddg_b200 import _lib
   lib = _lib.lib
-  names = {'ddg_gemm': None, 'ddg_attention': 'attention', 'ddg_ln_modulate': 'ln_modulate',
+  names = {'ddg_gemm': None, 'ddg_attention': 'attention', 'ddg_attention_live': 'attention',
+           'ddg_ln_modulate': 'ln_modulate', 'ddg_ln_modulate_live': 'ln_modulate',
            'ddg_sample_step': 'sample_step', 'ddg_cond_embed': 'cond', 'ddg_adaln': 'cond',
-           'ddg_step_advance': 'cond'}
-  for extra in ('ddg_gemm_ln',):
-    if hasattr(lib, extra):
-      names[extra] = 'gemm_ln'
+           'ddg_step_advance': 'cond', 'ddg_seq_compact': 'cond'}
   records = []
   orig = {n: getattr(lib, n) for n in names}
   h = cfg.model.hidden_size

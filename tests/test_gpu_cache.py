@@ -144,11 +144,11 @@ def test_use_cache_with_time_conditioning_matches_reference_rule(name):
   must agree bit for bit, both must skip forwards, and switching the cache off must
   change the result (the stale-sigma log-probs matter)."""
   case = cases.CASE_BY_NAME[name]
+  steps = 200                                    # small moves per step: many unchanged steps
   outs, n_fwd = {}, {}
-  for mode in ('graph', 'eager', 'nocache'):
+  for mode in ('graph', 'eager'):
     model, tok = _model(case)
-    model.config.sampling.steps = 200          # small moves per step: many unchanged steps
-    model.config.sampling.use_cache = mode != 'nocache'
+    model.config.sampling.steps = steps
     model.use_cuda_graph = mode != 'eager'
     calls = {'n': 0}
     orig = model.backbone.run
@@ -156,11 +156,31 @@ def test_use_cache_with_time_conditioning_matches_reference_rule(name):
     def counted(*a, _orig=orig, **k):
       calls['n'] += 1
       return _orig(*a, **k)
-    model.backbone.run = counted
+    if mode == 'eager':
+      model.backbone.run = counted
     outs[mode] = model.sample().cpu()
     n_fwd[mode] = calls['n']
-    if mode == 'graph':
-      assert model._loop.cached == 'batch'
   assert torch.equal(outs['graph'], outs['eager'])
-  assert n_fwd['eager'] < 0.8 * 200, n_fwd          # the host rule skipped forwards
-  assert not torch.equal(outs['graph'], outs['nocache'])
+  assert 0 < n_fwd['eager'] < 0.8 * steps, n_fwd        # the host rule skipped forwards
+  # the captured loop skips exactly the same steps: drive it step by step and read the
+  # device-side live count (n_fwd * B sequences, or 0)
+  model, tok = _model(case)
+  model.config.sampling.steps = steps
+  B, L = case.batch, case.length
+  model._call_count = 1                                  # the key sample() used above
+  xt = model._sample_prior(B, L)
+  sig, mct, mcs = model._step_scalars(steps, 1e-5)
+  guidance = model.config.get('guidance')
+  cond = (torch.full((B,), guidance.condition, dtype=torch.long, device=DEV)
+          if guidance is not None else None)
+  loop = model._get_loop(B, L, None if guidance is None else guidance.method, guidance)
+  assert loop.cached == 'batch'
+  loop.prepare(xt, sig, mct, mcs, cond)
+  lives = []
+  for _ in range(steps):
+    loop.replay(1)
+    torch.cuda.synchronize()
+    lives.append(int(loop.n_live))
+  assert set(lives) <= {0, loop.n_fwd * B}
+  assert sum(1 for v in lives if v) == n_fwd['eager'], (lives, n_fwd)
+  assert torch.equal(loop.xt.cpu(), outs['graph'])
