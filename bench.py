@@ -295,6 +295,8 @@ def build_model(wl, batch, device, seed, steps=None):
     model.set_classifier(ddg_b200.Classifier(cfg, tok, device=device).load_state_dict(csd))
   if os.environ.get('DDG_RACE_GROUP'):             # sampler A/B knob (0 | 8 | 64)
     model.race_group = int(os.environ['DDG_RACE_GROUP'])
+  if os.environ.get('DDG_FUSE_LN'):                # LayerNorm A/B knob (0 = separate launches)
+    model.backbone.fuse_ln = os.environ['DDG_FUSE_LN'] != '0'
   return model, cfg
 
 
@@ -313,8 +315,8 @@ def _barrier(world):
 
 
 class GraphRun:
-  """Steady-state timing of the captured step loop (`_GraphLoop`) of a null / cfg
-  workload."""
+  """Steady-state timing of the captured step loop (`_GraphLoop`) of a workload
+  (null / cfg / cbg guidance)."""
 
   def __init__(self, wl, B, device, seed, table_steps=None):
     self.wl, self.B = wl, B
@@ -368,32 +370,16 @@ class GraphRun:
 
 
 def time_cbg(wl, B, device, seed, K, W, world):
-  """D-CBG workloads: `_cbg_denoise` steps through the public per-step API."""
-  model, cfg = build_model(wl, B, device, seed)
-  Lw = cfg.model.length
-  g = cfg.guidance
-  xt = model._sample_prior(B, Lw)
-  sig, mct, mcs = (t.to(device) for t in model._step_scalars(wl.sampling_steps, 1e-5))
-
-  def step(i, x):
-    i = i % wl.sampling_steps
-    xs, _, _ = model._cbg_denoise(
-      g.condition, g.gamma, model.classifier_model, x, sig[i].expand(B),
-      mct[i].expand(B)[:, None, None], mcs[i].expand(B)[:, None, None],
-      use_approx=g.get('use_approx', False))
-    return xs
-  with torch.no_grad():
-    for i in range(W):
-      xt = step(i, xt)
-    _barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-      xt = step(W + i, xt)
-    e1.record()
-    _barrier(world)
+  """D-CBG workloads: the captured step loop of `sample()` (denoiser forward, classifier
+  forward + backward or exact single-token edits, guided sampler in one CUDA graph)."""
+  run = GraphRun(wl, B, device, seed)
+  run.replay(W)
+  run.restart()
+  ms, _ = run.timed(K, world, device, gather=True)
+  xt = run.loop.xt
   assert int(xt.min()) >= 0 and int(xt.max()) < wl.tok.vocab_size
-  return _max_over_ranks(e0.elapsed_time(e1), device, world) / K
+  del run
+  return ms
 
 
 def shard(total, world):

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DDG_B200_LIB: developer knob for same-box A/B runs of two builds of the library
 LIB_PATH = os.environ.get('DDG_B200_LIB') or os.path.join(_HERE, 'libddg_b200.so')
 
-ABI_VERSION = 4   # DDG_ABI_VERSION of include/ddg_b200.h these bindings were written for
+ABI_VERSION = 5   # DDG_ABI_VERSION of include/ddg_b200.h these bindings were written for
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 F32, F16, BF16 = 0, 1, 2
 ABSORBING, UNIFORM, AR = 0, 1, 2
@@ -26,7 +26,7 @@ DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 EXPORTS = (
   'ddg_abi_version', 'ddg_last_error', 'ddg_device_check', 'ddg_sm_count',
   'ddg_sample_step', 'ddg_low_confidence_select', 'ddg_log_probs', 'ddg_sample_prior', 'ddg_step_advance',
-  'ddg_cond_embed', 'ddg_adaln', 'ddg_ln_modulate', 'ddg_ln_modulate_live', 'ddg_seq_compact', 'ddg_gemm',
+  'ddg_cond_embed', 'ddg_adaln', 'ddg_ln_modulate', 'ddg_ln_modulate_live', 'ddg_seq_compact', 'ddg_gemm', 'ddg_gemm_ln_work_bytes',
   'ddg_attention', 'ddg_attention_live', 'ddg_attention_decode', 'ddg_cast', 'ddg_classifier_head', 'ddg_cbg_candidates',
   'ddg_classifier_head_backward', 'ddg_gate_mul', 'ddg_gelu_backward',
   'ddg_ln_modulate_backward', 'ddg_attention_backward', 'ddg_split16',
@@ -66,7 +66,10 @@ class GemmArgs(C.Structure):
     ('stats', C.c_void_p), ('stats_ld', C.c_int64),
     ('stats_mask_col', C.c_int32), ('accumulate', C.c_int32),
     ('rope_pos0', C.c_int32), ('reserved', C.c_int32),
-    ('live_seqs', C.c_void_p), ('out_seq_map', C.c_void_p)]      # ABI v4
+    ('live_seqs', C.c_void_p), ('out_seq_map', C.c_void_p),      # ABI v4
+    ('ln_weight', C.c_void_p), ('ln_shift', C.c_void_p), ('ln_scale', C.c_void_p),   # ABI v5
+    ('ln_out', C.c_void_p), ('ln_work', C.c_void_p), ('ln_mod_stride', C.c_int64),
+    ('ln_dtype', C.c_int32), ('reserved1', C.c_int32)]
 
 
 def _load():
@@ -101,6 +104,8 @@ def _load():
                                        i64, i32, vp, vp, i32, vp, vp]
   lib.ddg_seq_compact.argtypes = [vp, i32, vp, vp, i32, vp]
   lib.ddg_gemm.argtypes = [C.POINTER(GemmArgs), vp]
+  lib.ddg_gemm_ln_work_bytes.argtypes = [i32, i32]
+  lib.ddg_gemm_ln_work_bytes.restype = i64
   lib.ddg_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
   lib.ddg_attention_live.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
   lib.ddg_attention_decode.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]

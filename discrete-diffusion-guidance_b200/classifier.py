@@ -81,11 +81,11 @@ class Classifier:
                                           round_bf16=self.round_bf16,
                                           seqs_per_mod=seqs_per_mod)
 
-  def first_order_term(self, xt, sigma, conditioning_class, finalize=True):
+  def first_order_term(self, xt, sigma, conditioning_class, finalize=True, out=None, live=None):
     """The `use_approx` branch of `_cbg_denoise` (diffusion.py:1532-1548):
     `grad - (one_hot * grad).sum(-1) + log p(y | xt)` with `grad` the gradient
     of `get_log_probs(one_hot(xt), sigma)[..., y].sum()` w.r.t. the one-hot
     input.  Returns ((B, L, V) fp32 term, (B, classes) log-probs)."""
     return self.classifier_model.first_order_term(
       xt, self._process_sigma(sigma), conditioning_class,
-      round_bf16=self.round_bf16, finalize=finalize)
+      round_bf16=self.round_bf16, finalize=finalize, out=out, live=live)

@@ -30,7 +30,11 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;           // 64 x 16-bit = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 6;
+constexpr int MAX_STAGES = 6;
+// internal epilogue id: GATE_RESIDUAL followed by the next LayerNorm + modulate (fused on chip)
+constexpr int EPI_GATE_RESIDUAL_LN = 16;
+// the fused-LayerNorm variant trades one pipeline stage for its per-column LayerNorm vectors
+template <int EPI> __host__ __device__ constexpr int stages_for() { return EPI == EPI_GATE_RESIDUAL_LN ? 5 : MAX_STAGES; }
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int BNH = BN / 2;          // W rows staged by each CTA of the pair
 constexpr int B_STAGE_BYTES = BNH * BK * 2;
@@ -41,9 +45,15 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_ROW_BYTES = 80;                  // 64 B payload + 16 B pad: conflict-free 128-bit stores
 constexpr int EPI_SLAB_BYTES = 32 * EPI_ROW_BYTES;  // one warp's 32 accumulator rows
+constexpr int LN_ROW_BYTES = 144;                  // fused LayerNorm: 32 fp32 columns (128 B) + 16 B pad per row
+constexpr int LN_SLAB_BYTES = 32 * LN_ROW_BYTES;
 constexpr int EPI_BIAS_BYTES = NUM_EPI_WARPS * (BN / 2) * 4;   // fp32 bias (and gate) of each epilogue warp's 128 columns
-constexpr int SMEM_BYTES =
-  STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * EPI_SLAB_BYTES + 2 * EPI_BIAS_BYTES;
+constexpr int EPI_LN_BYTES = 3 * EPI_BIAS_BYTES;   // fused LayerNorm: weight, 1 + scale, shift (fp32) per epilogue warp
+template <int EPI> __host__ __device__ constexpr int smem_bytes() {
+  return stages_for<EPI>() * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+         8 * (EPI == EPI_GATE_RESIDUAL_LN ? LN_SLAB_BYTES : EPI_SLAB_BYTES) + 2 * EPI_BIAS_BYTES +
+         (EPI == EPI_GATE_RESIDUAL_LN ? EPI_LN_BYTES : 0);
+}
 
 struct GemmParams {
   void* out;
@@ -63,6 +73,15 @@ struct GemmParams {
   const int32_t* out_seq_map;  // optional (STORE): compact sequence s is written to output sequence out_seq_map[s]
   int stream_out;       // output larger than L2 (the vocab head's logits): evict-first stores,
                         // evict-last operand loads, so the write stream does not push W out of L2
+  // fused LayerNorm + modulate of the updated residual rows (EPI_GATE_RESIDUAL_LN)
+  const float* ln_w;    // (N,) fp32
+  const void* ln_shift; // rows of `ln_dtype` (stride ln_mod_stride, row = m / rows_per_mod) or null
+  const void* ln_scale; // 1 + scale, same layout
+  void* ln_out;         // (M, N) `ln_dtype`
+  float2* ln_part;      // (M, N / 128) per-row partial (mean, M2) of each 128-column run
+  int* ln_cnt;          // one arrival counter per 128-row block, zero between launches
+  int64_t ln_mod_stride;
+  int ln_dtype;
 };
 
 // ------------------------------------------------------------------ PTX
@@ -234,6 +253,46 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                  "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                :
                : "memory");
+}
+
+// registers -> tensor memory, same 32x32b layout as tmem_ld32 (lane = row, 32 consecutive columns)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+    "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+    "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+    ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+      "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]),
+      "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]),
+      "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+    : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 ld_relaxed_gpu_f2(const float2* p) {
+  float2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t ld_relaxed_gpu_b64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_b64(void* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // K-major, 128B-swizzled shared-memory matrix descriptor (PTX ISA "matrix
@@ -430,6 +489,7 @@ template <typename T, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const GemmParams p) {
+  constexpr int STAGES = stages_for<EPI>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -441,8 +501,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint8_t* smem_epi = smem + STAGES * STAGE_BYTES + 256;
-  uint8_t* smem_bias = smem_epi + NUM_EPI_WARPS * EPI_SLAB_BYTES;
+  constexpr int SLAB_BYTES = EPI == EPI_GATE_RESIDUAL_LN ? LN_SLAB_BYTES : EPI_SLAB_BYTES;
+  uint8_t* smem_bias = smem_epi + NUM_EPI_WARPS * SLAB_BYTES;
   uint8_t* smem_gate = smem_bias + EPI_BIAS_BYTES;
+  uint8_t* smem_ln = smem_gate + EPI_BIAS_BYTES;   // EPI_GATE_RESIDUAL_LN only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -551,7 +613,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int quarter = e & 3;                  // == warp % 4: TMEM lanes 32*quarter..
     const int chalf = e >> 2;                   // column half of the tile
     const int row_in_tile = quarter * 32 + lane;
-    const uint32_t stg = smem_u32(smem_epi + e * EPI_SLAB_BYTES);
+    const uint32_t stg = smem_u32(smem_epi + e * SLAB_BYTES);
     const uint32_t stg_wr = stg + (uint32_t)lane * EPI_ROW_BYTES;
     const int crow = lane >> 2;                 // coalesced phase: row in an 8-row slab
     const int cchunk = lane & 3;                // 16-byte chunk of the 64-byte row
@@ -567,12 +629,279 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int m = m0 + row_in_tile;
       const bool row_ok = m < M;
       const int mw = m0 + quarter * 32;         // first row of this warp's slab
+      // fused LayerNorm: fp32 tiles pass through the slab as 32 rows x (128 + 16) B; with lanes
+      // along the rows one access covers 4 rows x 128 contiguous bytes (r4 = row, c8 = 16-byte chunk)
+      const int r4 = lane >> 3, c8 = lane & 7;
+      const uint32_t xs_row = stg + (uint32_t)lane * LN_ROW_BYTES;
+      const uint32_t xs_co = stg + (uint32_t)r4 * LN_ROW_BYTES + (uint32_t)c8 * 16;
+      const bool cols_ok = n0 < p.N;
+      float4 xn[8];                             // x of the next 32 columns (lanes along the rows)
+      auto ln_prefetch_x = [&](int nc) {
+        const float* xb = reinterpret_cast<const float*>(p.out) + (int64_t)(mw + r4) * p.ld_out + nc + c8 * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          xn[i] = (mw + 4 * i + r4 < M) ? *reinterpret_cast<const float4*>(xb + (int64_t)(4 * i) * p.ld_out)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      if constexpr (EPI == EPI_GATE_RESIDUAL_LN) {
+        // the residual rows do not depend on the accumulator: their first chunk is on its way
+        // (and the rest of the warp's 32 x 128 block is pulled into L2) while the MMAs finish
+        if (cols_ok) {
+          ln_prefetch_x(n0);
+          if (mw + lane < M) {
+            const float* xb = reinterpret_cast<const float*>(p.out) + (int64_t)(mw + lane) * p.ld_out + n0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + k * 32));
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr =
         tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chalf * (BN / 2));
 
-      if (EPI == DDG_EPI_GATE_RESIDUAL || EPI == DDG_EPI_ACCUM_F32) {
+      if constexpr (EPI == EPI_GATE_RESIDUAL_LN) {
+        // -------- x += round(gate * round(acc + bias)) AND the LayerNorm + modulate of the updated
+        // row (models/dit.py:312-321: the norm that follows every residual add), without a second
+        // trip of x through HBM.  A row's 768 columns are spread over num_n tiles that different
+        // CTA pairs process at about the same time (N-inner tile order), so:
+        //   pass 1   x_new = x + delta, formed with thread = row (x comes in through the transposing
+        //            slab), PARKED in this tile's accumulator columns of tensor memory (tcgen05.st)
+        //            and reduced to a per-row (mean, M2) over the warp's 128 columns (shifted sums);
+        //   exchange each partial travels as ONE 64-bit word -- mean | M2 with the block's epoch
+        //            parity in M2's sign bit (M2 >= 0) -- so data and validity arrive together and
+        //            no fence is needed; a reader polls the words of its row until the parity
+        //            matches.  Every owner writes all 32 rows of its slab (also rows past M), so a
+        //            block's words always carry the parity of the block's last visit; the block's
+        //            counter word is (parity << 8) | departures and the last owner to leave flips
+        //            the parity for the next launch;
+        //   store    while the other owners' words travel, x_new goes from tensor memory to the
+        //            fp32 residual stream (coalesced through the slab);
+        //   pass 2   x_new comes back from tensor memory once more, ((x - mean) * rstd) * w
+        //            [* (1 + scale) + shift], one rounding to the LayerNorm's output type, coalesced
+        //            16-bit stores.
+        // Combining the partials in slot order gives every owner of a row the same mean / rstd.
+        // No deadlock: the owners of a block's tiles are distinct resident CTA pairs, and a pair's
+        // epilogue only ever waits for tiles numbered within num_n of its own current tile, whose
+        // mainloops depend on strictly earlier blocks only.
+        const int nvalid = p.N >> 7;                       // 128-column runs per row (host: N % 128 == 0, <= 8)
+        if (cols_ok) {
+          const bool have_bias = p.bias != nullptr;
+          const bool have_mod = p.ln_shift != nullptr;
+          const uint32_t bias_s = smem_u32(smem_bias) + (uint32_t)e * (BN / 2) * 4;
+          const uint32_t gate_s = smem_u32(smem_gate) + (uint32_t)e * (BN / 2) * 4;
+          const uint32_t lnw_s = smem_u32(smem_ln) + (uint32_t)e * (BN / 2) * 4;
+          const uint32_t lng_s = lnw_s + EPI_BIAS_BYTES, lns_s = lng_s + EPI_BIAS_BYTES;
+          // host guarantees rows_per_mod % 32 == 0: the warp's 32 rows share one conditioning row
+          const int rpm = p.rows_per_mod > 0x7fffffff ? 0x7fffffff : (int)p.rows_per_mod;
+          const int mrow = (mw < M ? mw : 0) / rpm;
+          const T* gate_row = p.gate ? reinterpret_cast<const T*>(p.gate) + (int64_t)mrow * p.gate_stride : nullptr;
+          if (have_bias) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(p.bias) + n0) + lane);
+            const float2 b01 = H2<T>::unpack(raw.x), b23 = H2<T>::unpack(raw.y);
+            st_shared_v4(bias_s + 16 * lane, __float_as_uint(b01.x), __float_as_uint(b01.y),
+                         __float_as_uint(b23.x), __float_as_uint(b23.y));
+          }
+          if (gate_row) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(gate_row + n0) + lane);
+            const float2 g01 = H2<T>::unpack(raw.x), g23 = H2<T>::unpack(raw.y);
+            st_shared_v4(gate_s + 16 * lane, __float_as_uint(g01.x), __float_as_uint(g01.y),
+                         __float_as_uint(g23.x), __float_as_uint(g23.y));
+          }
+          {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.ln_w + n0) + lane);
+            st_shared_v4(lnw_s + 16 * lane, __float_as_uint(w4.x), __float_as_uint(w4.y), __float_as_uint(w4.z),
+                         __float_as_uint(w4.w));
+          }
+          __syncwarp();
+          // the block's counter word, read before this warp publishes anything: no owner can have
+          // departed yet, so it is (parity << 8) exactly (used after pass 1: latency hidden)
+          int* cnt = p.ln_cnt + (mb * 2 + (int)cta_rank);
+          const int epoch_word = ld_relaxed_gpu(cnt);
+          // ---- pass 1
+          float s1 = 0.f, s2 = 0.f, c0 = 0.f;
+#pragma unroll 1
+          for (int g = 0; g < BN / 64; ++g) {
+            const int nc = n0 + g * 32;
+            uint32_t r0[32];
+            tmem_ld32(taddr + (uint32_t)(g * 32), r0);      // in flight while x goes through the slab
+            // x of this chunk (prefetched, lanes along the rows) -> slab
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              st_shared_v4(xs_co + (uint32_t)(4 * i) * LN_ROW_BYTES, __float_as_uint(xn[i].x), __float_as_uint(xn[i].y),
+                           __float_as_uint(xn[i].z), __float_as_uint(xn[i].w));
+            __syncwarp();
+            if (g + 1 < BN / 64) ln_prefetch_x(nc + 32);
+            tmem_ld_wait(r0);
+            float2 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = make_float2(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+            if (have_bias) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint4 b = ld_shared_v4(bias_s + (uint32_t)(g * 128 + 16 * i));
+                v[2 * i] = add2(v[2 * i], make_float2(__uint_as_float(b.x), __uint_as_float(b.y)));
+                v[2 * i + 1] = add2(v[2 * i + 1], make_float2(__uint_as_float(b.z), __uint_as_float(b.w)));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = H2<T>::unpack(H2<T>::pack(v[i].x, v[i].y));
+            if (gate_row) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint4 b = ld_shared_v4(gate_s + (uint32_t)(g * 128 + 16 * i));
+                v[2 * i] = mul2(v[2 * i], make_float2(__uint_as_float(b.x), __uint_as_float(b.y)));
+                v[2 * i + 1] = mul2(v[2 * i + 1], make_float2(__uint_as_float(b.z), __uint_as_float(b.w)));
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = H2<T>::unpack(H2<T>::pack(v[i].x, v[i].y));
+            }
+            // thread = row: x_new = x + delta
+            float xr[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint4 u = ld_shared_v4(xs_row + q * 16);
+              xr[4 * q] = __uint_as_float(u.x) + v[2 * q].x;
+              xr[4 * q + 1] = __uint_as_float(u.y) + v[2 * q].y;
+              xr[4 * q + 2] = __uint_as_float(u.z) + v[2 * q + 1].x;
+              xr[4 * q + 3] = __uint_as_float(u.w) + v[2 * q + 1].y;
+            }
+            __syncwarp();                      // slab free for the next chunk
+            if (g == 0) c0 = xr[0];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float d = xr[k] - c0;
+              s1 += d;
+              s2 = fmaf(d, d, s2);
+            }
+            tmem_st32(taddr + (uint32_t)(g * 32), xr);
+          }
+          tmem_st_wait();
+          // ---- publish this warp's partial of each of its 32 rows (also rows past M)
+          const int target = 4 * nvalid;
+          const uint32_t tagbit = (((uint32_t)epoch_word >> 8) + 1u) & 1u;
+          {
+            const float mean_i = c0 + s1 * (1.f / 128.f);
+            const float m2_i = fmaxf(s2 - s1 * s1 * (1.f / 128.f), 0.f);
+            const uint64_t word = (uint64_t)__float_as_uint(mean_i) |
+                                  ((uint64_t)((__float_as_uint(m2_i) & 0x7fffffffu) | (tagbit << 31)) << 32);
+            st_relaxed_gpu_b64(p.ln_part + (int64_t)m * nvalid + (nb * 2 + chalf), word);
+          }
+          // ---- x_new -> fp32 residual stream while the other owners' words travel
+          float* xrow = reinterpret_cast<float*>(p.out) + (int64_t)(mw + r4) * p.ld_out + c8 * 4;
+#pragma unroll 1
+          for (int g = 0; g < BN / 64; ++g) {
+            const int nc = n0 + g * 32;
+            uint32_t r[32];
+            tmem_ld32_sync(taddr + (uint32_t)(g * 32), r);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) st_shared_v4(xs_row + q * 16, r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 y = ld_shared_v4(xs_co + (uint32_t)(4 * i) * LN_ROW_BYTES);
+              if (mw + 4 * i + r4 < M) *reinterpret_cast<uint4*>(xrow + (int64_t)(4 * i) * p.ld_out + nc) = y;
+            }
+            __syncwarp();
+          }
+          // ---- the row's partials from all owners, combined in slot order (same result everywhere)
+          float mean, rstd;
+          {
+            float2 pt[8];
+            const uint64_t* slots = reinterpret_cast<const uint64_t*>(p.ln_part + (int64_t)m * nvalid);
+            const long long t0 = clock64();
+            bool all;
+            do {
+              all = true;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                if (k < nvalid) {
+                  const uint64_t w = ld_relaxed_gpu_b64(slots + k);
+                  all = all && ((uint32_t)(w >> 63) == tagbit);
+                  pt[k] = make_float2(__uint_as_float((uint32_t)w), __uint_as_float((uint32_t)(w >> 32) & 0x7fffffffu));
+                } else {
+                  pt[k] = make_float2(0.f, 0.f);
+                }
+              }
+              // ~0.15 s: never hang the device on a stale scratch buffer
+            } while (!all && clock64() - t0 < (1ll << 28));
+            float sm = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sm += pt[k].x;
+            mean = sm / (float)nvalid;
+            float m2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k < nvalid) {
+                const float d = pt[k].x - mean;
+                m2 += pt[k].y + 128.f * d * d;
+              }
+            rstd = rsqrtf(m2 / (float)p.N + 1e-5f);
+          }
+          __syncwarp();
+          // departure (relaxed): the last owner to leave flips the block's parity for the next launch
+          int departed = 0;
+          if (lane == 0) departed = atomicAdd(cnt, 1);
+          // ---- pass 2
+          auto pass2 = [&](auto tag) {
+            using TO = decltype(tag);
+            if (have_mod) {
+              const TO* sh = reinterpret_cast<const TO*>(p.ln_shift) + (int64_t)mrow * p.ln_mod_stride + n0;
+              const TO* sc = reinterpret_cast<const TO*>(p.ln_scale) + (int64_t)mrow * p.ln_mod_stride + n0;
+              const uint2 rs = __ldg(reinterpret_cast<const uint2*>(sh) + lane);
+              const uint2 rg = __ldg(reinterpret_cast<const uint2*>(sc) + lane);
+              const float2 s01 = H2<TO>::unpack(rs.x), s23 = H2<TO>::unpack(rs.y);
+              const float2 g01 = H2<TO>::unpack(rg.x), g23 = H2<TO>::unpack(rg.y);
+              st_shared_v4(lns_s + 16 * lane, __float_as_uint(s01.x), __float_as_uint(s01.y), __float_as_uint(s23.x),
+                           __float_as_uint(s23.y));
+              st_shared_v4(lng_s + 16 * lane, __float_as_uint(g01.x), __float_as_uint(g01.y), __float_as_uint(g23.x),
+                           __float_as_uint(g23.y));
+            }
+            __syncwarp();
+            TO* oslab = reinterpret_cast<TO*>(p.ln_out) + (int64_t)mw * p.N + cchunk * 8;
+            const float2 mean2 = make_float2(mean, mean), rs2 = make_float2(rstd, rstd);
+#pragma unroll 1
+            for (int g = 0; g < BN / 64; ++g) {
+              const int nc = n0 + g * 32;
+              uint32_t r[32];
+              tmem_ld32_sync(taddr + (uint32_t)(g * 32), r);
+              uint32_t w[16];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint4 lw = ld_shared_v4(lnw_s + (uint32_t)(g * 128 + 16 * i));
+                // ((x - mean) * rstd) * w, then * (1 + scale) + shift: ln_modulate_kernel's order
+                float2 y0 = mul2(mul2(sub2(make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), mean2), rs2),
+                                 make_float2(__uint_as_float(lw.x), __uint_as_float(lw.y)));
+                float2 y1 = mul2(mul2(sub2(make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), mean2), rs2),
+                                 make_float2(__uint_as_float(lw.z), __uint_as_float(lw.w)));
+                if (have_mod) {
+                  const uint4 lg = ld_shared_v4(lng_s + (uint32_t)(g * 128 + 16 * i));
+                  const uint4 ls = ld_shared_v4(lns_s + (uint32_t)(g * 128 + 16 * i));
+                  y0 = fma2(y0, make_float2(__uint_as_float(lg.x), __uint_as_float(lg.y)),
+                            make_float2(__uint_as_float(ls.x), __uint_as_float(ls.y)));
+                  y1 = fma2(y1, make_float2(__uint_as_float(lg.z), __uint_as_float(lg.w)),
+                            make_float2(__uint_as_float(ls.z), __uint_as_float(ls.w)));
+                }
+                w[2 * i] = H2<TO>::pack(y0.x, y0.y);
+                w[2 * i + 1] = H2<TO>::pack(y1.x, y1.y);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) st_shared_v4(stg_wr + q * 16, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int row = 8 * i + crow;
+                const uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
+                if (mw + row < M) *reinterpret_cast<uint4*>(oslab + (int64_t)row * p.N + nc) = y;
+              }
+            }
+          };
+          if (p.ln_dtype == DDG_BF16) pass2(__nv_bfloat16());
+          else pass2(__half());
+          if (lane == 0 && (departed & 255) == target - 1) atomicExch(cnt, (int)(tagbit << 8));
+        }
+      } else if (EPI == DDG_EPI_GATE_RESIDUAL || EPI == DDG_EPI_ACCUM_F32) {
         // ACCUM_F32: out = (accumulate ? out : 0) + acc, no rounding (fp32 dgrad outputs).
         constexpr bool PLAIN = EPI == DDG_EPI_ACCUM_F32;
         // -------- x += round(gate * round(acc + bias)), fp32 residual stream.
@@ -927,13 +1256,14 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-    DDG_CUDA(cudaFuncSetAttribute(gemm_kernel<T, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DDG_CUDA(cudaFuncSetAttribute(gemm_kernel<T, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  smem_bytes<EPI>()));
     attr_done[dev] = true;
   }
   const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
   int grid = sm_count() & ~1;           // CTA pairs
   if (grid > 2 * num_tiles) grid = 2 * num_tiles;
-  gemm_kernel<T, EPI><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, p);
+  gemm_kernel<T, EPI><<<grid, NUM_THREADS, smem_bytes<EPI>(), s>>>(ta, tb, p);
   return check_cuda(cudaGetLastError(), "gemm launch");
 }
 
@@ -943,7 +1273,9 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     case DDG_EPI_STORE: return launch_gemm<T, DDG_EPI_STORE>(ta, tb, p, s);
     case DDG_EPI_QKV_ROPE: return launch_gemm<T, DDG_EPI_QKV_ROPE>(ta, tb, p, s);
     case DDG_EPI_BIAS_GELU: return launch_gemm<T, DDG_EPI_BIAS_GELU>(ta, tb, p, s);
-    case DDG_EPI_GATE_RESIDUAL: return launch_gemm<T, DDG_EPI_GATE_RESIDUAL>(ta, tb, p, s);
+    case DDG_EPI_GATE_RESIDUAL:
+      if (p.ln_w) return launch_gemm<T, EPI_GATE_RESIDUAL_LN>(ta, tb, p, s);
+      return launch_gemm<T, DDG_EPI_GATE_RESIDUAL>(ta, tb, p, s);
     case DDG_EPI_ACCUM_F32: return launch_gemm<T, DDG_EPI_ACCUM_F32>(ta, tb, p, s);
   }
   set_error("gemm: bad epilogue %d", epi);
@@ -952,6 +1284,12 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
 
 }  // namespace
 }  // namespace ddg
+
+extern "C" int64_t ddg_gemm_ln_work_bytes(int32_t M, int32_t N) {
+  if (M < 0 || N <= 0) return 0;
+  const int64_t n_blocks = 2 * (((int64_t)M + 2 * ddg::BM - 1) / (2 * ddg::BM));
+  return (n_blocks * 4 + 255) / 256 * 256 + n_blocks * ddg::BM * ((N + 127) / 128) * 8;
+}
 
 extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
   using namespace ddg;
@@ -1009,6 +1347,34 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
   // 131072 rows) is written with an evict-first policy and its operands are loaded evict-last:
   // without this the write-allocate stream kept evicting W (47 MB) and ncu showed 4.4 GB of DRAM
   // reads per launch against 0.25 GB algorithmic (profiles/r01_traffic.json)
+  p.ln_w = nullptr; p.ln_shift = p.ln_scale = nullptr; p.ln_out = nullptr; p.ln_part = nullptr; p.ln_cnt = nullptr;
+  p.ln_mod_stride = 0; p.ln_dtype = 0;
+  if (a.ln_weight) {
+    // fused LayerNorm + modulate of the updated residual rows (see the epilogue)
+    DDG_REQUIRE(a.epilogue == DDG_EPI_GATE_RESIDUAL, DDG_ERR_INVALID, "gemm: ln_weight needs the GATE_RESIDUAL epilogue");
+    DDG_REQUIRE(a.N % 128 == 0 && a.N <= 1024 && a.ld_out == a.N, DDG_ERR_UNSUPPORTED,
+                "gemm: fused LayerNorm needs N %% 128 == 0, N <= 1024 and a dense residual (N=%d ld_out=%lld)", a.N,
+                (long long)a.ld_out);
+    DDG_REQUIRE(a.ln_out && a.ln_work && reinterpret_cast<uintptr_t>(a.ln_out) % 16 == 0 &&
+                reinterpret_cast<uintptr_t>(a.ln_work) % 256 == 0 && reinterpret_cast<uintptr_t>(a.ln_weight) % 16 == 0,
+                DDG_ERR_INVALID, "gemm: fused LayerNorm needs ln_out (16-byte aligned) and ln_work (256-byte aligned)");
+    DDG_REQUIRE(a.ln_dtype == DDG_F16 || a.ln_dtype == DDG_BF16, DDG_ERR_INVALID, "gemm: ln_dtype must be f16 or bf16");
+    DDG_REQUIRE((a.ln_shift == nullptr) == (a.ln_scale == nullptr), DDG_ERR_INVALID,
+                "gemm: ln_shift and ln_scale go together");
+    if (a.gate || a.ln_shift)
+      DDG_REQUIRE(a.rows_per_mod > 0 && a.rows_per_mod % 32 == 0, DDG_ERR_UNSUPPORTED,
+                  "gemm: fused LayerNorm needs rows_per_mod %% 32 == 0");
+    if (a.ln_shift)
+      DDG_REQUIRE(a.ln_mod_stride % 8 == 0 && reinterpret_cast<uintptr_t>(a.ln_shift) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(a.ln_scale) % 16 == 0, DDG_ERR_INVALID, "gemm: ln_shift / ln_scale layout");
+    p.ln_w = a.ln_weight; p.ln_shift = a.ln_shift; p.ln_scale = a.ln_scale; p.ln_out = a.ln_out;
+    p.ln_mod_stride = a.ln_mod_stride; p.ln_dtype = a.ln_dtype;
+    // ln_work = [one int32 counter per 128-row block, padded to 256 B][(M, N / 128) float2 partials]
+    const int64_t n_blocks = 2 * (((int64_t)a.M + 2 * BM - 1) / (2 * BM));
+    p.ln_cnt = reinterpret_cast<int*>(a.ln_work);
+    p.ln_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(a.ln_work) + (n_blocks * 4 + 255) / 256 * 256);
+    // (rows are padded to whole 128-row blocks: every owner publishes all rows of its slab)
+  }
   p.stream_out = (a.epilogue == DDG_EPI_STORE && (int64_t)a.M * a.N * 2 >= ((int64_t)256 << 20)) ? 1 : 0;
   if (a.stats) {
     DDG_REQUIRE(a.epilogue == DDG_EPI_STORE && a.stats_ld >= a.M &&

@@ -436,21 +436,25 @@ class Diffusion:
       'log_x_theta_uncond': lu, 'log_x_theta_cond': lc}
 
   def _classifier_term(self, classifier_model, xt, time_conditioning,
-                       conditioning_class, use_approx, raw_ok=False):
+                       conditioning_class, use_approx, raw_ok=False, out=None, live=None):
     """(B, L, V) fp32 classifier log-prob term of D-CBG.  `raw_ok`: the caller only
     samples from it (the term is not handed back), so the row-constant part of the
-    first-order term, which cancels in the guided softmax, may be left out."""
+    first-order term, which cancels in the guided softmax, may be left out.
+    `out` / `live` (the captured step loop): preallocated flat term buffer, and a device
+    int32 scalar that keeps the buffer's previous contents when it reads 0."""
     if use_approx:
       # first order (diffusion.py:1532-1548): one classifier forward + backward
       term, _ = classifier_model.first_order_term(xt, time_conditioning,
-                                                  conditioning_class, finalize=not raw_ok)
+                                                  conditioning_class, finalize=not raw_ok,
+                                                  out=out, live=live)
       return term
     # exact: every single-token edit of xt (diffusion.py:1549-1585), generated
     # chunk by chunk on the device and never materialised as a whole.
     B, L = xt.shape
     V = self.vocab_size
     total = B * L * V
-    term = torch.empty(total, dtype=torch.float32, device=self.device)
+    term = (out.view(-1)[:total] if out is not None
+            else torch.empty(total, dtype=torch.float32, device=self.device))
     sigma = self._process_sigma(time_conditioning).to(self.device, torch.float32)
     chunk = max(L * V, (classifier_model.chunk_sequences // (L * V)) * (L * V))
     for c0 in range(0, total, chunk):
@@ -462,7 +466,10 @@ class Diffusion:
       # sequence shares t), not one per candidate (diffusion.py:1584 repeats sigma instead)
       b0, b1 = c0 // (L * V), (c0 + n) // (L * V)
       lp = classifier_model.get_log_probs(ids, sigma[b0:b1], seqs_per_mod=L * V)
-      term[c0:c0 + n] = lp[:, conditioning_class]
+      new = lp[:, conditioning_class]
+      if live is not None:
+        new = torch.where(live > 0, new, term[c0:c0 + n])
+      term[c0:c0 + n] = new
     return term.view(B, L, V)
 
   def _cbg_denoise(self, conditioning_class, gamma, classifier_model, xt,
@@ -519,11 +526,13 @@ class Diffusion:
     xt = self._sample_prior(B, L)
     sigma_t, mc_t, mc_s = self._step_scalars(steps, eps)
     mixed_cond = cond is not None and not bool((cond == cond.reshape(-1)[0]).all())
-    if self.noise_fn is not None or self.return_q_xs or method == 'cbg' \
+    if self.noise_fn is not None or self.return_q_xs \
         or not self.use_cuda_graph or self._low_confidence or mixed_cond \
         or (self._use_float64 and method is None):
       return self._eager_loop(xt, sigma_t, mc_t, mc_s, method, guidance,
                               classifier_model, cond)
+    if method == 'cbg':
+      self.classifier_model = classifier_model
     loop = self._get_loop(B, L, method, guidance)
     return loop.run(xt, sigma_t, mc_t, mc_s, cond)
 
@@ -560,6 +569,9 @@ class Diffusion:
     gamma = None if guidance is None else float(guidance.gamma)
     key = (B, L, method, gamma, self.round_bf16, self.fast_math,
            self.race_group, self.logits_cache)
+    if method == 'cbg':
+      key += (int(guidance.condition), bool(guidance.get('use_approx', False)),
+              id(self.classifier_model))
     if self._loop is None or self._loop.key != key:
       self._loop = _GraphLoop(self, B, L, method, gamma, key)
     return self._loop
@@ -752,6 +764,17 @@ class _GraphLoop:
     self.stats = model.backbone.alloc_stats(self.n_fwd * B * L)
     self.labels = (torch.zeros(self.n_fwd, dtype=torch.int64, device=dev)
                    if method == 'cfg' else None)
+    # D-CBG (diffusion.py:1511-1624): denoiser forward, classifier term (first order: one
+    # forward + backward; exact: every single-token edit), guided sampler -- all in the
+    # captured step, the term in a persistent buffer
+    self.classifier = self.term = None
+    if method == 'cbg':
+      g = model.config.guidance
+      self.classifier = model.classifier_model
+      self.condition = int(g.condition)
+      self.use_approx = bool(g.get('use_approx', False))
+      ldv = (model.vocab_size + 3) // 4 * 4 if self.use_approx else model.vocab_size
+      self.term = torch.empty(B * L, ldv, dtype=torch.float32, device=dev)
     self.tables = None
     self.graph = None
     self.ws_generation = -1
@@ -798,15 +821,23 @@ class _GraphLoop:
                    ids_period=B * L, stats_out=self.stats,
                    stats_mask_col=m._stats_mask_col, live=live)
     ld = m.backbone.vocab_ld
+    term = None
+    if self.method == 'cbg':
+      # this step's sigma from the device table (one shared conditioning row)
+      sigma_now = sig.index_select(0, self.step).expand(B)
+      term = m._classifier_term(self.classifier, self.xt, sigma_now, self.condition,
+                                self.use_approx, raw_ok=True, out=self.term,
+                                live=self.n_live if self.cached else None)
+    guide = (_lib.GUIDE_CFG if self.two else
+             _lib.GUIDE_CBG if term is not None else _lib.GUIDE_NONE)
     m._launch_sampler(
       logits_a=self.logits.data_ptr(), ld_a=ld,
       logits_b=(self.logits.data_ptr() + B * L * ld * 2) if self.two else None,
-      ld_b=ld if self.two else 0, xt=self.xt, xs=self.xt, mc_t=mct, mc_s=mcs,
+      ld_b=ld if self.two else 0, clf=term, xt=self.xt, xs=self.xt, mc_t=mct, mc_s=mcs,
       rows=B * L, seq_len=L, mc_seq_stride=0, mc_step_stride=1,
       step_ptr=self.step, seed_ptr=self.seed_dev,
       stats=(self.stats, 0, B * L if self.two else 0),
-      guidance=_lib.GUIDE_CFG if self.two else _lib.GUIDE_NONE,
-      gamma=self.gamma if self.two else 1.0,
+      guidance=guide, gamma=self.gamma if guide != _lib.GUIDE_NONE else 1.0,
       seq_changed=self.changed if self.cached else None)
     check(lib.ddg_step_advance(ptr(self.step), stream_ptr()))
 

@@ -64,6 +64,7 @@ class DIT:
     self.head_dtype = torch.bfloat16
     self.vocab_ld = _pad_to(vocab_size, 64)   # padded logits leading dim
     self.seg_seqs = None                      # micro-batch (sequences) or None
+    self.fuse_ln = True                       # LayerNorm + modulate inside the residual GEMMs
     if classifier:
       pooling = m.get('pooling', 'mean')
       if pooling != 'mean':
@@ -186,6 +187,11 @@ class DIT:
       ws = {
         'x': torch.empty(rows, h, dtype=torch.float32, device=dev),
         'a16': torch.empty(seg, h, dtype=torch.int16, device=dev),
+        'att': torch.empty(seg, h, dtype=torch.int16, device=dev),
+        # scratch of the fused LayerNorm epilogue (arrival counters + per-row partials):
+        # zero once, every launch leaves the counters zero again
+        'ln_work': torch.zeros(int(lib.ddg_gemm_ln_work_bytes(rows, h)), dtype=torch.uint8,
+                               device=dev),
         'qkv': torch.empty(seg, 3 * h, dtype=torch.int16, device=dev),
         'h4': torch.empty(seg, 4 * h, dtype=torch.int16, device=dev),
         'c': torch.empty(n_mod, self.cond_dim, dtype=torch.float32, device=dev),
@@ -293,12 +299,19 @@ class DIT:
     seq_map, n_live = (ptr(live[0]), ptr(live[1])) if live is not None else (0, 0)
     x = ptr(ws['x']) + r0 * h * 4
     a16, qkv, h4 = ptr(ws['a16']), ptr(ws['qkv']), ptr(ws['h4'])
+    # The LayerNorm + modulate that follows a residual add runs inside that GEMM's epilogue
+    # (rows normalised while still on chip); only the first norm (embedding gather) is a launch
+    # of its own.  The attention output then needs its own buffer: a16 is the norm's output.
+    fuse = (self.fuse_ln and saved is None and h % 128 == 0 and h <= 1024
+            and rpm % 32 == 0)
+    att = ptr(ws['att']) if fuse else a16
+    ln_work = ptr(ws['ln_work'])
     modb = ptr(ws['mod_blk']) + mod0 * mod_stride * 2
     ids_p = ptr(ids) + (r0 % period) * 8
     ada = self.use_adaln
 
     def gemm(a, lda, w, ldw, out, ld_out, N, K, epi, dtype, bias=0, gate=0,
-             gate_stride=0, stats=0, stats_ld=0, out_map=0):
+             gate_stride=0, stats=0, stats_ld=0, out_map=0, ln=None):
       g = _lib.GemmArgs(
         a=a, w=w, out=out, bias=bias, gate=gate, rope_cos=ptr(cos),
         rope_sin=ptr(sin), lda=lda, ldw=ldw, ld_out=ld_out,
@@ -306,6 +319,9 @@ class DIT:
         epilogue=epi, seq_len=L, head_dim=self.head_dim, rope_cols=2 * h,
         stats=stats, stats_ld=stats_ld, stats_mask_col=stats_mask_col,
         live_seqs=n_live, out_seq_map=out_map)
+      if ln is not None:   # (weight, shift, 1 + scale, stride between conditioning rows, dtype)
+        g.ln_weight, g.ln_shift, g.ln_scale, g.ln_mod_stride, g.ln_dtype = ln
+        g.ln_out, g.ln_work = a16, ln_work
       check(lib.ddg_gemm(g, s))
 
     def ln(xp, ids_arg, emb, w, shift, scale, stride, code, out):
@@ -317,10 +333,13 @@ class DIT:
                                        stride, rpm, code, out, n_live, L,
                                        seq_map if ids_arg else 0, s))
 
+    fin = self.use_adaln and not self.classifier and self.final_adaln
+    mf = ptr(ws['mod_fin']) + mod0 * 2 * h * 2
     for i in range(nb):
       mb = modb + i * 6 * h * 2
-      ln(x, ids_p if i == 0 else 0, ptr(self.embedding), ptr(self.ln1[i]),
-         mb if ada else 0, mb + h * 2 if ada else 0, mod_stride, bcode, a16)
+      if i == 0 or not fuse:
+        ln(x, ids_p if i == 0 else 0, ptr(self.embedding), ptr(self.ln1[i]),
+           mb if ada else 0, mb + h * 2 if ada else 0, mod_stride, bcode, a16)
       qkv_i = qkv
       if saved is not None:   # block input (set by the gather above for i == 0); the rotated
         # QKV of this block is written straight into its own buffer (kept for the backward)
@@ -330,28 +349,39 @@ class DIT:
       gemm(a16, h, ptr(self.w_qkv[i]), h, qkv_i, 3 * h, 3 * h, h,
            _lib.EPI_QKV_ROPE, bcode)
       if live is None:
-        check(lib.ddg_attention(qkv_i, a16, n // L, L, self.n_heads, self.head_dim,
+        check(lib.ddg_attention(qkv_i, att, n // L, L, self.n_heads, self.head_dim,
                                 1 if self.causal else 0, bcode, s))
       else:
-        check(lib.ddg_attention_live(qkv_i, a16, n // L, L, self.n_heads, self.head_dim,
+        check(lib.ddg_attention_live(qkv_i, att, n // L, L, self.n_heads, self.head_dim,
                                      1 if self.causal else 0, bcode, n_live, s))
-      gemm(a16, h, ptr(self.w_out[i]), h, x, h, h, h, _lib.EPI_GATE_RESIDUAL,
-           bcode, gate=mb + 2 * h * 2 if ada else 0, gate_stride=mod_stride)
+      ln2 = (ptr(self.ln2[i]), mb + 3 * h * 2 if ada else 0, mb + 4 * h * 2 if ada else 0,
+             mod_stride, bcode)
+      gemm(att, h, ptr(self.w_out[i]), h, x, h, h, h, _lib.EPI_GATE_RESIDUAL,
+           bcode, gate=mb + 2 * h * 2 if ada else 0, gate_stride=mod_stride,
+           ln=ln2 if fuse else None)
       if saved is not None:
         saved[-1][1] = ws['x'][:n].clone()
-      ln(x, 0, 0, ptr(self.ln2[i]), mb + 3 * h * 2 if ada else 0,
-         mb + 4 * h * 2 if ada else 0, mod_stride, bcode, a16)
+      if not fuse:
+        ln(x, 0, 0, *ln2[:4], bcode, a16)
       gemm(a16, h, ptr(self.w_fc1[i]), h, h4, 4 * h, 4 * h, h,
            _lib.EPI_BIAS_GELU, bcode, bias=ptr(self.b_fc1[i]))
+      # the norm after this block's last residual add: norm1 of the next block, or the
+      # final layer's norm (bf16, models/dit.py:463); the classifier pools the raw rows
+      nxt = None
+      if fuse and i + 1 < nb:
+        mn = mb + 6 * h * 2
+        nxt = (ptr(self.ln1[i + 1]), mn if ada else 0, mn + h * 2 if ada else 0, mod_stride,
+               bcode)
+      elif fuse and not self.classifier:
+        nxt = (ptr(self.ln_f), mf if fin else 0, mf + h * 2 if fin else 0, 2 * h, hcode)
       gemm(h4, 4 * h, ptr(self.w_fc2[i]), 4 * h, x, h, h, 4 * h,
            _lib.EPI_GATE_RESIDUAL, bcode, bias=ptr(self.b_fc2[i]),
-           gate=mb + 5 * h * 2 if ada else 0, gate_stride=mod_stride)
+           gate=mb + 5 * h * 2 if ada else 0, gate_stride=mod_stride, ln=nxt)
     if self.classifier:
       return
-    fin = self.use_adaln and self.final_adaln
-    mf = ptr(ws['mod_fin']) + mod0 * 2 * h * 2
-    ln(x, 0, 0, ptr(self.ln_f), mf if fin else 0, mf + h * 2 if fin else 0, 2 * h,
-       hcode, a16)
+    if not fuse:
+      ln(x, 0, 0, ptr(self.ln_f), mf if fin else 0, mf + h * 2 if fin else 0, 2 * h,
+         hcode, a16)
     st, st_ld = 0, 0
     if stats_out is not None:    # (chunks, rows_total, 2): this segment starts at row r0
       st, st_ld = ptr(stats_out) + r0 * 8, stats_out.shape[1]
@@ -494,7 +524,8 @@ class DIT:
                                   stream_ptr()))
     return out
 
-  def first_order_term(self, indices, sigma, target, round_bf16=True, finalize=True):
+  def first_order_term(self, indices, sigma, target, round_bf16=True, finalize=True,
+                       out=None, live=None):
     """First-order D-CBG classifier term (diffusion.py:1532-1548): one forward
     and the backward of log p(target | x) w.r.t. the one-hot input, then
     `grad - grad[xt] + log p(target | xt)` -> (n, L, V) fp32.  The forward is
@@ -506,7 +537,11 @@ class DIT:
     are the same for every vocabulary entry of a row, and a row-constant shift of
     the classifier term cancels in the softmax of `log q + gamma * term`
     (diffusion.py:1612-1617), i.e. it changes neither q_xs nor the ids -- the
-    sampling loop skips that extra pass over (n, L, V)."""
+    sampling loop skips that extra pass over (n, L, V).
+
+    `out`: preallocated (n * L, pad4(V)) fp32 buffer for the term (the captured step loop);
+    `live`: device int32 scalar -- when it reads 0 the term buffer keeps its previous contents
+    (the whole-batch `sampling.use_cache` rule of the captured loop)."""
     assert self.classifier
     n, L = indices.shape
     h, nb, V, M = self.hidden, self.n_blocks, self.vocab_size, n * L
@@ -533,12 +568,13 @@ class DIT:
     a16, pre = ptr(ws['a16']), ptr(ws['h4'])
 
     def gemm(a, lda, w, ldw, out, ld_out, N, K, epi=_lib.EPI_STORE, bias=0,
-             accumulate=0):
+             accumulate=0, live_seqs=0):
       ga = _lib.GemmArgs(
         a=a, w=w, out=out, bias=bias, gate=0, rope_cos=ptr(cos), rope_sin=ptr(sin),
         lda=lda, ldw=ldw, ld_out=ld_out, gate_stride=0, rows_per_mod=rpm, M=M, N=N,
         K=K, dtype=bcode, epilogue=epi, seq_len=L, head_dim=self.head_dim,
-        rope_cols=0, stats=0, stats_ld=0, stats_mask_col=-1, accumulate=accumulate)
+        rope_cols=0, stats=0, stats_ld=0, stats_mask_col=-1, accumulate=accumulate,
+        live_seqs=live_seqs)
       check(lib.ddg_gemm(ga, s))
 
     for i in reversed(range(nb)):
@@ -576,9 +612,10 @@ class DIT:
     check(lib.ddg_split16(ptr(g), ptr(g_hi), ptr(g_lo), M * h, bcode, s))
     g_cat = torch.cat([g_hi, g_lo, g_hi], dim=1)
     ldv = _pad_to(V, 4)
-    term = torch.empty(M, ldv, dtype=torch.float32, device=dev)
+    term = out if out is not None else torch.empty(M, ldv, dtype=torch.float32, device=dev)
+    assert term.shape == (M, ldv) and term.is_contiguous()
     gemm(ptr(g_cat), 3 * h, ptr(self.emb_cat), 3 * h, ptr(term), ldv, V, 3 * h,
-         epi=_lib.EPI_ACCUM_F32)
+         epi=_lib.EPI_ACCUM_F32, live_seqs=ptr(live))
     if finalize:
       check(lib.ddg_cbg_first_order(
         ptr(term), ldv, ptr(ids), ptr(lp), self.num_classes, int(target), L, V, M,

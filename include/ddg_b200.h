@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DDG_ABI_VERSION 4
+#define DDG_ABI_VERSION 5
 #define DDG_API __attribute__((visibility("default")))
 
 typedef void* ddg_stream_t; /* cudaStream_t */
@@ -302,10 +302,35 @@ typedef struct ddg_gemm_args {
    *            their `stats`) are written at output sequence out_seq_map[s].  */
   const int32_t* live_seqs;
   const int32_t* out_seq_map;
+  /* ABI v5, GATE_RESIDUAL only, optional (ln_weight != NULL): the LayerNorm + adaLN
+   * modulate that follows every residual add of a DiT block (models/dit.py:312-321,
+   * 256-259: `modulate(norm(x), shift, scale)`) fused into this launch, so the
+   * updated fp32 rows are normalised while they are still on chip instead of being
+   * read back from HBM by ddg_ln_modulate:
+   *   ln_out[m, :] = round_ln_dtype(((x_new[m] - mean) * rstd) * ln_weight
+   *                                  [* ln_scale[m / rows_per_mod] + ln_shift[...]])
+   * with x_new the row this launch has just written to `out` (same values, same
+   * operation order as ddg_ln_modulate; mean / variance are combined from per-128-
+   * column partials, so rstd may differ from the stand-alone kernel in the last ulp).
+   * Needs N % 128 == 0, N <= 1024, ld_out == N, rows_per_mod % 32 == 0.
+   * ln_work: device scratch of ddg_gemm_ln_work_bytes(M, N) bytes, 256-byte aligned,
+   * ZERO before its first use; launches leave its counters zero again, so one
+   * buffer serves every launch of a stream (not concurrent launches).           */
+  const float* ln_weight;  /* (N,) fp32                                        */
+  const void* ln_shift;    /* `ln_dtype` rows, ln_mod_stride apart, or NULL    */
+  const void* ln_scale;    /* 1 + scale rows, same layout (NULL with ln_shift) */
+  void* ln_out;            /* (M, N) `ln_dtype`, dense                         */
+  void* ln_work;
+  int64_t ln_mod_stride;
+  int32_t ln_dtype;        /* DDG_F16 | DDG_BF16                               */
+  int32_t reserved1;
 } ddg_gemm_args;
 
 /* tcgen05 / TMEM / TMA GEMM: out = epilogue(a @ w^T). */
 DDG_API int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream);
+
+/* Bytes of `ln_work` scratch a fused-LayerNorm ddg_gemm over up to M rows needs. */
+DDG_API int64_t ddg_gemm_ln_work_bytes(int32_t M, int32_t N);
 
 /* Softmax attention over whole sequences (models/dit.py:303-307):
  * qkv (B*L, 3*H*D) 16-bit with column order (three, head, dim)

@@ -98,7 +98,8 @@ def test_step_api_ids_follow_own_logits(name):
 
 @pytest.mark.parametrize('name', ['udlm_null', 'mdlm_null', 'udlm_cfg_g2',
                                   'mdlm_cfg_g2', 'udlm_cfg_g0', 'udlm_cfg_g1',
-                                  'udlm_T1000', 'bert_udlm_cfg_g2'])
+                                  'udlm_T1000', 'bert_udlm_cfg_g2', 'udlm_cbg',
+                                  'udlm_cbg_approx', 'mdlm_cbg', 'mdlm_cbg_approx'])
 def test_graph_loop_equals_eager_loop(name):
   """sample() through the captured CUDA graph == the same steps launched
   eagerly through the per-step API (same Philox key), and repeated sample()
