@@ -297,6 +297,8 @@ def build_model(wl, batch, device, seed, steps=None):
     model.race_group = int(os.environ['DDG_RACE_GROUP'])
   if os.environ.get('DDG_FUSE_LN'):                # LayerNorm A/B knob (0 = separate launches)
     model.backbone.fuse_ln = os.environ['DDG_FUSE_LN'] != '0'
+    if model.classifier_model is not None:
+      model.classifier_model.classifier_model.fuse_ln = model.backbone.fuse_ln
   return model, cfg
 
 

@@ -78,8 +78,9 @@ struct GemmParams {
   const void* ln_shift; // rows of `ln_dtype` (stride ln_mod_stride, row = m / rows_per_mod) or null
   const void* ln_scale; // 1 + scale, same layout
   void* ln_out;         // (M, N) `ln_dtype`
-  float2* ln_part;      // (M, N / 128) per-row partial (mean, M2) of each 128-column run
-  int* ln_cnt;          // one arrival counter per 128-row block, zero between launches
+  uint8_t* ln_work;     // per 128-row block: [counter word, padded to 64 B][128 x N / 128 partial words of 8 B]
+                        // -- a layout that does not depend on M, so launches over different row counts
+                        // can share one buffer
   int64_t ln_mod_stride;
   int ln_dtype;
 };
@@ -716,7 +717,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           __syncwarp();
           // the block's counter word, read before this warp publishes anything: no owner can have
           // departed yet, so it is (parity << 8) exactly (used after pass 1: latency hidden)
-          int* cnt = p.ln_cnt + (mb * 2 + (int)cta_rank);
+          uint8_t* blk = p.ln_work + (int64_t)(mb * 2 + (int)cta_rank) * (64 + BM * nvalid * 8);
+          int* cnt = reinterpret_cast<int*>(blk);
+          uint64_t* part = reinterpret_cast<uint64_t*>(blk + 64) + (int64_t)row_in_tile * nvalid;   // this row's words
           const int epoch_word = ld_relaxed_gpu(cnt);
           // ---- pass 1
           float s1 = 0.f, s2 = 0.f, c0 = 0.f;
@@ -785,7 +788,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const float m2_i = fmaxf(s2 - s1 * s1 * (1.f / 128.f), 0.f);
             const uint64_t word = (uint64_t)__float_as_uint(mean_i) |
                                   ((uint64_t)((__float_as_uint(m2_i) & 0x7fffffffu) | (tagbit << 31)) << 32);
-            st_relaxed_gpu_b64(p.ln_part + (int64_t)m * nvalid + (nb * 2 + chalf), word);
+            st_relaxed_gpu_b64(part + (nb * 2 + chalf), word);
           }
           // ---- x_new -> fp32 residual stream while the other owners' words travel
           float* xrow = reinterpret_cast<float*>(p.out) + (int64_t)(mw + r4) * p.ld_out + c8 * 4;
@@ -808,7 +811,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           float mean, rstd;
           {
             float2 pt[8];
-            const uint64_t* slots = reinterpret_cast<const uint64_t*>(p.ln_part + (int64_t)m * nvalid);
+            const uint64_t* slots = part;
             const long long t0 = clock64();
             bool all;
             do {
@@ -1287,8 +1290,9 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
 
 extern "C" int64_t ddg_gemm_ln_work_bytes(int32_t M, int32_t N) {
   if (M < 0 || N <= 0) return 0;
+  // per 128-row block: a 64-byte counter slot + 128 rows x ceil(N / 128) words of 8 bytes
   const int64_t n_blocks = 2 * (((int64_t)M + 2 * ddg::BM - 1) / (2 * ddg::BM));
-  return (n_blocks * 4 + 255) / 256 * 256 + n_blocks * ddg::BM * ((N + 127) / 128) * 8;
+  return n_blocks * (64 + (int64_t)ddg::BM * ((N + 127) / 128) * 8);
 }
 
 extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
@@ -1347,7 +1351,7 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
   // 131072 rows) is written with an evict-first policy and its operands are loaded evict-last:
   // without this the write-allocate stream kept evicting W (47 MB) and ncu showed 4.4 GB of DRAM
   // reads per launch against 0.25 GB algorithmic (profiles/r01_traffic.json)
-  p.ln_w = nullptr; p.ln_shift = p.ln_scale = nullptr; p.ln_out = nullptr; p.ln_part = nullptr; p.ln_cnt = nullptr;
+  p.ln_w = nullptr; p.ln_shift = p.ln_scale = nullptr; p.ln_out = nullptr; p.ln_work = nullptr;
   p.ln_mod_stride = 0; p.ln_dtype = 0;
   if (a.ln_weight) {
     // fused LayerNorm + modulate of the updated residual rows (see the epilogue)
@@ -1369,11 +1373,7 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
                   reinterpret_cast<uintptr_t>(a.ln_scale) % 16 == 0, DDG_ERR_INVALID, "gemm: ln_shift / ln_scale layout");
     p.ln_w = a.ln_weight; p.ln_shift = a.ln_shift; p.ln_scale = a.ln_scale; p.ln_out = a.ln_out;
     p.ln_mod_stride = a.ln_mod_stride; p.ln_dtype = a.ln_dtype;
-    // ln_work = [one int32 counter per 128-row block, padded to 256 B][(M, N / 128) float2 partials]
-    const int64_t n_blocks = 2 * (((int64_t)a.M + 2 * BM - 1) / (2 * BM));
-    p.ln_cnt = reinterpret_cast<int*>(a.ln_work);
-    p.ln_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(a.ln_work) + (n_blocks * 4 + 255) / 256 * 256);
-    // (rows are padded to whole 128-row blocks: every owner publishes all rows of its slab)
+    p.ln_work = reinterpret_cast<uint8_t*>(a.ln_work);
   }
   p.stream_out = (a.epilogue == DDG_EPI_STORE && (int64_t)a.M * a.N * 2 >= ((int64_t)256 << 20)) ? 1 : 0;
   if (a.stats) {

@@ -314,8 +314,10 @@ typedef struct ddg_gemm_args {
    * column partials, so rstd may differ from the stand-alone kernel in the last ulp).
    * Needs N % 128 == 0, N <= 1024, ld_out == N, rows_per_mod % 32 == 0.
    * ln_work: device scratch of ddg_gemm_ln_work_bytes(M, N) bytes, 256-byte aligned,
-   * ZERO before its first use; launches leave its counters zero again, so one
-   * buffer serves every launch of a stream (not concurrent launches).           */
+   * ZERO before its first use.  Its layout depends on N only (per 128-row block: a
+   * counter word and the block's per-row partials), and every launch leaves it
+   * ready for the next one, so one buffer sized for the largest M serves every
+   * launch with the same N on a stream (not concurrent launches).              */
   const float* ln_weight;  /* (N,) fp32                                        */
   const void* ln_shift;    /* `ln_dtype` rows, ln_mod_stride apart, or NULL    */
   const void* ln_scale;    /* 1 + scale rows, same layout (NULL with ln_shift) */

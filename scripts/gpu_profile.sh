@@ -22,7 +22,7 @@ ncu --set full --clock-control none --import-source on -k regex:'sample_fused_ke
 echo "sampler rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:'attention_kernel|attention_tc_kernel' -s 12 -c 1 -f -o gpurun_out/${TAG}_attn $CMD > gpurun_out/ncu_attn.log 2>&1
 echo "attn rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'ln_modulate_kernel|ln_modulate_stream_kernel' -s 26 -c 1 -f -o gpurun_out/${TAG}_ln $CMD > gpurun_out/ncu_ln.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'ln_modulate_kernel|ln_modulate_stream_kernel' -s 1 -c 1 -f -o gpurun_out/${TAG}_ln $CMD > gpurun_out/ncu_ln.log 2>&1
 echo "ln rc=$?"
 rm -f gpurun_out/${TAG}_ncu_full_summary.csv
 for f in gemm sampler attn ln; do python scripts/ncu_summary.py gpurun_out/${TAG}_$f.ncu-rep gpurun_out/${TAG}_ncu_full_summary.csv; done

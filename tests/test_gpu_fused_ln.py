@@ -69,6 +69,8 @@ CASES = [
   (9000, 768, 3072, 128, torch.float16, torch.bfloat16, True, True, True),       # last fc2 -> final norm
   (2048, 1024, 512, 64, torch.bfloat16, torch.bfloat16, True, True, True),
   (40000, 768, 768, 1 << 40, torch.float16, torch.float16, True, True, True),    # > one wave of tiles
+  (20000, 512, 512, 1280, torch.bfloat16, torch.bfloat16, True, True, False),    # two N tiles per row block
+  (163840, 512, 2048, 40960, torch.bfloat16, torch.bfloat16, True, True, True),  # exact-CBG classifier chunk
 ]
 
 
@@ -98,16 +100,23 @@ def test_fused_layernorm_epilogue_matches_separate_launches(M, N, K, rpm, dt, ln
   ref = torch.empty(M, N, dtype=ln_dt, device=DEV)
   _ln(x_ref, M, lw, sh, sc, mod.stride(0), rpm, ln_dt, ref)
 
-  for rep in range(2):     # the second launch finds the counters the first one left behind
+  for rep in range(3):     # later launches find the counters / parities the earlier ones left behind
     x = x0.clone()
     out = torch.full((M, N), float('nan'), dtype=ln_dt, device=DEV)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     _residual_gemm(a, w, x, bias, gate, gate_tab.stride(0), rpm,
                    ln=(lw, sh, sc, mod.stride(0), ln_dt, out), work=work)
+    e1.record()
     torch.cuda.synchronize()
+    # a wait that only ends by its safety time-out (0.15 s) means a broken exchange
+    assert e0.elapsed_time(e1) < 60.0, f'launch took {e0.elapsed_time(e1):.1f} ms'
     assert torch.equal(x, x_ref), 'residual rows differ from the unfused GEMM'
-    n_blocks = 2 * ((M + 255) // 256)
-    # counter word = (epoch parity << 8) | departures: every owner has left again
-    assert int((work[:n_blocks * 4].view(torch.int32) & 255).max()) == 0, 'counters not reset'
+    # scratch layout: per 128-row block a 64-byte counter slot + 128 x N/128 words; the counter
+    # word is (epoch parity << 8) | departures: every owner has left again
+    stride = 64 + 128 * (N // 128) * 8
+    words = work.view(-1, stride)[:, :4].contiguous().view(torch.int32)
+    assert int((words & 255).max()) == 0, 'counters not reset'
     assert not torch.isnan(out.float()).any()
     frac, worst = _ulp_report(out, ref, ln_dt)
     assert worst <= 1.01 and frac < 5e-3, (frac, worst)
@@ -118,6 +127,35 @@ def test_fused_layernorm_epilogue_matches_separate_launches(M, N, K, rpm, dt, ln
     y = y * sc.float()[idx] + sh.float()[idx]
   rtol, atol = (4e-3, 2e-3) if ln_dt == torch.float16 else (2e-2, 1.5e-2)
   torch.testing.assert_close(out.float(), y.to(ln_dt).float(), rtol=rtol, atol=atol)
+
+
+def test_fused_layernorm_launches_over_different_row_counts_share_the_scratch():
+  """Exact D-CBG runs the classifier over chunks of different sizes with one workspace: the
+  scratch layout must not depend on M (a launch over fewer rows then one over all of them)."""
+  M, N, K = 20000, 768, 768
+  g = torch.Generator().manual_seed(11)
+  a = torch.randn(M, K, generator=g).half().to(DEV)
+  w = (torch.randn(N, K, generator=g) * 0.05).half().to(DEV)
+  lw = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV)
+  x0 = torch.randn(M, N, generator=g).to(DEV)
+  work = _work(M, N)
+  x_ref = x0.clone()
+  _residual_gemm(a, w, x_ref, None, None, 0, 1 << 40)
+  ref = torch.empty(M, N, dtype=torch.float16, device=DEV)
+  _ln(x_ref, M, lw, None, None, 0, 1 << 40, torch.float16, ref)
+  for rows in (M, 5120, M, 256, 7777, M):
+    x = x0.clone()
+    out = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _residual_gemm(a, w, x, None, None, 0, 1 << 40, ln=(lw, None, None, 0, torch.float16, out),
+                   work=work, M=rows)
+    e1.record()
+    torch.cuda.synchronize()
+    assert e0.elapsed_time(e1) < 60.0, f'{rows} rows: launch took {e0.elapsed_time(e1):.1f} ms'
+    assert torch.equal(x[:rows], x_ref[:rows]) and torch.equal(x[rows:], x0[rows:])
+    frac, worst = _ulp_report(out[:rows], ref[:rows], torch.float16)
+    assert worst <= 1.01 and frac < 5e-3, (rows, frac, worst)
 
 
 def test_fused_layernorm_over_dynamic_batch():
