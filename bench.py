@@ -456,6 +456,7 @@ def kernel_breakdown(model, cfg, loop):
            'ddg_sample_step': 'sample_step', 'ddg_cond_embed': 'cond', 'ddg_adaln': 'cond',
            'ddg_step_advance': 'cond', 'ddg_seq_compact': 'cond'}
   records = []
+  fused_ln = set()     # GEMM families whose launches also do the following LayerNorm + modulate
   orig = {n: getattr(lib, n) for n in names}
   h = cfg.model.hidden_size
 
@@ -469,6 +470,8 @@ def kernel_breakdown(model, cfg, loop):
         g = g._obj if hasattr(g, '_obj') else g
         label = {(3 * h, h): 'gemm_qkv', (h, h): 'gemm_attn_out', (4 * h, h): 'gemm_fc1',
                  (h, 4 * h): 'gemm_fc2'}.get((g.N, g.K), 'gemm_vocab')
+        if g.ln_weight:
+          fused_ln.add(label)
       e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       e0.record()
       rc = fn(*a)
@@ -489,6 +492,8 @@ def kernel_breakdown(model, cfg, loop):
     d = out.setdefault(label, {'ms': 0.0, 'launches': 0})
     d['ms'] += e0.elapsed_time(e1)
     d['launches'] += 1
+  for label in fused_ln:
+    out[label]['fused_ln'] = True
   return out
 
 
@@ -647,6 +652,12 @@ def run_gpu_arm(args, rank, world, local_rank):
   gemm_launches = sum(kb[k]['launches'] for k in gemm_keys)
   gemm_total_flops = sum(gemm_flops.values())
   kernels = {}
+  h_ = cfg.model.hidden_size
+  rows = n_fwd * B * L
+  g_k = {'gemm_attn_out': h_, 'gemm_fc2': 4 * h_}
+  pure = [k for k in gemm_keys if not kb[k].get('fused_ln')]
+  pure_tf = (sum(gemm_flops[k[5:]] for k in pure) / (sum(kb[k]['ms'] for k in pure) * 1e-3) / 1e12
+             if pure else None)
   for k, d in sorted(kb.items(), key=lambda kv: -kv[1]['ms']):
     ent = {'ms_per_step': round(d['ms'], 4), 'launches': d['launches'],
            'share': round(d['ms'] / step_kernel_ms, 4)}
@@ -654,9 +665,15 @@ def run_gpu_arm(args, rank, world, local_rank):
       fl = gemm_flops[k[5:]]
       ent['tflops'] = round(fl / (d['ms'] * 1e-3) / 1e12, 1)
       ent['frac_of_sustained_peak'] = round(ent['tflops'] / pk['tf_sustained'], 4)
+      if d.get('fused_ln'):
+        # the launch also normalises the rows it has just updated (the next LayerNorm + modulate):
+        # against HBM it moves A + x in/out + the 16-bit norm output
+        byts = rows * (g_k[k] * 2 + h_ * 4 * 2 + h_ * 2) * d['launches']
+        ent['fused'] = 'LayerNorm + adaLN modulate of the updated residual rows (was a separate launch)'
+        ent['hbm_gbs'] = round(byts / (d['ms'] * 1e-3) / 1e9, 1)
+        ent['frac_of_hbm_peak'] = round(ent['hbm_gbs'] / pk['hbm'], 4)
     kernels[k] = ent
-  rows = B * L
-  samp_bytes = rows * (2 * V * 2 + 16)
+  samp_bytes = B * L * (2 * V * 2 + 16)
   samp_ms = kb['sample_step']['ms']
   samp_gbs = samp_bytes / (samp_ms * 1e-3) / 1e9
   samp_alone = sampler_alone_ms(model, loop)
@@ -683,7 +700,14 @@ def run_gpu_arm(args, rank, world, local_rank):
       'flops_per_launch': gemm_total_flops / gemm_launches,
       'ms_per_launch': gemm_ms / gemm_launches,
       'peak_source': f"{pk['src']} sustained bf16 (kernel timed inside a long step)",
-      'share_of_step': round(gemm_ms / step_kernel_ms, 4)},
+      'share_of_step': round(gemm_ms / step_kernel_ms, 4),
+      'note': ('GEMM FLOPs over the time of ALL GEMM launches of a step; the 24 residual GEMMs '
+               '(attn-out, fc2) also do the following LayerNorm + modulate in their epilogue '
+               '(24 of the 25 norms of a step), so their time is not GEMM time alone'
+               if any(kb[k].get('fused_ln') for k in gemm_keys) else None),
+      'gemms_without_fused_layernorm': (
+        {'kernels': pure, 'achieved': round(pure_tf, 1),
+         'frac': round(pure_tf / pk['tf_sustained'], 4)} if pure_tf else None)},
     'roofline_sampler': {
       'kernel': 'sample_group_kernel (fused sampler, hierarchical race)', 'bound': 'hbm',
       'achieved': round(samp_gbs, 1), 'peak': pk['hbm'], 'unit': 'GB/s',
