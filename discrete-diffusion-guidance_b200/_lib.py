@@ -69,7 +69,7 @@ class GemmArgs(C.Structure):
     ('live_seqs', C.c_void_p), ('out_seq_map', C.c_void_p),      # ABI v4
     ('ln_weight', C.c_void_p), ('ln_shift', C.c_void_p), ('ln_scale', C.c_void_p),   # ABI v5
     ('ln_out', C.c_void_p), ('ln_work', C.c_void_p), ('ln_mod_stride', C.c_int64),
-    ('ln_dtype', C.c_int32), ('reserved1', C.c_int32)]
+    ('ln_dtype', C.c_int32), ('reserved1', C.c_int32), ('residual', C.c_void_p)]
 
 
 def _load():

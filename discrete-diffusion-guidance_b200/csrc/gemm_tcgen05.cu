@@ -78,6 +78,7 @@ struct GemmParams {
   const void* ln_shift; // rows of `ln_dtype` (stride ln_mod_stride, row = m / rows_per_mod) or null
   const void* ln_scale; // 1 + scale, same layout
   void* ln_out;         // (M, N) `ln_dtype`
+  const float* residual; // GATE_RESIDUAL: rows the delta is added to (null: `out` itself, in place)
   uint8_t* ln_work;     // per 128-row block: [counter word, padded to 64 B][128 x N / 128 partial words of 8 B]
                         // -- a layout that does not depend on M, so launches over different row counts
                         // can share one buffer
@@ -638,7 +639,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const bool cols_ok = n0 < p.N;
       float4 xn[8];                             // x of the next 32 columns (lanes along the rows)
       auto ln_prefetch_x = [&](int nc) {
-        const float* xb = reinterpret_cast<const float*>(p.out) + (int64_t)(mw + r4) * p.ld_out + nc + c8 * 4;
+        const float* xb = (p.residual ? p.residual : reinterpret_cast<const float*>(p.out)) +
+                          (int64_t)(mw + r4) * p.ld_out + nc + c8 * 4;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           xn[i] = (mw + 4 * i + r4 < M) ? *reinterpret_cast<const float4*>(xb + (int64_t)(4 * i) * p.ld_out)
@@ -650,7 +652,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (cols_ok) {
           ln_prefetch_x(n0);
           if (mw + lane < M) {
-            const float* xb = reinterpret_cast<const float*>(p.out) + (int64_t)(mw + lane) * p.ld_out + n0;
+            const float* xb = (p.residual ? p.residual : reinterpret_cast<const float*>(p.out)) +
+                              (int64_t)(mw + lane) * p.ld_out + n0;
 #pragma unroll
             for (int k = 1; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + k * 32));
           }
@@ -942,6 +945,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         __syncwarp();
         float* xslab = reinterpret_cast<float*>(p.out) + (int64_t)mw * p.ld_out + cchunk * 4;
+        // the rows the delta is added to: `out` itself (in place) or a separate residual input
+        const float* xin = (!PLAIN && p.residual) ? p.residual + (int64_t)mw * p.ld_out + cchunk * 4 : xslab;
         float4 xn[2][4];                         // x of the next 32 columns
         auto prefetch_x = [&](int nc) {
 #pragma unroll
@@ -950,7 +955,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             for (int i = 0; i < 4; ++i) {
               const int row = 8 * i + crow;
               const bool ok = (mw + row < M) && (nc + h * 16 + cchunk * 4 < p.N) && (!PLAIN || p.accumulate);
-              xn[h][i] = ok ? *reinterpret_cast<const float4*>(xslab + (int64_t)row * p.ld_out + nc + h * 16)
+              xn[h][i] = ok ? *reinterpret_cast<const float4*>(xin + (int64_t)row * p.ld_out + nc + h * 16)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
@@ -1352,6 +1357,12 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
   // without this the write-allocate stream kept evicting W (47 MB) and ncu showed 4.4 GB of DRAM
   // reads per launch against 0.25 GB algorithmic (profiles/r01_traffic.json)
   p.ln_w = nullptr; p.ln_shift = p.ln_scale = nullptr; p.ln_out = nullptr; p.ln_work = nullptr;
+  p.residual = nullptr;
+  if (a.residual) {
+    DDG_REQUIRE(a.epilogue == DDG_EPI_GATE_RESIDUAL && reinterpret_cast<uintptr_t>(a.residual) % 16 == 0,
+                DDG_ERR_INVALID, "gemm: residual needs the GATE_RESIDUAL epilogue and 16-byte alignment");
+    p.residual = a.residual;
+  }
   p.ln_mod_stride = 0; p.ln_dtype = 0;
   if (a.ln_weight) {
     // fused LayerNorm + modulate of the updated residual rows (see the epilogue)

@@ -285,11 +285,11 @@ class DIT:
         raise ValueError('micro-batch straddles a conditioning group')
       if (r0 % period) + n > period and not (r0 == 0 and n == M):
         raise ValueError('micro-batch straddles the id period')
-      self._run_segment(ws, ids, r0, n, L, period, mod0, rpm_arg, mod_stride,
-                        cos, sin, logits_out, bcode, hcode, s, stats_out,
-                        stats_mask_col, save_for_backward, live)
-    if self.classifier:
-      return ws['x'][:M]
+      x_final = self._run_segment(ws, ids, r0, n, L, period, mod0, rpm_arg, mod_stride,
+                                  cos, sin, logits_out, bcode, hcode, s, stats_out,
+                                  stats_mask_col, save_for_backward, live)
+    if self.classifier:    # with save_for_backward (one segment) the rows live in their own buffer
+      return x_final if save_for_backward is not None else ws['x'][:M]
     return logits_out
 
   def _run_segment(self, ws, ids, r0, n, L, period, mod0, rpm, mod_stride, cos,
@@ -302,8 +302,16 @@ class DIT:
     # The LayerNorm + modulate that follows a residual add runs inside that GEMM's epilogue
     # (rows normalised while still on chip); only the first norm (embedding gather) is a launch
     # of its own.  The attention output then needs its own buffer: a16 is the norm's output.
-    fuse = (self.fuse_ln and saved is None and h % 128 == 0 and h <= 1024
-            and rpm % 32 == 0)
+    fuse = self.fuse_ln and h % 128 == 0 and h <= 1024 and rpm % 32 == 0
+    # save_for_backward: every residual add writes a NEW buffer (out = residual + delta), so
+    # each block's input rows (xs[2 i]) and mid rows (xs[2 i + 1]) stay available to the
+    # backward without copying the residual stream
+    xs = None
+    if saved is not None:
+      xs = torch.empty(2 * nb + 1, n, h, dtype=torch.float32, device=self.device)
+
+    def xp(k):
+      return xs[k].data_ptr() if xs is not None else x
     att = ptr(ws['att']) if fuse else a16
     ln_work = ptr(ws['ln_work'])
     modb = ptr(ws['mod_blk']) + mod0 * mod_stride * 2
@@ -311,14 +319,14 @@ class DIT:
     ada = self.use_adaln
 
     def gemm(a, lda, w, ldw, out, ld_out, N, K, epi, dtype, bias=0, gate=0,
-             gate_stride=0, stats=0, stats_ld=0, out_map=0, ln=None):
+             gate_stride=0, stats=0, stats_ld=0, out_map=0, ln=None, residual=0):
       g = _lib.GemmArgs(
         a=a, w=w, out=out, bias=bias, gate=gate, rope_cos=ptr(cos),
         rope_sin=ptr(sin), lda=lda, ldw=ldw, ld_out=ld_out,
         gate_stride=gate_stride, rows_per_mod=rpm, M=n, N=N, K=K, dtype=dtype,
         epilogue=epi, seq_len=L, head_dim=self.head_dim, rope_cols=2 * h,
         stats=stats, stats_ld=stats_ld, stats_mask_col=stats_mask_col,
-        live_seqs=n_live, out_seq_map=out_map)
+        live_seqs=n_live, out_seq_map=out_map, residual=residual)
       if ln is not None:   # (weight, shift, 1 + scale, stride between conditioning rows, dtype)
         g.ln_weight, g.ln_shift, g.ln_scale, g.ln_mod_stride, g.ln_dtype = ln
         g.ln_out, g.ln_work = a16, ln_work
@@ -338,13 +346,13 @@ class DIT:
     for i in range(nb):
       mb = modb + i * 6 * h * 2
       if i == 0 or not fuse:
-        ln(x, ids_p if i == 0 else 0, ptr(self.embedding), ptr(self.ln1[i]),
+        ln(xp(2 * i), ids_p if i == 0 else 0, ptr(self.embedding), ptr(self.ln1[i]),
            mb if ada else 0, mb + h * 2 if ada else 0, mod_stride, bcode, a16)
       qkv_i = qkv
-      if saved is not None:   # block input (set by the gather above for i == 0); the rotated
-        # QKV of this block is written straight into its own buffer (kept for the backward)
+      if saved is not None:   # the rotated QKV of this block is written straight into its own
+        # buffer (kept for the backward)
         keep = torch.empty(n, 3 * h, dtype=self.block_dtype, device=self.device)
-        saved.append([ws['x'][:n].clone(), None, keep])
+        saved.append([xs[2 * i], xs[2 * i + 1], keep])
         qkv_i = ptr(keep)
       gemm(a16, h, ptr(self.w_qkv[i]), h, qkv_i, 3 * h, 3 * h, h,
            _lib.EPI_QKV_ROPE, bcode)
@@ -356,13 +364,11 @@ class DIT:
                                      1 if self.causal else 0, bcode, n_live, s))
       ln2 = (ptr(self.ln2[i]), mb + 3 * h * 2 if ada else 0, mb + 4 * h * 2 if ada else 0,
              mod_stride, bcode)
-      gemm(att, h, ptr(self.w_out[i]), h, x, h, h, h, _lib.EPI_GATE_RESIDUAL,
+      gemm(att, h, ptr(self.w_out[i]), h, xp(2 * i + 1), h, h, h, _lib.EPI_GATE_RESIDUAL,
            bcode, gate=mb + 2 * h * 2 if ada else 0, gate_stride=mod_stride,
-           ln=ln2 if fuse else None)
-      if saved is not None:
-        saved[-1][1] = ws['x'][:n].clone()
+           ln=ln2 if fuse else None, residual=xp(2 * i) if xs is not None else 0)
       if not fuse:
-        ln(x, 0, 0, *ln2[:4], bcode, a16)
+        ln(xp(2 * i + 1), 0, 0, *ln2[:4], bcode, a16)
       gemm(a16, h, ptr(self.w_fc1[i]), h, h4, 4 * h, 4 * h, h,
            _lib.EPI_BIAS_GELU, bcode, bias=ptr(self.b_fc1[i]))
       # the norm after this block's last residual add: norm1 of the next block, or the
@@ -374,13 +380,14 @@ class DIT:
                bcode)
       elif fuse and not self.classifier:
         nxt = (ptr(self.ln_f), mf if fin else 0, mf + h * 2 if fin else 0, 2 * h, hcode)
-      gemm(h4, 4 * h, ptr(self.w_fc2[i]), 4 * h, x, h, h, 4 * h,
+      gemm(h4, 4 * h, ptr(self.w_fc2[i]), 4 * h, xp(2 * i + 2), h, h, 4 * h,
            _lib.EPI_GATE_RESIDUAL, bcode, bias=ptr(self.b_fc2[i]),
-           gate=mb + 5 * h * 2 if ada else 0, gate_stride=mod_stride, ln=nxt)
+           gate=mb + 5 * h * 2 if ada else 0, gate_stride=mod_stride, ln=nxt,
+           residual=xp(2 * i + 1) if xs is not None else 0)
     if self.classifier:
-      return
+      return xs[2 * nb] if xs is not None else None
     if not fuse:
-      ln(x, 0, 0, ptr(self.ln_f), mf if fin else 0, mf + h * 2 if fin else 0, 2 * h,
+      ln(xp(2 * nb), 0, 0, ptr(self.ln_f), mf if fin else 0, mf + h * 2 if fin else 0, 2 * h,
          hcode, a16)
     st, st_ld = 0, 0
     if stats_out is not None:    # (chunks, rows_total, 2): this segment starts at row r0

@@ -326,6 +326,11 @@ typedef struct ddg_gemm_args {
   int64_t ln_mod_stride;
   int32_t ln_dtype;        /* DDG_F16 | DDG_BF16                               */
   int32_t reserved1;
+  /* GATE_RESIDUAL only, optional: (M, ld_out) fp32 rows the delta is added to,
+   * out = residual + round(gate * round(acc [+ bias])); NULL = `out` in place.
+   * Lets a caller keep every block's input rows (the first-order D-CBG backward
+   * needs them) without copying the residual stream.                          */
+  const float* residual;
 } ddg_gemm_args;
 
 /* tcgen05 / TMEM / TMA GEMM: out = epilogue(a @ w^T). */

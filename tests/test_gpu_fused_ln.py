@@ -23,7 +23,7 @@ def _work(M, N):
 
 
 def _residual_gemm(a, w, x, bias, gate, gate_stride, rpm, *, ln=None, work=None, M=None,
-                   live=None, seq_len=1):
+                   live=None, seq_len=1, residual=None):
   """x += round(gate * round(a @ w^T + bias)); ln = (weight, shift, scale, stride, dtype, out)."""
   Mfull, K = a.shape
   N = w.shape[0]
@@ -32,7 +32,7 @@ def _residual_gemm(a, w, x, bias, gate, gate_stride, rpm, *, ln=None, work=None,
     rope_cos=0, rope_sin=0, lda=a.stride(0), ldw=w.stride(0), ld_out=x.stride(0),
     gate_stride=gate_stride, rows_per_mod=rpm, M=M or Mfull, N=N, K=K,
     dtype=_lib.DTYPE_CODE[a.dtype], epilogue=_lib.EPI_GATE_RESIDUAL, seq_len=seq_len,
-    head_dim=64, rope_cols=0, live_seqs=_lib.ptr(live))
+    head_dim=64, rope_cols=0, live_seqs=_lib.ptr(live), residual=_lib.ptr(residual))
   if ln is not None:
     lw, sh, sc, stride, dt, out = ln
     g.ln_weight, g.ln_shift, g.ln_scale = lw.data_ptr(), _lib.ptr(sh), _lib.ptr(sc)
@@ -156,6 +156,34 @@ def test_fused_layernorm_launches_over_different_row_counts_share_the_scratch():
     assert torch.equal(x[:rows], x_ref[:rows]) and torch.equal(x[rows:], x0[rows:])
     frac, worst = _ulp_report(out[:rows], ref[:rows], torch.float16)
     assert worst <= 1.01 and frac < 5e-3, (rows, frac, worst)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_residual_input_buffer_is_left_untouched(fused):
+  """out = residual + delta with a separate residual input (the first-order D-CBG forward keeps
+  every block's input rows this way): same values as the in-place form, input unchanged."""
+  M, N, K = 3000, 768, 768
+  g = torch.Generator().manual_seed(21)
+  a = torch.randn(M, K, generator=g).to(torch.bfloat16).to(DEV)
+  w = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(DEV)
+  gate = torch.randn(1, N, generator=g).to(torch.bfloat16).to(DEV)
+  lw = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV)
+  x0 = torch.randn(M, N, generator=g).to(DEV)
+  work = _work(M, N)
+
+  def ln_args(out):
+    return (lw, None, None, 0, torch.bfloat16, out) if fused else None
+  x_inplace = x0.clone()
+  y_inplace = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+  _residual_gemm(a, w, x_inplace, None, gate, N, 1 << 40, ln=ln_args(y_inplace), work=work)
+  res = x0.clone()
+  x_out = torch.full((M, N), float('nan'), device=DEV)
+  y_out = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+  _residual_gemm(a, w, x_out, None, gate, N, 1 << 40, ln=ln_args(y_out), work=work, residual=res)
+  torch.cuda.synchronize()
+  assert torch.equal(res, x0)
+  assert torch.equal(x_out, x_inplace)
+  assert torch.equal(y_out.view(torch.int16), y_inplace.view(torch.int16))
 
 
 def test_fused_layernorm_over_dynamic_batch():
