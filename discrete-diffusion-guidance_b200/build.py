@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libddg_b200.so')
 STAMP = os.path.join(HERE, 'csrc', '.build_stamp')
-SOURCES = ['capi.cu', 'sample_step.cu', 'sample_fused.cu', 'sample_group.cu', 'sample_aux.cu', 'dit_ops.cu', 'dit_bwd.cu', 'attention_bwd.cu',
+SOURCES = ['capi.cu', 'sample_step.cu', 'sample_fused.cu', 'sample_group.cu', 'sample_aux.cu', 'dit_ops.cu', 'dit_bwd.cu', 'attention_bwd.cu', 'attention_bwd_tc.cu',
            'gemm_tcgen05.cu', 'attention.cu']
 NVCC_FLAGS = [
   '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',

@@ -7,10 +7,15 @@
 // and the final first-order term.  Everything is a first version aimed at
 // correctness (fp32 CUDA-core math on 16-bit tensors); the classifier is small
 // next to the denoiser.
+#include <cstdlib>
+
 #include "ddg_common.cuh"
 
 namespace ddg {
 // attention_bwd.cu: tensor-core path for seq_len <= 128
+bool attention_bwd_tc_supported(int batch, int seq_len, int causal);   // attention_bwd_tc.cu
+int launch_attention_bwd_tc(const void* qkv, const void* g_o, const void* rope_cos, const void* rope_sin, int batch,
+                            int seq_len, int n_heads, int dtype, void* g_qkv, cudaStream_t s);
 int launch_attention_bwd_mma(const void* qkv, const void* g_o, const void* rope_cos, const void* rope_sin, int batch,
                              int seq_len, int n_heads, int causal, int dtype, void* g_qkv, cudaStream_t s);
 namespace {
@@ -537,6 +542,17 @@ extern "C" int ddg_attention_backward(const void* qkv, const void* g_out, const 
               "attention_backward: head_dim must be 64 and seq_len <= 256");
   if (batch == 0) return DDG_OK;
   DDG_REQUIRE(dtype == DDG_F16 || dtype == DDG_BF16, DDG_ERR_INVALID, "attention_backward: dtype must be f16 or bf16");
+  // tcgen05 / tensor-memory kernel for the non-causal 32 / 64 / 128-token shapes (DDG_ATT_BWD=mma
+  // keeps the mma.sync kernel: A/B measurements and the parity test of the two kernels)
+  static const bool force_mma = [] {
+    const char* e = getenv("DDG_ATT_BWD");
+    return e != nullptr && e[0] == 'm';
+  }();
+  if (!force_mma && attention_bwd_tc_supported(batch, seq_len, causal) &&
+      reinterpret_cast<uintptr_t>(qkv) % 16 == 0 && reinterpret_cast<uintptr_t>(g_out) % 16 == 0 &&
+      reinterpret_cast<uintptr_t>(g_qkv) % 16 == 0)
+    return launch_attention_bwd_tc(qkv, g_out, rope_cos, rope_sin, batch, seq_len, n_heads, dtype, g_qkv,
+                                   reinterpret_cast<cudaStream_t>(stream));
   if (seq_len <= 128)
     return launch_attention_bwd_mma(qkv, g_out, rope_cos, rope_sin, batch, seq_len, n_heads, causal, dtype, g_qkv,
                                     reinterpret_cast<cudaStream_t>(stream));

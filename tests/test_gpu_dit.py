@@ -189,16 +189,7 @@ def test_attention_tensor_memory_kernel_packed_sequences(L, B, dtype):
   assert bool((out[B * L:] == 9.0).all()), 'rows past the last sequence must stay untouched'
 
 
-@pytest.mark.parametrize('L', [16, 24, 32, 48, 64, 100, 128, 160])
-@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize('causal', [False, True])
-def test_attention_backward(L, dtype, causal):
-  """d loss / d (QKV GEMM output) from d loss / d (attention output), through
-  softmax(q k^T / 8) v and the rotary (models/dit.py:284-307), against fp64
-  autograd on the same post-rotary q, k, v.  L <= 128 runs the tensor-core
-  kernel (P, dS rounded to the 16-bit type like the reference's flash backward),
-  longer sequences the CUDA-core one; ragged L covers the padded tiles."""
-  B, H = 3, 2
+def _attention_backward_case(L, dtype, causal, B, H):
   g = torch.Generator().manual_seed(100 + L)
   qkv = (torch.randn(B, L, 3, H, 64, generator=g) * 1.2).to(dtype)     # post-rotary q, k and v
   go = torch.randn(B, L, H, 64, generator=g).to(dtype)
@@ -232,6 +223,28 @@ def test_attention_backward(L, dtype, causal):
     assert err <= tol * scale, (nm, err, scale)
     rms = ((got[:, :, i] - ref[:, :, i]).pow(2).mean() / ref[:, :, i].pow(2).mean()).sqrt().item()
     assert rms <= tol / 3, (nm, rms)
+
+
+@pytest.mark.parametrize('L', [16, 24, 32, 48, 64, 100, 128, 160])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('causal', [False, True])
+def test_attention_backward(L, dtype, causal):
+  """d loss / d (QKV GEMM output) from d loss / d (attention output), through
+  softmax(q k^T / 8) v and the rotary (models/dit.py:284-307), against fp64
+  autograd on the same post-rotary q, k, v.  Non-causal L in {32, 64, 128} with at
+  least 128 token rows runs the tcgen05 kernel, other L <= 128 the mma.sync one (P,
+  dS rounded to the 16-bit type like the reference's flash backward), longer
+  sequences the CUDA-core one; ragged L covers the padded tiles."""
+  _attention_backward_case(L, dtype, causal, B=3, H=2)
+
+
+@pytest.mark.parametrize('L,B', [(32, 4), (32, 9), (32, 700), (64, 5), (64, 320), (128, 1), (128, 7), (128, 170)])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+def test_attention_backward_tensor_memory_kernel(L, B, dtype):
+  """The tcgen05 backward (attention_bwd_tc.cu) on packed short sequences, ragged last
+  items (B * L not a multiple of 128) and several items per CTA (more items than SMs:
+  both shared-memory buffer sets and both barrier phases are re-used)."""
+  _attention_backward_case(L, dtype, False, B=B, H=3)
 
 
 @pytest.mark.parametrize('hidden', [128, 512, 768, 1024])
