@@ -486,6 +486,20 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
   nb = n_first + (r - mb * width);
 }
 
+// Developer build only (-DDDG_LN_PROF, scripts/ln_epilogue_prof.py): clock64() per phase of the
+// fused-LayerNorm epilogue, summed by one warp of one CTA.
+#ifdef DDG_LN_PROF
+__device__ unsigned long long g_ln_prof[8];
+#define DDG_LNP(i)                                                                   \
+  if (e == 0 && lane == 0 && blockIdx.x == 2) {                                      \
+    const long long lnp_now = clock64();                                             \
+    atomicAdd(&g_ln_prof[i], (unsigned long long)(lnp_now - lnp_t));                 \
+    lnp_t = lnp_now;                                                                 \
+  }
+#else
+#define DDG_LNP(i)
+#endif
+
 // ------------------------------------------------------------------ kernel
 template <typename T, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -579,7 +593,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+#ifdef DDG_LN_PROF
+        const long long mma_t0 = clock64();
+#endif
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+#ifdef DDG_LN_PROF
+        if (blockIdx.x == 2) atomicAdd(&g_ln_prof[6], (unsigned long long)(clock64() - mma_t0));
+#endif
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -623,6 +643,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tmem_empty_leader0 = map_to_cta(smem_u32(&tmem_empty[0]), 0);
+#ifdef DDG_LN_PROF
+    long long lnp_t = clock64();
+#endif
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int mb, nb;
       tile_coords(tile, num_m, num_n, n_panel, mb, nb);
@@ -661,6 +684,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      DDG_LNP(0)
       const uint32_t taddr =
         tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chalf * (BN / 2));
 
@@ -783,6 +807,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             tmem_st32(taddr + (uint32_t)(g * 32), xr);
           }
           tmem_st_wait();
+          DDG_LNP(1)
           // ---- publish this warp's partial of each of its 32 rows (also rows past M)
           const int target = 4 * nvalid;
           const uint32_t tagbit = (((uint32_t)epoch_word >> 8) + 1u) & 1u;
@@ -810,6 +835,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             __syncwarp();
           }
+          DDG_LNP(2)
           // ---- the row's partials from all owners, combined in slot order (same result everywhere)
           float mean, rstd;
           {
@@ -845,6 +871,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             rstd = rsqrtf(m2 / (float)p.N + 1e-5f);
           }
           __syncwarp();
+          DDG_LNP(3)
           // departure (relaxed): the last owner to leave flips the block's parity for the next launch
           int departed = 0;
           if (lane == 0) departed = atomicAdd(cnt, 1);
@@ -906,6 +933,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           if (p.ln_dtype == DDG_BF16) pass2(__nv_bfloat16());
           else pass2(__half());
           if (lane == 0 && (departed & 255) == target - 1) atomicExch(cnt, (int)(tagbit << 8));
+          DDG_LNP(4)
+#ifdef DDG_LN_PROF
+          if (e == 0 && lane == 0 && blockIdx.x == 2) atomicAdd(&g_ln_prof[5], 1ull);
+#endif
         }
       } else if (EPI == DDG_EPI_GATE_RESIDUAL || EPI == DDG_EPI_ACCUM_F32) {
         // ACCUM_F32: out = (accumulate ? out : 0) + acc, no rounding (fp32 dgrad outputs).
@@ -1292,6 +1323,19 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
 
 }  // namespace
 }  // namespace ddg
+
+#ifdef DDG_LN_PROF
+// out[0..4]: cycles waiting for the accumulator / pass 1 / publish + residual store / polling the
+// neighbours' partials / pass 2; [5] tiles; [6] cycles the MMA thread waited for a free accumulator
+extern "C" __attribute__((visibility("default"))) int ddg_debug_ln_prof(unsigned long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, ddg::g_ln_prof, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(ddg::g_ln_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 extern "C" int64_t ddg_gemm_ln_work_bytes(int32_t M, int32_t N) {
   if (M < 0 || N <= 0) return 0;

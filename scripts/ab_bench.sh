@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 A=$1; B=$2; R=${3:-2}
 for r in $(seq 1 $R); do
   for L in $A $B; do
-    DDG_B200_LIB=$PWD/$L timeout -s KILL 600 python -W ignore bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/ab.log 2>&1
+    DDG_B200_LIB=$PWD/$L timeout -s KILL 600 python -W ignore bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-configs > gpurun_out/ab.log 2>&1
     python - <<PY
 import json
 d = json.loads(open('gpurun_out/ab.log').read().strip().splitlines()[-1])
