@@ -69,7 +69,12 @@ class Workload:
   metric: str = ''
 
 
-_UDLM = ('parameterization=d3pm', 'diffusion=uniform', 'time_conditioning=True', 'T=0')
+# sampling.use_cache=False: with time conditioning the reference's whole-batch cache rule
+# (diffusion.py:1371-1374, honoured by the step loop) skips the forward of a step when no token of
+# the batch changed in the previous one -- late in a 1000-step run, and the earlier the smaller the
+# per-GPU batch.  The timed loop must not contain skipped work, so every bench step is a full step.
+_UDLM = ('parameterization=d3pm', 'diffusion=uniform', 'time_conditioning=True', 'T=0',
+         'sampling.use_cache=False')
 _CFG = ('guidance=cfg', f'guidance.gamma={GAMMA}', 'guidance.condition=1',
         '+data.num_classes=2')
 _CBG = ('classifier_backbone=dit', 'guidance=cbg', 'guidance.gamma=2.0',
@@ -275,6 +280,9 @@ def workload_config(wl, batch, world):
     'cache': 'per-step working set (>= 1 GB of logits per 64 sequences) exceeds the 126 MB L2; '
              'no flush needed',
   }
+  if 'sampling.use_cache=False' in wl.overrides:
+    cfg['use_cache'] = ('off in the timed loop: every step runs the full forward (the reference\'s '
+                        'whole-batch cache rule would skip steps in which no token changed)')
   return cfg
 
 
