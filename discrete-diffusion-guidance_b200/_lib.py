@@ -13,13 +13,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DDG_B200_LIB: developer knob for same-box A/B runs of two builds of the library
 LIB_PATH = os.environ.get('DDG_B200_LIB') or os.path.join(_HERE, 'libddg_b200.so')
 
-ABI_VERSION = 5   # DDG_ABI_VERSION of include/ddg_b200.h these bindings were written for
+ABI_VERSION = 6   # DDG_ABI_VERSION of include/ddg_b200.h these bindings were written for
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 F32, F16, BF16 = 0, 1, 2
 ABSORBING, UNIFORM, AR = 0, 1, 2
 GUIDE_NONE, GUIDE_CFG, GUIDE_CBG = 0, 1, 2
 SELECT_RACE, SELECT_ARGMAX, SELECT_GUMBEL = 0, 1, 2
-EPI_STORE, EPI_QKV_ROPE, EPI_BIAS_GELU, EPI_GATE_RESIDUAL, EPI_ACCUM_F32 = 0, 1, 2, 3, 4
+EPI_STORE, EPI_QKV_ROPE, EPI_BIAS_GELU, EPI_GATE_RESIDUAL, EPI_ACCUM_F32, EPI_GELU_BWD = 0, 1, 2, 3, 4, 5
 
 DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
@@ -69,7 +69,8 @@ class GemmArgs(C.Structure):
     ('live_seqs', C.c_void_p), ('out_seq_map', C.c_void_p),      # ABI v4
     ('ln_weight', C.c_void_p), ('ln_shift', C.c_void_p), ('ln_scale', C.c_void_p),   # ABI v5
     ('ln_out', C.c_void_p), ('ln_work', C.c_void_p), ('ln_mod_stride', C.c_int64),
-    ('ln_dtype', C.c_int32), ('reserved1', C.c_int32), ('residual', C.c_void_p)]
+    ('ln_dtype', C.c_int32), ('reserved1', C.c_int32), ('residual', C.c_void_p),
+    ('aux', C.c_void_p), ('ld_aux', C.c_int64)]                                      # ABI v6
 
 
 def _load():

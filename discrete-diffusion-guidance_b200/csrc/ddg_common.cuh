@@ -56,6 +56,28 @@ template <> struct Cvt<__nv_bfloat16> {
   static __device__ __forceinline__ float round(float v) { return bf16_round(v); }
 };
 
+// d/dv [0.5 v (1 + tanh u)],  u = sqrt(2/pi) (v + 0.044715 v^3)   (models/dit.py:243, the backward of
+// nn.GELU(approximate='tanh')).  With s = sigmoid(2u) = (1 + tanh u) / 2:  1 - tanh^2 u = 4 s (1 - s), so
+//   gelu'(v) = s (1 + v (2 du) (1 - s)),   2 du = 2 k0 (1 + 3 k1 v^2),   s = 1 / (1 + 2^(-2 u log2 e))
+// -- one ex2 and one rcp (MUFU; abs. error ~1e-7, far below the 16-bit rounding of the product this
+// feeds), exact limits for large |v|.  Every step is an explicitly rounded operation so that the
+// packed f32x2 twin in the GEMM's GELU_BWD epilogue (gemm_tcgen05.cu) gives bit-identical results.
+constexpr float kGeluK0 = 0.7978845608028654f;                 // sqrt(2 / pi)
+constexpr float kGeluK1 = 0.044715f;
+constexpr float kGeluExp = -2.f * 0.7978845608028654f * 1.4426950408889634f;   // -2 k0 log2 e
+constexpr float kGeluD0 = 2.f * 0.7978845608028654f;           // 2 k0
+constexpr float kGeluD1 = 6.f * 0.7978845608028654f * 0.044715f;   // 6 k0 k1
+__device__ __forceinline__ float gelu_tanh_grad(float v) {
+  const float v2 = __fmul_rn(v, v);
+  const float arg = __fmul_rn(v, __fmaf_rn(kGeluK1, v2, 1.f));
+  float e, s;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(arg, kGeluExp)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(__fadd_rn(e, 1.f)));
+  const float w = __fmul_rn(v, __fmaf_rn(kGeluD1, v2, kGeluD0));
+  const float oms = __fmaf_rn(s, -1.f, 1.f);
+  return __fmul_rn(s, __fmaf_rn(w, oms, 1.f));
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -147,13 +147,7 @@ gate_mul_vec_kernel(const float* __restrict__ g, const T* __restrict__ gate, int
 }
 
 // ---------------------------------------------------------------- GELU'(pre) * g
-// d/dv [0.5 v (1 + tanh u)],  u = sqrt(2/pi) (v + 0.044715 v^3)   (models/dit.py:243)
-__device__ __forceinline__ float gelu_tanh_grad(float v) {
-  const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
-  const float t = tanhf(u);
-  const float du = 0.7978845608028654f * (1.f + 3.f * 0.044715f * v * v);
-  return 0.5f * (1.f + t) + 0.5f * v * (1.f - t * t) * du;
-}
+// gelu_tanh_grad(): ddg_common.cuh (shared with the GEMM's GELU_BWD epilogue)
 template <typename T>
 __global__ void gelu_bwd_kernel(const T* __restrict__ g_h, const T* __restrict__ pre, T* __restrict__ out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -171,7 +165,7 @@ gelu_bwd_vec_kernel(const T* __restrict__ g_h, const T* __restrict__ pre, T* __r
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 gg = unpack2<T>(a[k]), pp = unpack2<T>(b[k]);
-      o[k] = pack2<T>(gg.x * gelu_tanh_grad(pp.x), gg.y * gelu_tanh_grad(pp.y));
+      o[k] = pack2<T>(__fmul_rn(gg.x, gelu_tanh_grad(pp.x)), __fmul_rn(gg.y, gelu_tanh_grad(pp.y)));
     }
     reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }

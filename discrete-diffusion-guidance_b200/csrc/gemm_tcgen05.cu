@@ -79,6 +79,8 @@ struct GemmParams {
   const void* ln_scale; // 1 + scale, same layout
   void* ln_out;         // (M, N) `ln_dtype`
   const float* residual; // GATE_RESIDUAL: rows the delta is added to (null: `out` itself, in place)
+  void* aux;            // BIAS_GELU: optional pre-activation output; GELU_BWD: pre-activation input (16-bit, ld_aux)
+  int64_t ld_aux;
   uint8_t* ln_work;     // per 128-row block: [counter word, padded to 64 B][128 x N / 128 partial words of 8 B]
                         // -- a layout that does not depend on M, so launches over different row counts
                         // can share one buffer
@@ -452,6 +454,24 @@ __device__ __forceinline__ float2 gelu_tanh2(float2 v) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(d.x));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(d.y));
   return mul2(v, make_float2(rx, ry));
+}
+
+// gelu_tanh_grad() of ddg_common.cuh for a column pair, operation for operation in packed f32x2
+__device__ __forceinline__ float2 gelu_tanh_grad2(float2 v) {
+  const float2 one = make_float2(1.f, 1.f);
+  const float2 v2 = mul2(v, v);
+  const float2 arg = mul2(v, fma2(make_float2(kGeluK1, kGeluK1), v2, one));
+  const float2 z = mul2(arg, make_float2(kGeluExp, kGeluExp));
+  float ex, ey, sx, sy;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(z.y));
+  const float2 d = add2(make_float2(ex, ey), one);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sx) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sy) : "f"(d.y));
+  const float2 s = make_float2(sx, sy);
+  const float2 w = mul2(v, fma2(make_float2(kGeluD1, kGeluD1), v2, make_float2(kGeluD0, kGeluD0)));
+  const float2 oms = fma2(s, make_float2(-1.f, -1.f), one);
+  return mul2(s, fma2(w, oms, one));
 }
 
 __device__ __forceinline__ float gelu_tanh(float v) {
@@ -1078,8 +1098,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         __syncwarp();
         const uint64_t pol_out = policy_evict_first();
-        // stages 32 columns (16 packed words per row) through the slab and stores them coalesced
-        auto store_chunk = [&](const uint32_t (&w)[16], int nc) {
+        // the 16-bit side tensor (ABI v6): rows mw.., this lane's 8-column chunk
+        T* aslab = p.aux ? reinterpret_cast<T*>(p.aux) + (int64_t)mw * p.ld_aux + cchunk * 8 : nullptr;
+        // BIAS_GELU with a side output: the pre-activation round(acc + bias) of 32 columns -> aux
+        auto store_aux_chunk = [&](const uint32_t (&w)[16], int nc) {
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) st_shared_v4(stg_wr + q * 16, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
@@ -1089,6 +1111,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int i = 0; i < 4; ++i) {
             const int row = 8 * i + crow;
             const uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
+            if (mw + row < M && col + 8 <= p.N) *reinterpret_cast<uint4*>(aslab + (int64_t)row * p.ld_aux + nc) = y;
+          }
+        };
+        // stages 32 columns (16 packed words per row) through the slab and stores them coalesced
+        // GELU_BWD: the pre-activations of this lane's four 16-byte pieces of a 32-column chunk; issued
+        // before the chunk's accumulator load so that they travel during it and the transpose
+        uint4 pre[4];
+        auto load_pre = [&](int nc) {
+          const int col = nc + cchunk * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = 8 * i + crow;
+            pre[i] = (mw + row < M && col + 8 <= p.N)
+                       ? __ldcs(reinterpret_cast<const uint4*>(aslab + (int64_t)row * p.ld_aux + nc))
+                       : make_uint4(0, 0, 0, 0);
+          }
+        };
+        auto store_chunk = [&](const uint32_t (&w)[16], int nc) {
+          const int col = nc + cchunk * 8;
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) st_shared_v4(stg_wr + q * 16, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = 8 * i + crow;
+            uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
+            if (EPI == DDG_EPI_GELU_BWD) {     // round(g * gelu'(pre)): ddg_gelu_backward's arithmetic
+              const uint32_t gw[4] = {y.x, y.y, y.z, y.w}, pw[4] = {pre[i].x, pre[i].y, pre[i].z, pre[i].w};
+              uint32_t o[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 r = mul2(H2<T>::unpack(gw[k]), gelu_tanh_grad2(H2<T>::unpack(pw[k])));
+                o[k] = H2<T>::pack(r.x, r.y);
+              }
+              y = make_uint4(o[0], o[1], o[2], o[3]);
+            }
             if (mw + row < M) {
               T* dst = oslab + (int64_t)row * p.ld_out + nc;
               if (col + 8 <= p.N) {
@@ -1175,6 +1234,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int c = 0; c < BN / 64; ++c) {
             const int nc = n0 + c * 32;
             if (nc >= p.N) break;                    // warp-uniform
+            if (EPI == DDG_EPI_GELU_BWD) load_pre(nc);
             uint32_t r[32];
             tmem_ld32_sync(taddr + (uint32_t)(c * 32), r);
             float2 v[16];
@@ -1185,6 +1245,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
             for (int i = 0; i < 16; ++i) w[i] = H2<T>::pack(v[i].x, v[i].y);
             if (EPI == DDG_EPI_BIAS_GELU) {
+              if (aslab) store_aux_chunk(w, nc);
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const float2 y = gelu_tanh2(H2<T>::unpack(w[i]));
@@ -1316,6 +1377,7 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
       if (p.ln_w) return launch_gemm<T, EPI_GATE_RESIDUAL_LN>(ta, tb, p, s);
       return launch_gemm<T, DDG_EPI_GATE_RESIDUAL>(ta, tb, p, s);
     case DDG_EPI_ACCUM_F32: return launch_gemm<T, DDG_EPI_ACCUM_F32>(ta, tb, p, s);
+    case DDG_EPI_GELU_BWD: return launch_gemm<T, DDG_EPI_GELU_BWD>(ta, tb, p, s);
   }
   set_error("gemm: bad epilogue %d", epi);
   return DDG_ERR_INVALID;
@@ -1429,6 +1491,15 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
     p.ln_w = a.ln_weight; p.ln_shift = a.ln_shift; p.ln_scale = a.ln_scale; p.ln_out = a.ln_out;
     p.ln_mod_stride = a.ln_mod_stride; p.ln_dtype = a.ln_dtype;
     p.ln_work = reinterpret_cast<uint8_t*>(a.ln_work);
+  }
+  p.aux = nullptr; p.ld_aux = 0;
+  if (a.aux || a.epilogue == DDG_EPI_GELU_BWD) {
+    DDG_REQUIRE(a.epilogue == DDG_EPI_BIAS_GELU || a.epilogue == DDG_EPI_GELU_BWD, DDG_ERR_INVALID,
+                "gemm: aux goes with the BIAS_GELU (output) and GELU_BWD (input) epilogues");
+    DDG_REQUIRE(a.aux && a.ld_aux >= a.N && a.ld_aux % 8 == 0 && a.N % 8 == 0 &&
+                reinterpret_cast<uintptr_t>(a.aux) % 16 == 0, DDG_ERR_INVALID,
+                "gemm: aux needs N %% 8 == 0, ld_aux >= N, ld_aux %% 8 == 0 and 16-byte alignment");
+    p.aux = a.aux; p.ld_aux = a.ld_aux;
   }
   p.stream_out = (a.epilogue == DDG_EPI_STORE && (int64_t)a.M * a.N * 2 >= ((int64_t)256 << 20)) ? 1 : 0;
   if (a.stats) {

@@ -319,14 +319,15 @@ class DIT:
     ada = self.use_adaln
 
     def gemm(a, lda, w, ldw, out, ld_out, N, K, epi, dtype, bias=0, gate=0,
-             gate_stride=0, stats=0, stats_ld=0, out_map=0, ln=None, residual=0):
+             gate_stride=0, stats=0, stats_ld=0, out_map=0, ln=None, residual=0, aux=0):
       g = _lib.GemmArgs(
         a=a, w=w, out=out, bias=bias, gate=gate, rope_cos=ptr(cos),
         rope_sin=ptr(sin), lda=lda, ldw=ldw, ld_out=ld_out,
         gate_stride=gate_stride, rows_per_mod=rpm, M=n, N=N, K=K, dtype=dtype,
         epilogue=epi, seq_len=L, head_dim=self.head_dim, rope_cols=2 * h,
         stats=stats, stats_ld=stats_ld, stats_mask_col=stats_mask_col,
-        live_seqs=n_live, out_seq_map=out_map, residual=residual)
+        live_seqs=n_live, out_seq_map=out_map, residual=residual, aux=aux,
+        ld_aux=N if aux else 0)
       if ln is not None:   # (weight, shift, 1 + scale, stride between conditioning rows, dtype)
         g.ln_weight, g.ln_shift, g.ln_scale, g.ln_mod_stride, g.ln_dtype = ln
         g.ln_out, g.ln_work = a16, ln_work
@@ -351,8 +352,11 @@ class DIT:
       qkv_i = qkv
       if saved is not None:   # the rotated QKV of this block is written straight into its own
         # buffer (kept for the backward)
+        # buffer, and so is the MLP's pre-activation (the fc1 GEMM's side output): the backward
+        # needs GELU'(pre) and would otherwise redo the norm and the fc1 GEMM
         keep = torch.empty(n, 3 * h, dtype=self.block_dtype, device=self.device)
-        saved.append([xs[2 * i], xs[2 * i + 1], keep])
+        pre = torch.empty(n, 4 * h, dtype=self.block_dtype, device=self.device)
+        saved.append([xs[2 * i], xs[2 * i + 1], keep, pre])
         qkv_i = ptr(keep)
       gemm(a16, h, ptr(self.w_qkv[i]), h, qkv_i, 3 * h, 3 * h, h,
            _lib.EPI_QKV_ROPE, bcode)
@@ -370,7 +374,8 @@ class DIT:
       if not fuse:
         ln(xp(2 * i + 1), 0, 0, *ln2[:4], bcode, a16)
       gemm(a16, h, ptr(self.w_fc1[i]), h, h4, 4 * h, 4 * h, h,
-           _lib.EPI_BIAS_GELU, bcode, bias=ptr(self.b_fc1[i]))
+           _lib.EPI_BIAS_GELU, bcode, bias=ptr(self.b_fc1[i]),
+           aux=ptr(saved[i][3]) if saved is not None else 0)
       # the norm after this block's last residual add: norm1 of the next block, or the
       # final layer's norm (bf16, models/dit.py:463); the classifier pools the raw rows
       nxt = None
@@ -572,31 +577,27 @@ class DIT:
     g_a = torch.empty(M, h, dtype=self.block_dtype, device=dev)
     g_h = torch.empty(M, 4 * h, dtype=self.block_dtype, device=dev)
     g_qkv = torch.empty(M, 3 * h, dtype=self.block_dtype, device=dev)
-    a16, pre = ptr(ws['a16']), ptr(ws['h4'])
 
     def gemm(a, lda, w, ldw, out, ld_out, N, K, epi=_lib.EPI_STORE, bias=0,
-             accumulate=0, live_seqs=0):
+             accumulate=0, live_seqs=0, aux=0):
       ga = _lib.GemmArgs(
         a=a, w=w, out=out, bias=bias, gate=0, rope_cos=ptr(cos), rope_sin=ptr(sin),
         lda=lda, ldw=ldw, ld_out=ld_out, gate_stride=0, rows_per_mod=rpm, M=M, N=N,
         K=K, dtype=bcode, epilogue=epi, seq_len=L, head_dim=self.head_dim,
         rope_cols=0, stats=0, stats_ld=0, stats_mask_col=-1, accumulate=accumulate,
-        live_seqs=live_seqs)
+        live_seqs=live_seqs, aux=aux, ld_aux=N if aux else 0)
       check(lib.ddg_gemm(ga, s))
 
     for i in reversed(range(nb)):
       mb = ptr(ws['mod_blk']) + i * 6 * h * 2
-      x_in, x_mid, qkv_i = saved[i]
-      # ---- MLP branch: x_out = x_mid + gate_mlp * fc2(gelu(fc1(mod(LN(x_mid)))))
+      x_in, x_mid, qkv_i, pre_i = saved[i]
+      # ---- MLP branch: x_out = x_mid + gate_mlp * fc2(gelu(fc1(mod(LN(x_mid))))).  The fc2
+      # input-gradient GEMM multiplies by GELU'(pre) in its epilogue (pre = the forward's fc1
+      # side output): no recomputed norm / fc1 GEMM and no elementwise pass over (M, 4h)
       check(lib.ddg_gate_mul(ptr(g), mb + 5 * h * 2 if ada else 0, mod_stride, rpm,
                              M, h, bcode, ptr(g16), s))
-      gemm(ptr(g16), h, ptr(self.w_fc2_t[i]), h, ptr(g_h), 4 * h, 4 * h, h)
-      check(lib.ddg_ln_modulate(
-        ptr(x_mid), M, h, 0, M, 0, ptr(self.ln2[i]), mb + 3 * h * 2 if ada else 0,
-        mb + 4 * h * 2 if ada else 0, mod_stride, rpm, bcode, a16, s))
-      gemm(a16, h, ptr(self.w_fc1[i]), h, pre, 4 * h, 4 * h, h,
-           bias=ptr(self.b_fc1[i]))
-      check(lib.ddg_gelu_backward(ptr(g_h), pre, ptr(g_h), M * 4 * h, bcode, s))
+      gemm(ptr(g16), h, ptr(self.w_fc2_t[i]), h, ptr(g_h), 4 * h, 4 * h, h,
+           epi=_lib.EPI_GELU_BWD, aux=ptr(pre_i))
       gemm(ptr(g_h), 4 * h, ptr(self.w_fc1_t[i]), 4 * h, ptr(g_a), h, h, 4 * h)
       check(lib.ddg_ln_modulate_backward(
         ptr(x_mid), ptr(g_a), M, h, ptr(self.ln2[i]), mb + 4 * h * 2 if ada else 0,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DDG_ABI_VERSION 5
+#define DDG_ABI_VERSION 6
 #define DDG_API __attribute__((visibility("default")))
 
 typedef void* ddg_stream_t; /* cudaStream_t */
@@ -261,8 +261,11 @@ enum ddg_epilogue {
   DDG_EPI_QKV_ROPE = 1,     /* round, then NeoX rotary on q,k heads 16-bit   */
   DDG_EPI_BIAS_GELU = 2,    /* round(gelu_tanh(round(acc + bias)))  16-bit   */
   DDG_EPI_GATE_RESIDUAL = 3, /* x += round(gate * round(acc [+ bias])) fp32  */
-  DDG_EPI_ACCUM_F32 = 4     /* out = (accumulate ? out : 0) + acc, fp32, no
+  DDG_EPI_ACCUM_F32 = 4,    /* out = (accumulate ? out : 0) + acc, fp32, no
                                rounding (classifier dgrad outputs)            */
+  DDG_EPI_GELU_BWD = 5      /* round(round(acc) * gelu_tanh'(aux))  16-bit:
+                               the fc2 input-gradient GEMM of the first-order
+                               D-CBG backward times GELU'(pre-activation)     */
 };
 
 typedef struct ddg_gemm_args {
@@ -331,6 +334,13 @@ typedef struct ddg_gemm_args {
    * Lets a caller keep every block's input rows (the first-order D-CBG backward
    * needs them) without copying the residual stream.                          */
   const float* residual;
+  /* ABI v6, optional 16-bit side tensor (M, ld_aux), `dtype`, 16-byte aligned rows:
+   *   BIAS_GELU  output: aux = round(acc + bias), the pre-activation the GELU is
+   *              applied to (models/dit.py:242-245) -- kept for the backward of
+   *              first-order D-CBG instead of recomputing the fc1 GEMM there;
+   *   GELU_BWD   input (required): the pre-activation saved by the forward.     */
+  void* aux;
+  int64_t ld_aux;
 } ddg_gemm_args;
 
 /* tcgen05 / TMEM / TMA GEMM: out = epilogue(a @ w^T). */

@@ -25,7 +25,7 @@ def test_header_symbols_are_exported():
   for n in names:
     assert hasattr(lib, n), f'{n} declared in ddg_b200.h but not exported'
   assert set(names) == set(_lib.EXPORTS)
-  assert lib.ddg_abi_version() == 5 == ddg_b200._lib.ABI_VERSION
+  assert lib.ddg_abi_version() == 6 == ddg_b200._lib.ABI_VERSION
 
 
 def test_struct_layouts_match_header():

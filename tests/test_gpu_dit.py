@@ -22,7 +22,7 @@ DEV = 'cuda'
 
 
 def _gemm(a, w, *, epi, out=None, bias=None, gate=None, rows_per_mod=1 << 40,
-          cos=None, sin=None, seq_len=1, ld_out=None):
+          cos=None, sin=None, seq_len=1, ld_out=None, aux=None):
   M, K = a.shape
   N = w.shape[0]
   dtype = a.dtype
@@ -41,7 +41,8 @@ def _gemm(a, w, *, epi, out=None, bias=None, gate=None, rows_per_mod=1 << 40,
     lda=a.stride(0), ldw=w.stride(0), ld_out=out.stride(0),
     gate_stride=gate.stride(0) if gate is not None else 0,
     rows_per_mod=rows_per_mod, M=M, N=N, K=K, dtype=_lib.DTYPE_CODE[dtype],
-    epilogue=epi, seq_len=seq_len, head_dim=64, rope_cols=(N // 3) * 2)
+    epilogue=epi, seq_len=seq_len, head_dim=64, rope_cols=(N // 3) * 2,
+    aux=_lib.ptr(aux), ld_aux=aux.stride(0) if aux is not None else 0)
   _lib.check(_lib.lib.ddg_gemm(g, _lib.stream_ptr()))
   torch.cuda.synchronize()
   return out
@@ -101,6 +102,48 @@ def test_gemm_bias_gelu(dtype):
   ref = torch.nn.functional.gelu(pre, approximate='tanh').to(dtype).float()
   rtol, atol = _tol(dtype)
   torch.testing.assert_close(out[:, :N].float(), ref, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('M,N,K', [(777, 3072, 768), (4096, 2048, 512), (130, 512, 128)])
+def test_gemm_gelu_side_output_and_fused_gelu_backward(dtype, M, N, K):
+  """ABI v6 `aux`: (i) BIAS_GELU also writes the pre-activation round(acc + bias) -- bit-equal
+  to the STORE epilogue of the same product, GELU output unchanged; (ii) GELU_BWD =
+  round(round(acc) * gelu'(aux)) -- bit-equal to STORE followed by ddg_gelu_backward (the two
+  launches it replaces in the first-order D-CBG backward), and close to autograd through
+  torch's tanh-GELU (models/dit.py:243)."""
+  g = torch.Generator().manual_seed(M + N)
+  a = (torch.randn(M, K, generator=g) * 0.7).to(dtype).to(DEV)
+  w = (torch.randn(N, K, generator=g) * 0.06).to(dtype).to(DEV)
+  bias = (torch.randn(N, generator=g) * 0.2).to(dtype).to(DEV)
+  pre_ref = _gemm(a, w, epi=_lib.EPI_STORE, bias=bias)
+  act_ref = _gemm(a, w, epi=_lib.EPI_BIAS_GELU, bias=bias)
+  pre = torch.full((M + 8, N), 7.0, dtype=dtype, device=DEV)          # guard rows behind the end
+  act = _gemm(a, w, epi=_lib.EPI_BIAS_GELU, bias=bias, aux=pre)
+  assert torch.equal(act, act_ref)
+  assert torch.equal(pre[:M], pre_ref[:, :N])
+  assert bool((pre[M:] == 7.0).all())
+  # (ii) the input-gradient GEMM: g_h = g @ w2^T (N2 = N outputs, K2 inputs), times gelu'(pre)
+  K2 = 256
+  gin = torch.randn(M, K2, generator=g).to(dtype).to(DEV)
+  w2 = (torch.randn(N, K2, generator=g) * 0.05).to(dtype).to(DEV)
+  gh = _gemm(gin, w2, epi=_lib.EPI_STORE)
+  two = torch.empty(M, N, dtype=dtype, device=DEV)
+  _lib.check(_lib.lib.ddg_gelu_backward(gh.data_ptr(), pre.data_ptr(), two.data_ptr(), M * N,
+                                        _lib.DTYPE_CODE[dtype], _lib.stream_ptr()))
+  fused = _gemm(gin, w2, epi=_lib.EPI_GELU_BWD, aux=pre)
+  torch.cuda.synchronize()
+  assert torch.equal(fused[:, :N], two)
+  x = pre[:M].float().requires_grad_(True)
+  torch.nn.functional.gelu(x, approximate='tanh').backward(gh[:, :N].float())
+  rtol, atol = _tol(dtype)
+  torch.testing.assert_close(fused[:, :N].float(), x.grad.to(dtype).float(), rtol=rtol, atol=atol)
+  # GELU_BWD without aux is an error, aux with another epilogue too
+  bad = _lib.GemmArgs(a=a.data_ptr(), w=w.data_ptr(), out=act.data_ptr(), lda=K, ldw=K, ld_out=N, M=M,
+                      N=N, K=K, dtype=_lib.DTYPE_CODE[dtype], epilogue=_lib.EPI_GELU_BWD)
+  assert _lib.lib.ddg_gemm(bad, _lib.stream_ptr()) != 0
+  bad.epilogue, bad.aux, bad.ld_aux = _lib.EPI_STORE, pre.data_ptr(), N
+  assert _lib.lib.ddg_gemm(bad, _lib.stream_ptr()) != 0
 
 
 @pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
