@@ -10,7 +10,8 @@
 // All transcendental work is in base 2 (ex2/lg2.approx), selection scores are
 //     s_j = log2 q~_j - log2 E_j,      E_j = 1e-10 - ln(U_j + 1e-10)
 // (the reference's p_j / E_j race in the log domain; common factors dropped).
-// Modes: UDLM posterior (null / D-CFG) and MDLM absorbing posterior (null).
+// Modes: UDLM posterior (null / D-CFG / D-CBG with the fp32 classifier term of
+// diffusion.py:1587-1621 read alongside the logits) and MDLM absorbing posterior (null).
 #include "ddg_common.cuh"
 
 namespace ddg {
@@ -20,7 +21,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kThreads = 256;
 
-enum FMode : int { F_UNI_NONE = 0, F_UNI_CFG = 1, F_ABS_NONE = 2 };
+enum FMode : int { F_UNI_NONE = 0, F_UNI_CFG = 1, F_ABS_NONE = 2, F_UNI_CBG = 3 };
 
 __device__ __forceinline__ float ex2a(float x) {
   float y;
@@ -59,6 +60,7 @@ struct FusedConst {
   float dA, c0;            // uniform: q~_j = dA x_j + c0 (+ zc at j = z)
   float zc_a, zc_b;
   float gam, omg;          // gamma, 1 - gamma
+  bool clf_round;          // D-CBG: gamma * clf is a bf16 product (exact classifier term on a GPU)
   float mask_score;        // absorbing: log2(r / (1 - r)) of the mask column
   int z, mask_index, V;
 };
@@ -66,6 +68,13 @@ struct FusedConst {
 // log2 of the unnormalised (guided) posterior at one column.  `extra` selects
 // the j == z (uniform) handling; the absorbing mask column is handled by the
 // caller.
+// D-CBG: gamma * classifier term in log2 units (diffusion.py:1607, 1612)
+__device__ __forceinline__ float clf2(const FusedConst& c, float cf) {
+  float gc = c.gam * cf;
+  if (c.clf_round) gc = bf16_round(gc);
+  return gc * kLog2e;
+}
+
 template <int MODE, bool ROUND>
 __device__ __forceinline__ float g2_one(const FusedConst& c, float la, float lb, bool is_z) {
   float lpa = la - c.Ka;
@@ -80,6 +89,7 @@ __device__ __forceinline__ float g2_one(const FusedConst& c, float la, float lb,
   if (is_z) na += c.zc_a;
   const float lqa = lg2a(na);
   if (MODE == F_UNI_NONE) return lqa;
+  if (MODE == F_UNI_CBG) return lqa + clf2(c, lb);      // lb carries the classifier term
   float lpb = lb - c.Kb;
   if (ROUND) lpb = bf16_round(lpb);
   float xb = ex2a(lpb * kLog2e);
@@ -120,10 +130,14 @@ sample_fused_kernel(const ddg_sample_step_args a) {
       MODE == F_UNI_CFG ? reinterpret_cast<const __nv_bfloat16*>(a.logits_b) + row * a.ld_b : nullptr;
     // first vectors in flight while warp 0 folds the partials
     const int jfirst = tid * 8;
+    // D-CBG: the row of the fp32 classifier term (16-byte aligned, padded to whole vectors of 8)
+    const float* pc = MODE == F_UNI_CBG ? a.clf + row * a.ld_clf : nullptr;
     uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+    uint4 rc0 = make_uint4(0, 0, 0, 0), rc1 = make_uint4(0, 0, 0, 0);
     if (jfirst < V) {
       ra = ldg_stream(pa + jfirst);
       if (MODE == F_UNI_CFG) rb = ldg_stream(pb + jfirst);
+      if (MODE == F_UNI_CBG) { rc0 = ldg_stream(pc + jfirst); rc1 = ldg_stream(pc + jfirst + 4); }
     }
     // ---- row normalisers from the GEMM partials (warps 0 and 1)
     if (warp < (MODE == F_UNI_CFG ? 2 : 1)) {
@@ -146,6 +160,7 @@ sample_fused_kernel(const ddg_sample_step_args a) {
     c.Kb = MODE == F_UNI_CFG ? s_k[1] : 0.f;
     c.z = z; c.mask_index = a.mask_index; c.V = V;
     c.gam = a.gamma; c.omg = 1.f - a.gamma;
+    c.clf_round = a.clf_round_bf16 != 0;
     const int64_t mc_off = (row / a.seq_len) * a.mc_seq_stride + (int64_t)step * a.mc_step_stride;
     const float mc_t = a.mc_t[mc_off], mc_s = a.mc_s[mc_off];
     int special;                                        // column needing the careful path
@@ -182,10 +197,17 @@ sample_fused_kernel(const ddg_sample_step_args a) {
       float va[8], vb[8], nl[8];
       unpack8(ra, va);
       if (MODE == F_UNI_CFG) unpack8(rb, vb);
+      if (MODE == F_UNI_CBG) {                          // vb = the classifier term of these 8 columns
+        vb[0] = __uint_as_float(rc0.x); vb[1] = __uint_as_float(rc0.y);
+        vb[2] = __uint_as_float(rc0.z); vb[3] = __uint_as_float(rc0.w);
+        vb[4] = __uint_as_float(rc1.x); vb[5] = __uint_as_float(rc1.y);
+        vb[6] = __uint_as_float(rc1.z); vb[7] = __uint_as_float(rc1.w);
+      }
       const int jn = j0 + kThreads * 8;                 // prefetch the next vectors
       if (jn < V) {
         ra = ldg_stream(pa + jn);
         if (MODE == F_UNI_CFG) rb = ldg_stream(pb + jn);
+        if (MODE == F_UNI_CBG) { rc0 = ldg_stream(pc + jn); rc1 = ldg_stream(pc + jn + 4); }
       }
       if (INJ) {
 #pragma unroll
@@ -224,6 +246,7 @@ sample_fused_kernel(const ddg_sample_step_args a) {
                   g0 = fmaf(c.gam, g0, c.omg * lg2a(fmaf(c.dA, y0, c.c0)));
                   g1 = fmaf(c.gam, g1, c.omg * lg2a(fmaf(c.dA, y1, c.c0)));
                 }
+                if (MODE == F_UNI_CBG) { g0 += clf2(c, vb[e]); g1 += clf2(c, vb[e + 1]); }
               }
             } else {
               const float ka2 = c.Ka * kLog2e;
@@ -239,6 +262,7 @@ sample_fused_kernel(const ddg_sample_step_args a) {
                 g0 = fmaf(c.gam, g0, c.omg * lg2a(fmaf(c.dA, ex2a(fmaf(vb[e], kLog2e, -kb2)), c.c0)));
                 g1 = fmaf(c.gam, g1, c.omg * lg2a(fmaf(c.dA, ex2a(fmaf(vb[e + 1], kLog2e, -kb2)), c.c0)));
               }
+              if (MODE == F_UNI_CBG) { g0 += clf2(c, vb[e]); g1 += clf2(c, vb[e + 1]); }
             }
             const float s0 = g0 + nl[e], s1 = g1 + nl[e + 1];
             if (s0 > best) { best = s0; bidx = j0 + e; }
@@ -256,7 +280,7 @@ sample_fused_kernel(const ddg_sample_step_args a) {
             if (j == a.mask_index) g = c.mask_score;
             else g = g2_one<MODE, ROUND>(c, va[e], 0.f, false);
           } else {
-            g = g2_one<MODE, ROUND>(c, va[e], MODE == F_UNI_CFG ? vb[e] : 0.f, j == z);
+            g = g2_one<MODE, ROUND>(c, va[e], MODE != F_UNI_NONE ? vb[e] : 0.f, j == z);
           }
           const float sc = g + nl[e];
           if (sc > best) { best = sc; bidx = j; }
@@ -313,7 +337,8 @@ int try_sample_fused(const ddg_sample_step_args& a, cudaStream_t s) {
     set_error("sample_step: race_group must be 0, 8 or 64 (got %d)", a.race_group);
     return DDG_ERR_INVALID;
   }
-  if (!a.stats_a || a.stats_chunks <= 0 || a.logits_dtype != DDG_BF16 || a.q_out || a.clf) return 0;
+  if (!a.stats_a || a.stats_chunks <= 0 || a.logits_dtype != DDG_BF16 || a.q_out) return 0;
+  if ((a.clf != nullptr) != (a.guidance == DDG_GUIDE_CBG)) return 0;
   if (a.select != DDG_SELECT_RACE || !a.fast_math || a.vocab < 2048) return 0;
   if (a.stats_chunks != (a.vocab + 127) / 128) return 0;
   const int64_t vpad = (a.vocab + 7) / 8 * 8;
@@ -328,8 +353,12 @@ int try_sample_fused(const ddg_sample_step_args& a, cudaStream_t s) {
     mode = F_UNI_CFG;
   } else if (a.diffusion == DDG_ABSORBING && a.guidance == DDG_GUIDE_NONE && a.subs && a.mask_logit)
     mode = F_ABS_NONE;   // stats must have been built with stats_mask_col = mask_index
-  else return 0;
-  if (a.race_group != 0 && !a.noise) {
+  else if (a.diffusion == DDG_UNIFORM && a.guidance == DDG_GUIDE_CBG && !a.mask_logit) {
+    // the fp32 classifier term is read as two 16-byte vectors per 8 columns: rows padded to whole vectors
+    if (reinterpret_cast<uintptr_t>(a.clf) % 16 != 0 || a.ld_clf % 4 != 0 || a.ld_clf < vpad) return 0;
+    mode = F_UNI_CBG;
+  } else return 0;
+  if (a.race_group != 0 && !a.noise && mode != F_UNI_CBG) {
     const int rcg = launch_sample_group(mode, a, s);   // hierarchical race (Philox only)
     return rcg ? rcg : 1;
   }
@@ -340,7 +369,9 @@ int try_sample_fused(const ddg_sample_step_args& a, cudaStream_t s) {
     case 2: rc = launch_inj<F_UNI_CFG, false>(a, s); break;
     case 3: rc = launch_inj<F_UNI_CFG, true>(a, s); break;
     case 4: rc = launch_inj<F_ABS_NONE, false>(a, s); break;
-    default: rc = launch_inj<F_ABS_NONE, true>(a, s); break;
+    case 5: rc = launch_inj<F_ABS_NONE, true>(a, s); break;
+    case 6: rc = launch_inj<F_UNI_CBG, false>(a, s); break;
+    default: rc = launch_inj<F_UNI_CBG, true>(a, s); break;
   }
   return rc ? rc : 1;
 }

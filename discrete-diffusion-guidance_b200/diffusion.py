@@ -773,7 +773,7 @@ class _GraphLoop:
       self.classifier = model.classifier_model
       self.condition = int(g.condition)
       self.use_approx = bool(g.get('use_approx', False))
-      ldv = (model.vocab_size + 3) // 4 * 4 if self.use_approx else model.vocab_size
+      ldv = (model.vocab_size + 7) // 8 * 8 if self.use_approx else model.vocab_size
       self.term = torch.empty(B * L, ldv, dtype=torch.float32, device=dev)
     self.tables = None
     self.graph = None

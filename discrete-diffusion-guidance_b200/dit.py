@@ -619,7 +619,7 @@ class DIT:
     g_hi = g_a
     check(lib.ddg_split16(ptr(g), ptr(g_hi), ptr(g_lo), M * h, bcode, s))
     g_cat = torch.cat([g_hi, g_lo, g_hi], dim=1)
-    ldv = _pad_to(V, 4)
+    ldv = _pad_to(V, 8)      # whole 8-column vectors per row: the single-pass sampler reads the term 2 x 16 B at a time
     term = out if out is not None else torch.empty(M, ldv, dtype=torch.float32, device=dev)
     assert term.shape == (M, ldv) and term.is_contiguous()
     gemm(ptr(g_cat), 3 * h, ptr(self.emb_cat), 3 * h, ptr(term), ldv, V, 3 * h,

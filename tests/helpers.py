@@ -122,14 +122,19 @@ def sampler_kernel(*, logits_a, xt, mc_t, mc_s, vocab, seq_len, diffusion,
   scode = {'race': _lib.SELECT_RACE, 'argmax': _lib.SELECT_ARGMAX, 'gumbel': _lib.SELECT_GUMBEL}[select]
   if noise is not None:
     noise = noise.reshape(rows, vocab).to(dev, torch.float32).contiguous()
+  ld_clf = vocab
   if clf is not None:
-    clf = clf.reshape(rows, vocab).to(dev, torch.float32).contiguous()
+    if clf.dim() == 2 and clf.shape[0] == rows and clf.shape[1] > vocab:   # rows padded by the caller
+      clf = clf.to(dev, torch.float32).contiguous()
+      ld_clf = clf.stride(0)
+    else:
+      clf = clf.reshape(rows, vocab).to(dev, torch.float32).contiguous()
   a = _lib.SampleStepArgs(
     logits_a=logits_a.data_ptr(), logits_b=_lib.ptr(logits_b), clf=_lib.ptr(clf),
     noise=_lib.ptr(noise), xt=xt.data_ptr(), mc_t=mct.data_ptr(),
     mc_s=mcs.data_ptr(), step_ptr=0, seed_ptr=0, xs=xs.data_ptr(),
     q_out=_lib.ptr(q), rows=rows, ld_a=logits_a.stride(0),
-    ld_b=logits_b.stride(0) if logits_b is not None else 0, ld_clf=vocab,
+    ld_b=logits_b.stride(0) if logits_b is not None else 0, ld_clf=ld_clf,
     ld_noise=vocab, ld_q=vocab, seq_len=seq_len, vocab=vocab,
     mc_seq_stride=1 if mct.numel() > 1 else 0, mc_step_stride=0,
     logits_dtype=_lib.DTYPE_CODE[logits_a.dtype], diffusion=dcode,

