@@ -74,6 +74,15 @@ class DIT:
       raise NotImplementedError(
         'ddg_b200 kernels need head_dim == 64 and hidden % 128 == 0 '
         f'(got hidden={self.hidden}, n_heads={self.n_heads})')
+    # the attention kernels take whole sequences of at most 256 tokens (multiples of 16); the
+    # reference's default `model.length=1024` (OpenWebText) is outside this path -- say so here
+    # instead of at the first forward
+    L = int(m.get('length', 0) or 0)
+    if L > 256 or L % 16 != 0:
+      raise NotImplementedError(
+        f'ddg_b200 attention kernels support model.length in multiples of 16 up to 256 '
+        f'(text8 256, LM1B / Amazon 128, QM9 32); got model.length={L}: override it, e.g. '
+        f'model.length=128')
     self._loaded = False
     self._ws = None
     self._ws_rows = 0

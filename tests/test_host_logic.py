@@ -146,3 +146,19 @@ def test_group_race_restatement_is_a_categorical_draw(group):
   qn = (q / q.sum()).double()
   z = (c - qn * n) / (qn * n * (1 - qn)).clamp_min(1).sqrt()
   assert z.abs().max().item() < 4.5, z
+
+
+def test_unsupported_model_length_is_reported_at_construction():
+  """The reference's default `model.length=1024` is outside the attention kernels' range
+  (<= 256 tokens, multiples of 16): the constructor says so instead of the first forward."""
+  import ddg_b200
+  from ddg_b200 import dit
+  cfg = ddg_b200.compose(['model=small', '+data.num_classes=2'])
+  assert cfg.model.length == 1024
+  with pytest.raises(NotImplementedError, match='model.length'):
+    dit.DIT(cfg, 100)
+  cfg = ddg_b200.compose(['model=small', 'model.length=40', '+data.num_classes=2'])
+  with pytest.raises(NotImplementedError, match='multiples of 16'):
+    dit.DIT(cfg, 100)
+  cfg = ddg_b200.compose(['model=small', 'model.length=128', '+data.num_classes=2'])
+  assert dit.DIT(cfg, 100).hidden == 768
