@@ -129,19 +129,60 @@ def peaks():
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+  """SM clock, board power and throttle reasons sampled DURING the timed region: NVML polled every
+  20 ms from a thread (a timed region at 64 sequences per GPU is ~0.1 s: `nvidia-smi -lms` would
+  return at most one sample), `nvidia-smi` when NVML is unavailable."""
   Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
        'clocks_event_reasons.sw_power_cap')
+  REASON_BITS = (('sw_power_cap', 0x4), ('hw_slowdown', 0x8), ('sw_thermal_slowdown', 0x20),
+                 ('hw_thermal_slowdown', 0x40))
 
   def __init__(self, index):
-    self.index, self.rows, self.proc = index, [], None
+    self.index, self.rows, self.proc, self.nv, self.h = index, [], None, None, None
+    self.stop_flag = threading.Event()
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+      self.nv = pynvml
+      self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+    except Exception:
+      self.nv = None
+
+  @staticmethod
+  def _physical_index(index):
+    vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+    ids = [v for v in vis.split(',') if v.strip() != '']
+    if ids and all(v.strip().isdigit() for v in ids) and index < len(ids):
+      return int(ids[index])
+    return index
+
+  def _poll(self):
+    nv = self.nv
+    while True:
+      try:
+        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        try:
+          bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+          bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        self.rows.append((sm, pw, bits))
+      except Exception:
+        pass
+      if self.stop_flag.wait(0.02):
+        break
 
   def start(self):
+    if self.nv is not None:
+      self.t = threading.Thread(target=self._poll, daemon=True)
+      self.t.start()
+      return
     try:
       self.proc = subprocess.Popen(
         ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-         '-i', str(self.index), '-lms', '200'], stdout=subprocess.PIPE, text=True)
+         '-i', str(self.index), '-lms', '100'], stdout=subprocess.PIPE, text=True)
       self.t = threading.Thread(target=self._read, daemon=True)
       self.t.start()
     except Exception:
@@ -152,6 +193,18 @@ class ClockSampler:
       self.rows.append([x.strip() for x in line.split(',')])
 
   def stop(self):
+    if self.nv is not None:
+      self.stop_flag.set()
+      self.t.join(timeout=2)
+      sm = [r[0] for r in self.rows]
+      pw = [r[1] for r in self.rows]
+      bits = 0
+      for r in self.rows:
+        bits |= r[2]
+      return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': self.max_mhz,
+              'reasons': sorted(n for n, b in self.REASON_BITS if bits & b),
+              'power_w': round(statistics.median(pw), 2) if pw else None, 'samples': len(sm),
+              'source': 'nvml, 20 ms'}
     if self.proc is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
     self.proc.terminate()
@@ -167,7 +220,8 @@ class ClockSampler:
                       for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
     return {'sm_mhz': statistics.median(sm) if sm else None,
             'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-            'power_w': statistics.median(pw) if pw else None, 'samples': len(sm)}
+            'power_w': statistics.median(pw) if pw else None, 'samples': len(sm),
+            'source': 'nvidia-smi -lms 100'}
 
 
 # ---------------------------------------------------------------- CPU arm
