@@ -29,7 +29,11 @@ needs_reference = pytest.mark.skipif(
   reason='no copy of the reference reachable (baseline/_ref is staged by build())')
 
 
-TOL = dict(min_exact=0.25, max_rel_lp=2.5e-2, q_med=3e-2, q_max=0.35, id_frac=0.05)
+# Measured on the B200 (scripts: pytest -s prints the statistics; DESIGN.md section 2 has the table):
+# bit-equal share of the bf16 log-probs 0.62 - 0.97, their largest relative deviation 0.6 - 2.2 %
+# (1 - 3 bf16 ulps), posterior median deviation <= 6.8e-3 and largest <= 0.157 (entries whose bf16
+# log-prob flipped by one ulp), at most 1 id in 64 - 384 different.  Bounds = those with margin.
+TOL = dict(min_exact=0.45, max_rel_lp=2.5e-2, q_med=2e-2, q_max=0.25, id_frac=0.03)
 
 
 @needs_reference
