@@ -463,8 +463,9 @@ def test_classifier_matches_oracle():
 def test_first_order_cbg_term_matches_oracle(name):
   """First-order D-CBG term (diffusion.py:1532-1548): CUDA classifier forward +
   hand-written backward against autograd through the CPU oracle (fp32 and with
-  the bf16 forward roundings).  Tolerance: the block GEMMs / gradients are
-  bf16 like the reference's autocast backward."""
+  the bf16 forward roundings).  The block GEMMs / gradients are bf16 like the
+  reference's autocast backward: measured on the B200, the ratio term deviates by
+  0.18 - 0.24 % of its scale (max and rms); the bound is 1 %."""
   from oracle import ref_sampler
   case = cases.CASE_BY_NAME[name]
   m, cfg, tok, sd, csd = _model(case, classifier=True)
@@ -476,7 +477,7 @@ def test_first_order_cbg_term_matches_oracle(name):
   term, lp = m.first_order_term(xt.to(DEV), sigma.to(DEV), case.condition, round_bf16=True)
   torch.cuda.synchronize()
   term, lp = term.float().cpu(), lp.cpu()
-  for rounding, tol in ((ref_dit.Rounding.none(), 0.08), (ref_dit.Rounding.gpu_classifier(), 0.08)):
+  for rounding, tol in ((ref_dit.Rounding.none(), 0.01), (ref_dit.Rounding.gpu_classifier(), 0.01)):
     def clf(x, s):
       return ref_dit.classifier_log_probs(csd, x, s, n_heads=case.n_heads,
                                           time_conditioning=case.time_conditioning,
@@ -488,7 +489,10 @@ def test_first_order_cbg_term_matches_oracle(name):
     ratio, ratio_ref = term - lp[:, case.condition][:, None, None], ref - lp_ref[:, case.condition][:, None, None]
     scale = ratio_ref.abs().max().item()
     err = (ratio - ratio_ref).abs().max().item()
+    rms = ((ratio - ratio_ref).pow(2).mean() / ratio_ref.pow(2).mean()).sqrt().item()
+    print(f'[first-order term] {name}: max err / scale {err / scale:.4f}, relative rms {rms:.4f}')
     assert err <= tol * scale + 1e-4, (err, scale)
+    assert rms <= tol / 2, rms
     # term at xt itself is log p(y | xt) exactly (ratio 0)
     at = term.gather(-1, xt[..., None])[..., 0]
     torch.testing.assert_close(at, lp[:, case.condition][:, None].expand(n, L), rtol=0, atol=1e-6)
