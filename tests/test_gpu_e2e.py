@@ -269,5 +269,8 @@ def test_step_api_against_reference_under_gpu_autocast(name):
   V = 30522 cases compare the strided column summary the fixtures keep.  (The same
   comparison against the reference run ON the GPU: tests/test_gpu_reference.py.)"""
   helpers.check_against_reference_trace(
-    cases.CASE_BY_NAME[name], helpers.load_golden(name + '_amp'), min_exact=0.25,
-    max_rel_lp=2.5e-2, q_med=3e-2, q_max=0.35, id_frac=0.05)
+    cases.CASE_BY_NAME[name], helpers.load_golden(name + '_amp'), min_exact=0.35,
+    max_rel_lp=2.5e-2, q_med=2.5e-2, q_max=0.28, id_frac=0.03)
+  # measured on the B200 against these CPU-emulation fixtures: bit-equal share 0.44 - 0.84, rest within
+  # 0.7 - 1.7 %, posterior median <= 1.6e-2 / max <= 0.19, at most 1 id of 64 - 384 different (the
+  # reference's own GPU run agrees more closely: tests/test_gpu_reference.py)
