@@ -263,7 +263,7 @@ def test_step_api_against_reference_under_gpu_autocast(name):
   policy emulated on the CPU (tests/golden/make_golden.py --amp), i.e. rounded
   where the reference rounds on a GPU.  Two implementations that round at the
   same points agree bit for bit wherever upstream accumulation-order noise did
-  not flip a rounding, so the bf16 log-probs must share >= 25 % of their entries
+  not flip a rounding, so the bf16 log-probs must share >= 35 % of their entries
   exactly (an fp32 pipeline shares ~0 %, tests/test_oracle_pins.py), stay within
   3 bf16 ulps everywhere, and the ids may differ only at a few near-ties.  The
   V = 30522 cases compare the strided column summary the fixtures keep.  (The same
