@@ -818,7 +818,8 @@ def run_gpu_arm(args, rank, world, local_rank):
   if rank != 0:
     return
   if world == 1 and not args.no_cpu_baseline:
-    s_per_step, cores, timed, kind = cpu_reference_steps(8, 3, 1)
+    # ~10 s of CPU work: 16 reverse steps at batch 8 (0.6 - 0.7 s each on 16 threads)
+    s_per_step, cores, timed, kind = cpu_reference_steps(8, 16, 1, budget_s=30.0)
     what = ("the reference's own Diffusion._cfg_denoise (unmodified, baseline/_ref)"
             if kind == 'reference' else 'oracle/ CPU restatement of the reference step')
     line['cpu_baseline'] = {
