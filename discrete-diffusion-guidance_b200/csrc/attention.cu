@@ -361,6 +361,31 @@ __device__ __forceinline__ void tmem_ld32_sync(uint32_t taddr, uint32_t (&r)[32]
     : "r"(taddr)
     : "memory");
 }
+// The same load without the wait, and the wait with the registers as in/out operands (no use of them
+// can be scheduled ahead of it): the next chunk's load is in flight while this chunk is processed.
+// tcgen05.wait::ld covers every earlier load of the thread, so the order is wait -> issue next -> use.
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+    : "r"(taddr)
+    : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 // 128B-swizzled shared-memory matrix descriptor; SBO = 1024 B (8 rows of 128 B)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
@@ -495,35 +520,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
       constexpr int NCH = 4 * NK;                       // chunks of the score tile
       constexpr int CPS = LSEQ / 32;                    // chunks per sequence
       const int c_lo = (warp / CPS) * CPS, c_hi = c_lo + CPS;
-      float m = -INFINITY;
-#pragma unroll 1
-      for (int c = c_lo; c < c_hi; ++c) {
-        uint32_t r[32];
-        tmem_ld32_sync(tm_s + lane_addr + (uint32_t)(c * 32), r);
+      // The thread phase is what bounds this kernel once the SM clock is held down by the step's GEMMs,
+      // so its latency chains are kept short: the next 32-column chunk's tensor-memory load is in flight
+      // while the current one is processed (two register buffers, loops fully unrolled), and the row
+      // maximum / sum run as four independent chains.
+      uint32_t rr[2][32];
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      tmem_ld32_async(tm_s + lane_addr + (uint32_t)(c_lo * 32), rr[0]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+      for (int cc = 0; cc < CPS; ++cc) {
+        uint32_t (&r)[32] = rr[cc & 1];
+        tmem_ld_wait32(r);
+        // next: the following chunk of this pass, or the first chunk again for the exponentials
+        tmem_ld32_async(tm_s + lane_addr + (uint32_t)((cc + 1 < CPS ? c_lo + cc + 1 : c_lo) * 32), rr[(cc + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
       }
+      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       const float msc = m * kScale2;
-      float l = 0.f;
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
       if (it > 0) mbar_wait(b_o, ph ^ 1);               // P of the previous item has been consumed
-#pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        uint32_t w[16];
-        if (c >= c_lo && c < c_hi) {                      // warp-uniform
-          uint32_t r[32];
-          tmem_ld32_sync(tm_s + lane_addr + (uint32_t)(c * 32), r);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), kScale2, -msc));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), kScale2, -msc));
-            l += p0 + p1;
-            w[i] = Mma<T>::pack(p0, p1);
-          }
-        } else {                                          // keys of the other sequences of the item
-#pragma unroll
-          for (int i = 0; i < 16; ++i) w[i] = 0u;
-        }
-        // keys 32c .. 32c+31 of row `row`: tile c / 2, 16-byte chunks 4 (c & 1) .. + 3, swizzled
+      // keys 32c .. 32c+31 of row `row`: tile c / 2, 16-byte chunks 4 (c & 1) .. + 3, swizzled
+      auto store_p = [&](int c, const uint32_t (&w)[16]) {
         const uint32_t tile = sp + (uint32_t)(c >> 1) * TILE + (uint32_t)row * 128u;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -531,7 +549,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, T* __restrict__
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (ch << 4)), "r"(w[4 * q]),
                        "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]) : "memory");
         }
+      };
+#pragma unroll
+      for (int cc = 0; cc < CPS; ++cc) {
+        uint32_t (&r)[32] = rr[(CPS + cc) & 1];
+        tmem_ld_wait32(r);
+        if (cc + 1 < CPS) tmem_ld32_async(tm_s + lane_addr + (uint32_t)((c_lo + cc + 1) * 32), rr[(CPS + cc + 1) & 1]);
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), kScale2, -msc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), kScale2, -msc));
+          l4[i & 3] += p0 + p1;
+          w[i] = Mma<T>::pack(p0, p1);
+        }
+        store_p(c_lo + cc, w);
       }
+      if (CPS < NCH) {                                    // keys of the other sequences of the item
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c)
+          if (c < c_lo || c >= c_hi) store_p(c, z);
+      }
+      const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P visible to the tensor core
       tc_fence_before();
       mbar_arrive(b_p);
