@@ -312,8 +312,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
       // ================= pass A: this thread = query row
       mbar_wait(b_sA, ph);
       tc_fence_after();
+      // (row maximum, sum and D as four independent chains each: the thread phases are latency-bound)
       float e[LSEQ];
-      float m = -INFINITY;
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int cc = 0; cc < CPS; ++cc) {
         uint32_t r[32];
@@ -321,26 +322,27 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           e[cc * 32 + i] = __uint_as_float(r[i]);
-          m = fmaxf(m, e[cc * 32 + i]);
+          m4[i & 3] = fmaxf(m4[i & 3], e[cc * 32 + i]);
         }
       }
+      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       const float msc = m * kScale2;
-      float l = 0.f;
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < LSEQ; ++i) {
         e[i] = ex2_approx(fmaf(e[i], kScale2, -msc));
-        l += e[i];
+        l4[i & 3] += e[i];
       }
-      const float inv = 1.f / l;
-      float dsum = 0.f;
+      const float inv = 1.f / ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int cc = 0; cc < CPS; ++cc) {
         uint32_t r[32];
         tmem_ld32_sync(tm_dp + lane_addr + (uint32_t)((c_lo + cc) * 32), r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dsum = fmaf(e[cc * 32 + i], __uint_as_float(r[i]), dsum);
+        for (int i = 0; i < 32; ++i) d4[i & 3] = fmaf(e[cc * 32 + i], __uint_as_float(r[i]), d4[i & 3]);
       }
-      const float D = dsum * inv;
+      const float D = ((d4[0] + d4[1]) + (d4[2] + d4[3])) * inv;
       const float pscale = inv * kScale;
 #pragma unroll
       for (int cc = 0; cc < CPS; ++cc) {
