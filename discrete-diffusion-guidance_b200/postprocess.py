@@ -5,8 +5,12 @@ unigram entropy of the re-encoded samples.  Host-side code: the ids are (B, L)
 int64, three orders of magnitude less data than one step's logits.
 
 Generative perplexity (`eval_utils.compute_generative_ppl`, eval_utils.py:28-90)
-scores the decoded text with a pretrained GPT-2; its weights need a network, so
-`generate_and_score` takes the scorer as an optional callable instead.
+scores the decoded text with a pretrained causal LM (GPT-2 large in the reference's
+scripts).  `generative_ppl` is that computation for an eval model / tokenizer the caller
+already holds, `compute_generative_ppl` the reference's signature (name or LOCAL path ->
+`transformers.*.from_pretrained`; there is no network here, so the tests score with a
+random-init GPT-2 built from a config).  `generate_and_score` takes the scorer as an
+optional callable.
 """
 from __future__ import annotations
 
@@ -42,6 +46,56 @@ def token_entropy(ids: torch.Tensor) -> float:
   (main.py:293-296); works on the device the ids live on."""
   _, counts = torch.unique(ids, return_counts=True, sorted=False)
   return torch.special.entr(counts.float() / counts.sum()).sum().item()
+
+
+@torch.no_grad()
+def generative_ppl(sentences: typing.Sequence[str], eval_model, eval_tokenizer,
+                   gen_ppl_eval_batch_size: int = 8, max_length: typing.Optional[int] = 128,
+                   eval_context_size: int = 1024, device=None) -> float:
+  """eval_utils.py:28-90 with the eval model and tokenizer passed in: the sentences are
+  re-tokenised with the eval model's tokenizer (truncation + padding to the longest, pad =
+  eos when the tokenizer has no pad token), scored in batches of `gen_ppl_eval_batch_size`
+  (a trailing partial batch is dropped, as in the reference) and in chunks of
+  `eval_context_size` tokens; perplexity = exp(sum of the next-token NLLs over the
+  non-padding target positions / their count) -- `diffusion.Perplexity` (diffusion.py:46-67:
+  a weighted mean with the attention mask as weight)."""
+  if getattr(eval_tokenizer, 'pad_token', None) is None:
+    eval_tokenizer.pad_token = eval_tokenizer.eos_token
+    eval_tokenizer.pad_token_id = eval_tokenizer.eos_token_id
+  if device is None:
+    device = 'cuda' if torch.cuda.is_available() else 'cpu'
+  eval_model = eval_model.eval().to(device)
+  enc = eval_tokenizer(list(sentences), return_tensors='pt', return_token_type_ids=False,
+                       return_attention_mask=True, truncation=True, padding=True,
+                       max_length=max_length)
+  samples = enc['input_ids'].to(device)
+  attn_mask = enc['attention_mask'].to(device)
+  nll_sum = torch.zeros((), dtype=torch.float32, device=device)
+  weight = torch.zeros((), dtype=torch.float32, device=device)
+  bs = gen_ppl_eval_batch_size
+  for i in range(samples.shape[0] // bs):
+    chunks = zip(torch.split(samples[i * bs:(i + 1) * bs], eval_context_size, dim=-1),
+                 torch.split(attn_mask[i * bs:(i + 1) * bs], eval_context_size, dim=-1))
+    for sample_chunk, mask_chunk in chunks:
+      logits = eval_model(sample_chunk, attention_mask=mask_chunk)[0].transpose(-1, -2)
+      nlls = torch.nn.functional.cross_entropy(logits[..., :-1], sample_chunk[..., 1:],
+                                               reduction='none')
+      w = mask_chunk[..., 1:].to(nlls.dtype)
+      nll_sum += (nlls * w).sum().float()
+      weight += w.sum().float()
+  return torch.exp(nll_sum / weight).item()
+
+
+def compute_generative_ppl(sentences, eval_model_name_or_path, gen_ppl_eval_batch_size=8,
+                           max_length=128) -> float:
+  """The reference's entry point (eval_utils.py:28-33): loads tokenizer and causal LM with
+  `transformers` (a local directory works offline) and scores with `generative_ppl`."""
+  import os
+  import transformers
+  os.environ['TOKENIZERS_PARALLELISM'] = 'false'
+  tok = transformers.AutoTokenizer.from_pretrained(eval_model_name_or_path)
+  lm = transformers.AutoModelForCausalLM.from_pretrained(eval_model_name_or_path)
+  return generative_ppl(sentences, lm, tok, gen_ppl_eval_batch_size, max_length)
 
 
 def generate_and_score(model, tokenizer=None, num_sample_batches=None,

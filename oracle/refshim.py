@@ -134,7 +134,26 @@ def _install_stubs():
         setattr(self, name, default)
 
     class MeanMetric(Metric):
-      pass
+      """torchmetrics.aggregation.MeanMetric as the reference uses it (diffusion.py:46-67: NLL /
+      BPD / Perplexity read `mean_value` and `weight`): weighted running sum and weight sum."""
+      def __init__(self, *a, **k):
+        super().__init__()
+        self.mean_value = torch.zeros(())
+        self.weight = torch.zeros(())
+
+      def update(self, value, weight=1.0):
+        value = torch.as_tensor(value, dtype=torch.float32)
+        weight = torch.broadcast_to(torch.as_tensor(weight, dtype=torch.float32, device=value.device),
+                                    value.shape)
+        self.mean_value = self.mean_value.to(value.device) + (value * weight).sum()
+        self.weight = self.weight.to(value.device) + weight.sum()
+
+      def compute(self):
+        return self.mean_value / self.weight
+
+      def reset(self):
+        self.mean_value = torch.zeros(())
+        self.weight = torch.zeros(())
 
     class MetricCollection(nn.Module):
       def __init__(self, *a, **k):
