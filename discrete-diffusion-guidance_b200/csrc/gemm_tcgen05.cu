@@ -1100,21 +1100,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const uint64_t pol_out = policy_evict_first();
         // the 16-bit side tensor (ABI v6): rows mw.., this lane's 8-column chunk
         T* aslab = p.aux ? reinterpret_cast<T*>(p.aux) + (int64_t)mw * p.ld_aux + cchunk * 8 : nullptr;
-        // BIAS_GELU with a side output: the pre-activation round(acc + bias) of 32 columns -> aux
-        auto store_aux_chunk = [&](const uint32_t (&w)[16], int nc) {
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) st_shared_v4(stg_wr + q * 16, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-          __syncwarp();
-          const int col = nc + cchunk * 8;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = 8 * i + crow;
-            const uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
-            if (mw + row < M && col + 8 <= p.N) *reinterpret_cast<uint4*>(aslab + (int64_t)row * p.ld_aux + nc) = y;
-          }
-        };
-        // stages 32 columns (16 packed words per row) through the slab and stores them coalesced
         // GELU_BWD: the pre-activations of this lane's four 16-byte pieces of a 32-column chunk; issued
         // before the chunk's accumulator load so that they travel during it and the transpose
         uint4 pre[4];
@@ -1138,6 +1123,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int i = 0; i < 4; ++i) {
             const int row = 8 * i + crow;
             uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
+            if (EPI == DDG_EPI_BIAS_GELU && aslab != nullptr) {
+              // side output: y is the pre-activation round(acc + bias); the GELU of these 8 values is
+              // formed here, lanes along the row, so both tensors leave through ONE trip through the slab
+              if (mw + row < M && col + 8 <= p.N) *reinterpret_cast<uint4*>(aslab + (int64_t)row * p.ld_aux + nc) = y;
+              const uint32_t pw[4] = {y.x, y.y, y.z, y.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 r = gelu_tanh2(H2<T>::unpack(pw[k]));
+                o[k] = H2<T>::pack(r.x, r.y);
+              }
+              y = make_uint4(o[0], o[1], o[2], o[3]);
+            }
             if (EPI == DDG_EPI_GELU_BWD) {     // round(g * gelu'(pre)): ddg_gelu_backward's arithmetic
               const uint32_t gw[4] = {y.x, y.y, y.z, y.w}, pw[4] = {pre[i].x, pre[i].y, pre[i].z, pre[i].w};
               uint32_t o[4];
@@ -1244,8 +1242,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             uint32_t w[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) w[i] = H2<T>::pack(v[i].x, v[i].y);
-            if (EPI == DDG_EPI_BIAS_GELU) {
-              if (aslab) store_aux_chunk(w, nc);
+            if (EPI == DDG_EPI_BIAS_GELU && aslab == nullptr) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const float2 y = gelu_tanh2(H2<T>::unpack(w[i]));
