@@ -33,6 +33,9 @@ constexpr int UMMA_K = 16;
 constexpr int MAX_STAGES = 6;
 // internal epilogue id: GATE_RESIDUAL followed by the next LayerNorm + modulate (fused on chip)
 constexpr int EPI_GATE_RESIDUAL_LN = 16;
+// internal epilogue id: BIAS_GELU that also writes the pre-activation (ddg_gemm_args.aux); a separate
+// instantiation so that the plain BIAS_GELU kernel of the sampling step carries no extra branch
+constexpr int EPI_BIAS_GELU_AUX = 17;
 // the fused-LayerNorm variant trades one pipeline stage for its per-column LayerNorm vectors
 template <int EPI> __host__ __device__ constexpr int stages_for() { return EPI == EPI_GATE_RESIDUAL_LN ? 5 : MAX_STAGES; }
 constexpr int A_STAGE_BYTES = BM * BK * 2;
@@ -1099,7 +1102,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         __syncwarp();
         const uint64_t pol_out = policy_evict_first();
         // the 16-bit side tensor (ABI v6): rows mw.., this lane's 8-column chunk
-        T* aslab = p.aux ? reinterpret_cast<T*>(p.aux) + (int64_t)mw * p.ld_aux + cchunk * 8 : nullptr;
+        T* aslab = (EPI == EPI_BIAS_GELU_AUX || EPI == DDG_EPI_GELU_BWD)
+                     ? reinterpret_cast<T*>(p.aux) + (int64_t)mw * p.ld_aux + cchunk * 8 : nullptr;
         // GELU_BWD: the pre-activations of this lane's four 16-byte pieces of a 32-column chunk; issued
         // before the chunk's accumulator load so that they travel during it and the transpose
         uint4 pre[4];
@@ -1123,7 +1127,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int i = 0; i < 4; ++i) {
             const int row = 8 * i + crow;
             uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
-            if (EPI == DDG_EPI_BIAS_GELU && aslab != nullptr) {
+            if (EPI == EPI_BIAS_GELU_AUX) {
               // side output: y is the pre-activation round(acc + bias); the GELU of these 8 values is
               // formed here, lanes along the row, so both tensors leave through ONE trip through the slab
               if (mw + row < M && col + 8 <= p.N) *reinterpret_cast<uint4*>(aslab + (int64_t)row * p.ld_aux + nc) = y;
@@ -1242,7 +1246,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             uint32_t w[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) w[i] = H2<T>::pack(v[i].x, v[i].y);
-            if (EPI == DDG_EPI_BIAS_GELU && aslab == nullptr) {
+            if (EPI == DDG_EPI_BIAS_GELU) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const float2 y = gelu_tanh2(H2<T>::unpack(w[i]));
@@ -1369,7 +1373,9 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   switch (epi) {
     case DDG_EPI_STORE: return launch_gemm<T, DDG_EPI_STORE>(ta, tb, p, s);
     case DDG_EPI_QKV_ROPE: return launch_gemm<T, DDG_EPI_QKV_ROPE>(ta, tb, p, s);
-    case DDG_EPI_BIAS_GELU: return launch_gemm<T, DDG_EPI_BIAS_GELU>(ta, tb, p, s);
+    case DDG_EPI_BIAS_GELU:
+      if (p.aux) return launch_gemm<T, EPI_BIAS_GELU_AUX>(ta, tb, p, s);
+      return launch_gemm<T, DDG_EPI_BIAS_GELU>(ta, tb, p, s);
     case DDG_EPI_GATE_RESIDUAL:
       if (p.ln_w) return launch_gemm<T, EPI_GATE_RESIDUAL_LN>(ta, tb, p, s);
       return launch_gemm<T, DDG_EPI_GATE_RESIDUAL>(ta, tb, p, s);
