@@ -224,6 +224,41 @@ def test_production_shapes_graph_equals_eager(B, guidance):
   assert not torch.equal(a, c)
 
 
+def test_benchmark_configuration_at_full_size():
+  """BASELINE.json configs[2] exactly as bench.py times it -- DiT-small, 12 blocks, 512 sequences
+  x 128 tokens x 30522 entries, D-CFG gamma = 2 (the cond / uncond pair = 131 072 token rows per
+  forward) -- through `sample()` for a few steps.  Size-independent properties: the captured-graph
+  loop equals the eager loop bit for bit, a repeated call with the same key reproduces the ids,
+  another key does not, ids stay in range, and (uniform diffusion from t = 1) almost every
+  token has moved after the first steps while late steps would move few."""
+  import dataclasses
+  base = cases.CASE_BY_NAME['bert_udlm_cfg_g2']
+  case = dataclasses.replace(base, name='c3_full', batch=512, length=128, hidden=768, n_heads=12,
+                             n_blocks=12, guidance='cfg', steps=4)
+  model, cfg, tok = _diffusion(case)
+  V = tok.vocab_size
+  prior = model._sample_prior(512, 128).clone()
+  a = model.sample()
+  torch.cuda.synchronize()
+  model._call_count -= 1
+  model.use_cuda_graph = False
+  b = model.sample()
+  torch.cuda.synchronize()
+  assert tuple(a.shape) == (512, 128) and a.dtype == torch.int64
+  assert torch.equal(a, b), 'graph loop != eager loop at the benchmarked size'
+  assert int(a.min()) >= 0 and int(a.max()) < V
+  model.use_cuda_graph = True
+  model._call_count -= 1
+  assert torch.equal(model.sample(), a), 'same key, same ids'
+  c = model.sample()
+  assert not torch.equal(a, c)
+  # 4 steps over t in (0, 1]: every position is redrawn at least once, so two runs agree only by chance
+  # (a random-init network's predictive distribution has a perplexity in the hundreds or more)
+  assert (a != c).float().mean().item() > 0.9
+  assert (a != prior).float().mean().item() > 0.9
+  assert torch.unique(a).numel() > 300
+
+
 @pytest.mark.parametrize('guidance', [None, 'cfg'])
 def test_ar_kv_cache_equals_prefix_reencode(guidance):
   """AR sampling with the KV cache (one token per step through the network) against the
