@@ -21,6 +21,8 @@
 // tile i+1.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "ddg_common.cuh"
 
 namespace ddg {
@@ -37,7 +39,17 @@ constexpr int EPI_GATE_RESIDUAL_LN = 16;
 // instantiation so that the plain BIAS_GELU kernel of the sampling step carries no extra branch
 constexpr int EPI_BIAS_GELU_AUX = 17;
 // the fused-LayerNorm variant trades one pipeline stage for its per-column LayerNorm vectors
-template <int EPI> __host__ __device__ constexpr int stages_for() { return EPI == EPI_GATE_RESIDUAL_LN ? 5 : MAX_STAGES; }
+// 16-bit outputs with no work in the coalesced phase leave through TMA stores (cp.async.bulk.tensor
+// shared -> global): thread = row writes into a 64B-swizzled 32 x 32 slab, one lane issues the copy
+template <int EPI> __host__ __device__ constexpr bool tma_out() {
+  return EPI == DDG_EPI_STORE || EPI == DDG_EPI_QKV_ROPE || EPI == DDG_EPI_BIAS_GELU;
+}
+#ifndef DDG_TMA_OUT_STAGES
+#define DDG_TMA_OUT_STAGES 5
+#endif
+template <int EPI> __host__ __device__ constexpr int stages_for() {
+  return EPI == EPI_GATE_RESIDUAL_LN ? 5 : tma_out<EPI>() ? DDG_TMA_OUT_STAGES : MAX_STAGES;
+}
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int BNH = BN / 2;          // W rows staged by each CTA of the pair
 constexpr int B_STAGE_BYTES = BNH * BK * 2;
@@ -48,13 +60,19 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_ROW_BYTES = 80;                  // 64 B payload + 16 B pad: conflict-free 128-bit stores
 constexpr int EPI_SLAB_BYTES = 32 * EPI_ROW_BYTES;  // one warp's 32 accumulator rows
+constexpr int TMA_SLAB_BYTES = 32 * 64;            // TMA-store slab: 32 rows x 64 B, SWIZZLE_64B
+#ifndef DDG_TMA_OUT_BUFS
+#define DDG_TMA_OUT_BUFS 2
+#endif
+constexpr int TMA_OUT_BUFS = DDG_TMA_OUT_BUFS;     // slabs per epilogue warp (2: the copy of chunk c reads while c + 1 is written)
 constexpr int LN_ROW_BYTES = 144;                  // fused LayerNorm: 32 fp32 columns (128 B) + 16 B pad per row
 constexpr int LN_SLAB_BYTES = 32 * LN_ROW_BYTES;
 constexpr int EPI_BIAS_BYTES = NUM_EPI_WARPS * (BN / 2) * 4;   // fp32 bias (and gate) of each epilogue warp's 128 columns
 constexpr int EPI_LN_BYTES = 3 * EPI_BIAS_BYTES;   // fused LayerNorm: weight, 1 + scale, shift (fp32) per epilogue warp
 template <int EPI> __host__ __device__ constexpr int smem_bytes() {
   return stages_for<EPI>() * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-         8 * (EPI == EPI_GATE_RESIDUAL_LN ? LN_SLAB_BYTES : EPI_SLAB_BYTES) + 2 * EPI_BIAS_BYTES +
+         8 * (EPI == EPI_GATE_RESIDUAL_LN ? LN_SLAB_BYTES : tma_out<EPI>() ? TMA_OUT_BUFS * TMA_SLAB_BYTES : EPI_SLAB_BYTES) +
+         2 * EPI_BIAS_BYTES +
          (EPI == EPI_GATE_RESIDUAL_LN ? EPI_LN_BYTES : 0);
 }
 
@@ -84,6 +102,7 @@ struct GemmParams {
   const float* residual; // GATE_RESIDUAL: rows the delta is added to (null: `out` itself, in place)
   void* aux;            // BIAS_GELU: optional pre-activation output; GELU_BWD: pre-activation input (16-bit, ld_aux)
   int64_t ld_aux;
+  int64_t out_rows;     // rows of `out` a TMA-store epilogue may address (M; the whole buffer with out_seq_map)
   uint8_t* ln_work;     // per 128-row block: [counter word, padded to 64 B][128 x N / 128 partial words of 8 B]
                         // -- a layout that does not depend on M, so launches over different row counts
                         // can share one buffer
@@ -527,21 +546,24 @@ __device__ unsigned long long g_ln_prof[8];
 template <typename T, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const GemmParams p) {
+            const __grid_constant__ CUtensorMap tma_o, const GemmParams p) {
   constexpr int STAGES = stages_for<EPI>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  constexpr int SLAB_BYTES = EPI == EPI_GATE_RESIDUAL_LN ? LN_SLAB_BYTES
+                             : tma_out<EPI>() ? TMA_OUT_BUFS * TMA_SLAB_BYTES : EPI_SLAB_BYTES;
+  // the epilogue warps' slabs follow the stages (1024-byte aligned: the TMA-store slabs are swizzled),
+  // then the barriers, then the per-column vectors
+  uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + NUM_EPI_WARPS * SLAB_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;   // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  uint8_t* smem_epi = smem + STAGES * STAGE_BYTES + 256;
-  constexpr int SLAB_BYTES = EPI == EPI_GATE_RESIDUAL_LN ? LN_SLAB_BYTES : EPI_SLAB_BYTES;
-  uint8_t* smem_bias = smem_epi + NUM_EPI_WARPS * SLAB_BYTES;
+  uint8_t* smem_bias = reinterpret_cast<uint8_t*>(bars) + 256;
   uint8_t* smem_gate = smem_bias + EPI_BIAS_BYTES;
   uint8_t* smem_ln = smem_gate + EPI_BIAS_BYTES;   // EPI_GATE_RESIDUAL_LN only
 
@@ -562,6 +584,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (tma_out<EPI>()) tma_prefetch_desc(&tma_o);
   }
   if (warp == 1 && lane == 0) {
     // full: the leader producer's arrival + both CTAs' TMA bytes, leader's copy is the live one;
@@ -666,6 +689,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tmem_empty_leader0 = map_to_cta(smem_u32(&tmem_empty[0]), 0);
+    uint32_t tma_chunk = 0;                     // TMA-store epilogues: chunks this warp has sent (slab = parity)
 #ifdef DDG_LN_PROF
     long long lnp_t = clock64();
 #endif
@@ -1118,6 +1142,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           }
         };
         auto store_chunk = [&](const uint32_t (&w)[16], int nc) {
+          if constexpr (tma_out<EPI>()) {
+            // thread = row: 64 B of this chunk into the swizzled slab (16-byte piece q of row r at
+            // q ^ ((r >> 1) & 3): conflict-free), then ONE bulk tensor store of the 32 x 32 box; columns
+            // past N and rows past M are clipped by the tensor map.  The slab written two chunks ago
+            // must have been read by its copy before it is overwritten.
+            const uint32_t slab = stg + (uint32_t)(tma_chunk % TMA_OUT_BUFS) * TMA_SLAB_BYTES;
+            if (lane == 0)
+              asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TMA_OUT_BUFS - 1) : "memory");
+            __syncwarp();
+            const uint32_t rowp = slab + (uint32_t)lane * 64u;
+            const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(rowp + (((uint32_t)q ^ sw) << 4), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && mw < M) {            // (a warp wholly past the live rows sends nothing)
+              if (p.stream_out)
+                asm volatile(
+                  "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                  ::"l"(reinterpret_cast<uint64_t>(&tma_o)), "r"(slab), "r"(nc), "r"(mw_out), "l"(pol_out) : "memory");
+              else
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tma_o)), "r"(slab), "r"(nc), "r"(mw_out) : "memory");
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            ++tma_chunk;
+            return;
+          }
           const int col = nc + cchunk * 8;
           __syncwarp();
 #pragma unroll
@@ -1297,6 +1350,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    // TMA-store epilogues: this warp's copies have left shared memory and are complete
+    if (tma_out<EPI>() && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -1351,6 +1406,23 @@ int make_tma_rows64(void* map, const void* base, int64_t rows, int64_t cols, int
 
 namespace {
 
+// 16-bit row-major output as a 2-D tensor map {cols, rows} with a {32 columns, 32 rows} box (64 B x 32) and
+// the 64-byte swizzle: the destination of the TMA-store epilogues (clips columns >= N and rows >= M)
+int make_tma_out(CUtensorMap* map, void* base, int64_t rows, int64_t cols, int64_t ld, int dtype) {
+  EncodeTiledFn fn = get_encode_fn();
+  DDG_REQUIRE(fn != nullptr, DDG_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dtype == DDG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base,
+                  gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DDG_REQUIRE(r == CUDA_SUCCESS, DDG_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d): rows=%lld cols=%lld ld=%lld",
+              (int)r, (long long)rows, (long long)cols, (long long)ld);
+  return DDG_OK;
+}
+
 template <typename T, int EPI>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
   static bool attr_done[64] = {false};
@@ -1364,7 +1436,12 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
   const int num_tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
   int grid = sm_count() & ~1;           // CTA pairs
   if (grid > 2 * num_tiles) grid = 2 * num_tiles;
-  gemm_kernel<T, EPI><<<grid, NUM_THREADS, smem_bytes<EPI>(), s>>>(ta, tb, p);
+  CUtensorMap to = ta;                  // only the TMA-store epilogues read it
+  if constexpr (tma_out<EPI>()) {
+    const int rc = make_tma_out(&to, p.out, p.out_rows, p.N, p.ld_out, std::is_same<T, __half>::value ? DDG_F16 : DDG_BF16);
+    if (rc) return rc;
+  }
+  gemm_kernel<T, EPI><<<grid, NUM_THREADS, smem_bytes<EPI>(), s>>>(ta, tb, to, p);
   return check_cuda(cudaGetLastError(), "gemm launch");
 }
 
@@ -1496,6 +1573,8 @@ extern "C" int ddg_gemm(const ddg_gemm_args* args, ddg_stream_t stream) {
     p.ln_work = reinterpret_cast<uint8_t*>(a.ln_work);
   }
   p.aux = nullptr; p.ld_aux = 0;
+  // with a sequence scatter map the output rows are those of the full batch: M is its upper bound too
+  p.out_rows = a.M;
   if (a.aux || a.epilogue == DDG_EPI_GELU_BWD) {
     DDG_REQUIRE(a.epilogue == DDG_EPI_BIAS_GELU || a.epilogue == DDG_EPI_GELU_BWD, DDG_ERR_INVALID,
                 "gemm: aux goes with the BIAS_GELU (output) and GELU_BWD (input) epilogues");

@@ -271,7 +271,11 @@ enum ddg_epilogue {
 typedef struct ddg_gemm_args {
   const void* a;        /* (M, K) activations, 16-bit `dtype`, row-major     */
   const void* w;        /* (N, K) nn.Linear weight, 16-bit `dtype`           */
-  void* out;            /* (M, ld_out) 16-bit, or the fp32 residual stream   */
+  void* out;            /* (M, ld_out) 16-bit, or the fp32 residual stream.
+                           16-bit outputs leave through TMA stores that clip at
+                           16-byte units: with N % 8 != 0 the columns up to the
+                           next multiple of 8 are written too (ld_out covers
+                           them: it is a multiple of 8)                        */
   const void* bias;     /* (N,) `dtype` or NULL; readable up to the next
                            multiple of 256 columns                           */
   const void* gate;     /* GATE_RESIDUAL: adaLN gate rows (`dtype`) or NULL  */
