@@ -546,7 +546,8 @@ __device__ unsigned long long g_ln_prof[8];
 template <typename T, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const __grid_constant__ CUtensorMap tma_o, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tma_o, const __grid_constant__ CUtensorMap tma_o2,
+            const GemmParams p) {
   constexpr int STAGES = stages_for<EPI>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -584,7 +585,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    if (tma_out<EPI>()) tma_prefetch_desc(&tma_o);
+    if (tma_out<EPI>() || EPI == EPI_GATE_RESIDUAL_LN) tma_prefetch_desc(&tma_o);
+    if (EPI == EPI_GATE_RESIDUAL_LN) tma_prefetch_desc(&tma_o2);
   }
   if (warp == 1 && lane == 0) {
     // full: the leader producer's arrival + both CTAs' TMA bytes, leader's copy is the live one;
@@ -795,6 +797,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           int* cnt = reinterpret_cast<int*>(blk);
           uint64_t* part = reinterpret_cast<uint64_t*>(blk + 64) + (int64_t)row_in_tile * nvalid;   // this row's words
           const int epoch_word = ld_relaxed_gpu(cnt);
+          // the slab doubles as the source of the previous tile's last TMA stores: they have been read
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
           // ---- pass 1
           float s1 = 0.f, s2 = 0.f, c0 = 0.f;
 #pragma unroll 1
@@ -865,22 +870,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                   ((uint64_t)((__float_as_uint(m2_i) & 0x7fffffffu) | (tagbit << 31)) << 32);
             st_relaxed_gpu_b64(part + (nb * 2 + chalf), word);
           }
-          // ---- x_new -> fp32 residual stream while the other owners' words travel
-          float* xrow = reinterpret_cast<float*>(p.out) + (int64_t)(mw + r4) * p.ld_out + c8 * 4;
+          // ---- x_new -> fp32 residual stream while the other owners' words travel: thread = row writes
+          // 16 columns (64 B) at a time into one of two 64B-swizzled 32 x 64 B slabs, one lane sends the
+          // 32 x 16 box with a TMA store (rows >= M clipped by the tensor map), the slabs alternate
+          const uint32_t sw64 = (uint32_t)(lane >> 1) & 3u;
 #pragma unroll 1
           for (int g = 0; g < BN / 64; ++g) {
             const int nc = n0 + g * 32;
             uint32_t r[32];
             tmem_ld32_sync(taddr + (uint32_t)(g * 32), r);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) st_shared_v4(xs_row + q * 16, r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-            __syncwarp();
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t slab = stg + (tma_chunk & 1u) * TMA_SLAB_BYTES;
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              __syncwarp();
+              const uint32_t rowp = slab + (uint32_t)lane * 64u;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint4 y = ld_shared_v4(xs_co + (uint32_t)(4 * i) * LN_ROW_BYTES);
-              if (mw + 4 * i + r4 < M) *reinterpret_cast<uint4*>(xrow + (int64_t)(4 * i) * p.ld_out + nc) = y;
+              for (int q = 0; q < 4; ++q)
+                st_shared_v4(rowp + (((uint32_t)q ^ sw64) << 4), r[16 * hh + 4 * q], r[16 * hh + 4 * q + 1],
+                             r[16 * hh + 4 * q + 2], r[16 * hh + 4 * q + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                if (mw < M)
+                  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                               ::"l"(reinterpret_cast<uint64_t>(&tma_o)), "r"(slab), "r"(nc + 16 * hh), "r"(mw) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+              ++tma_chunk;
             }
-            __syncwarp();
           }
           DDG_LNP(2)
           // ---- the row's partials from all owners, combined in slot order (same result everywhere)
@@ -938,7 +956,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                            __float_as_uint(g23.y));
             }
             __syncwarp();
-            TO* oslab = reinterpret_cast<TO*>(p.ln_out) + (int64_t)mw * p.N + cchunk * 8;
             const float2 mean2 = make_float2(mean, mean), rs2 = make_float2(rstd, rstd);
 #pragma unroll 1
             for (int g = 0; g < BN / 64; ++g) {
@@ -965,15 +982,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 w[2 * i] = H2<TO>::pack(y0.x, y0.y);
                 w[2 * i + 1] = H2<TO>::pack(y1.x, y1.y);
               }
-              __syncwarp();
+              {
+                const uint32_t slab = stg + (tma_chunk & 1u) * TMA_SLAB_BYTES;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                const uint32_t rowp = slab + (uint32_t)lane * 64u;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) st_shared_v4(stg_wr + q * 16, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-              __syncwarp();
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int row = 8 * i + crow;
-                const uint4 y = ld_shared_v4(stg_rd + (uint32_t)(8 * i) * EPI_ROW_BYTES);
-                if (mw + row < M) *reinterpret_cast<uint4*>(oslab + (int64_t)row * p.N + nc) = y;
+                for (int q = 0; q < 4; ++q)
+                  st_shared_v4(rowp + (((uint32_t)q ^ sw64) << 4), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                  if (mw < M)
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(&tma_o2)), "r"(slab), "r"(nc), "r"(mw) : "memory");
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                ++tma_chunk;
               }
             }
           };
@@ -1351,7 +1376,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       if (acc == 0) acc_phase ^= 1;
     }
     // TMA-store epilogues: this warp's copies have left shared memory and are complete
-    if (tma_out<EPI>() && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if ((tma_out<EPI>() || EPI == EPI_GATE_RESIDUAL_LN) && lane == 0)
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -1408,14 +1434,17 @@ namespace {
 
 // 16-bit row-major output as a 2-D tensor map {cols, rows} with a {32 columns, 32 rows} box (64 B x 32) and
 // the 64-byte swizzle: the destination of the TMA-store epilogues (clips columns >= N and rows >= M)
+// dtype DDG_F32: fp32 rows, {16 columns, 32 rows} box (also 64 B x 32): the fused-LayerNorm epilogue's x_new
 int make_tma_out(CUtensorMap* map, void* base, int64_t rows, int64_t cols, int64_t ld, int dtype) {
   EncodeTiledFn fn = get_encode_fn();
   DDG_REQUIRE(fn != nullptr, DDG_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  const bool f32 = dtype == DDG_F32;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {32, 32};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {f32 ? 16u : 32u, 32};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, dtype == DDG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base,
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                        : dtype == DDG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base,
                   gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DDG_REQUIRE(r == CUDA_SUCCESS, DDG_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d): rows=%lld cols=%lld ld=%lld",
@@ -1441,7 +1470,14 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
     const int rc = make_tma_out(&to, p.out, p.out_rows, p.N, p.ld_out, std::is_same<T, __half>::value ? DDG_F16 : DDG_BF16);
     if (rc) return rc;
   }
-  gemm_kernel<T, EPI><<<grid, NUM_THREADS, smem_bytes<EPI>(), s>>>(ta, tb, to, p);
+  CUtensorMap to2 = ta;                 // fused LayerNorm: the normalised 16-bit rows
+  if constexpr (EPI == EPI_GATE_RESIDUAL_LN) {
+    int rc = make_tma_out(&to, p.out, p.M, p.N, p.ld_out, DDG_F32);
+    if (rc) return rc;
+    rc = make_tma_out(&to2, p.ln_out, p.M, p.N, p.N, p.ln_dtype);
+    if (rc) return rc;
+  }
+  gemm_kernel<T, EPI><<<grid, NUM_THREADS, smem_bytes<EPI>(), s>>>(ta, tb, to, to2, p);
   return check_cuda(cudaGetLastError(), "gemm launch");
 }
 
