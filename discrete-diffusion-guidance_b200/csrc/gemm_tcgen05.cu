@@ -346,6 +346,12 @@ template <> __host__ __device__ constexpr uint32_t make_idesc<__nv_bfloat16>() {
 // ------------------------------------------------------------------ 16-bit helpers
 template <typename T> struct H2;
 template <> struct H2<__half> {
+  // packed product in T: the exact product of two 11-bit significands rounded once (= fp32 multiply + cvt.rn)
+  static __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+  }
   static __device__ __forceinline__ uint32_t pack(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -355,6 +361,11 @@ template <> struct H2<__half> {
   }
 };
 template <> struct H2<__nv_bfloat16> {
+  static __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+  }
   static __device__ __forceinline__ uint32_t pack(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -779,11 +790,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             st_shared_v4(bias_s + 16 * lane, __float_as_uint(b01.x), __float_as_uint(b01.y),
                          __float_as_uint(b23.x), __float_as_uint(b23.y));
           }
-          if (gate_row) {
+          if (gate_row) {   // kept 16-bit: gate * round(acc + bias) is ONE packed multiply in T (exact product,
+            // one rounding = the fp32 multiply + conversion it replaces, bit for bit)
             const uint2 raw = __ldg(reinterpret_cast<const uint2*>(gate_row + n0) + lane);
-            const float2 g01 = H2<T>::unpack(raw.x), g23 = H2<T>::unpack(raw.y);
-            st_shared_v4(gate_s + 16 * lane, __float_as_uint(g01.x), __float_as_uint(g01.y),
-                         __float_as_uint(g23.x), __float_as_uint(g23.y));
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(gate_s + 8 * lane), "r"(raw.x), "r"(raw.y) : "memory");
           }
           {
             const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.ln_w + n0) + lane);
@@ -826,36 +836,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 v[2 * i + 1] = add2(v[2 * i + 1], make_float2(__uint_as_float(b.z), __uint_as_float(b.w)));
               }
             }
+            uint32_t dw[16];                   // round(acc + bias), packed
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = H2<T>::unpack(H2<T>::pack(v[i].x, v[i].y));
+            for (int i = 0; i < 16; ++i) dw[i] = H2<T>::pack(v[i].x, v[i].y);
             if (gate_row) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const uint4 b = ld_shared_v4(gate_s + (uint32_t)(g * 128 + 16 * i));
-                v[2 * i] = mul2(v[2 * i], make_float2(__uint_as_float(b.x), __uint_as_float(b.y)));
-                v[2 * i + 1] = mul2(v[2 * i + 1], make_float2(__uint_as_float(b.z), __uint_as_float(b.w)));
+              for (int i = 0; i < 4; ++i) {
+                const uint4 b = ld_shared_v4(gate_s + (uint32_t)(g * 64 + 16 * i));
+                dw[4 * i] = H2<T>::mul(dw[4 * i], b.x);
+                dw[4 * i + 1] = H2<T>::mul(dw[4 * i + 1], b.y);
+                dw[4 * i + 2] = H2<T>::mul(dw[4 * i + 2], b.z);
+                dw[4 * i + 3] = H2<T>::mul(dw[4 * i + 3], b.w);
               }
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = H2<T>::unpack(H2<T>::pack(v[i].x, v[i].y));
             }
-            // thread = row: x_new = x + delta
+            // thread = row: x_new = x + delta (packed f32x2), then the shifted sums of this chunk
             float xr[32];
+            float2 s1p = make_float2(0.f, 0.f), s2p = make_float2(0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const uint4 u = ld_shared_v4(xs_row + q * 16);
-              xr[4 * q] = __uint_as_float(u.x) + v[2 * q].x;
-              xr[4 * q + 1] = __uint_as_float(u.y) + v[2 * q].y;
-              xr[4 * q + 2] = __uint_as_float(u.z) + v[2 * q + 1].x;
-              xr[4 * q + 3] = __uint_as_float(u.w) + v[2 * q + 1].y;
+              const float2 a0 = add2(make_float2(__uint_as_float(u.x), __uint_as_float(u.y)), H2<T>::unpack(dw[2 * q]));
+              const float2 a1 = add2(make_float2(__uint_as_float(u.z), __uint_as_float(u.w)), H2<T>::unpack(dw[2 * q + 1]));
+              xr[4 * q] = a0.x; xr[4 * q + 1] = a0.y; xr[4 * q + 2] = a1.x; xr[4 * q + 3] = a1.y;
             }
             __syncwarp();                      // slab free for the next chunk
             if (g == 0) c0 = xr[0];
+            const float2 c02 = make_float2(c0, c0);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const float d = xr[k] - c0;
-              s1 += d;
-              s2 = fmaf(d, d, s2);
+            for (int k = 0; k < 16; ++k) {
+              const float2 d = sub2(make_float2(xr[2 * k], xr[2 * k + 1]), c02);
+              s1p = add2(s1p, d);
+              s2p = fma2(d, d, s2p);
             }
+            s1 += s1p.x + s1p.y;
+            s2 += s2p.x + s2p.y;
             tmem_st32(taddr + (uint32_t)(g * 32), xr);
           }
           tmem_st_wait();
